@@ -1,0 +1,171 @@
+/*
+ * s2f.h -- C ABI of libs2f.so, the sm_100a kernels of the Spike2Former spiking hot path.
+ *
+ * Every entry point takes raw device pointers, plain sizes and a cudaStream_t (as void*),
+ * returns 0 on success and a non-zero code on failure (message via s2f_last_error()).
+ * Nothing allocates, nothing synchronises with the host: every call is CUDA-graph capturable.
+ * There is no CPU implementation behind any of these symbols.
+ *
+ * Layouts: activations are channels-last.  "spikes" are int8 levels 0..D (the reference's
+ * float spike value is level/norm); real tensors are fp32.  n = T*B images.
+ *
+ * Each function cites the reference code it replaces (paths relative to
+ * /root/reference/Segmentation).
+ */
+#ifndef S2F_H_
+#define S2F_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define S2F_API __attribute__((visibility("default")))
+#else
+#define S2F_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2F_OK 0
+#define S2F_ERR_ARG 1
+#define S2F_ERR_CUDA 2
+#define S2F_ERR_UNSUPPORTED 3
+
+/* Thread-local description of the last failure. */
+S2F_API const char* s2f_last_error(void);
+/* ABI version of the library (bumped when a signature changes). */
+S2F_API int s2f_abi_version(void);
+/* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
+S2F_API uint64_t s2f_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a) NI-LIF neuron.  Replaces Q_IFNode.forward / BaseNode.forward + quant.forward:
+ *     Qtrick_architecture/clock_driven/neuron.py:459-460,115-131,133-153,166-197 and
+ *     surrogate.py:522-529.
+ *   for t in [0,T): u = x[t,i]*scale[c] + shift[c] + residual[t,i]   (each term optional, c = i % C)
+ *                   v += u ; s = rint(clamp(v, 0, d_max)) ; v -= s
+ *   levels[t,i] = s (int8)   ;  y_norm[t,i] = s / norm (fp32, optional)
+ *   v starts at v_in[i] (or 0) and is kept in a register across the T loop; v_out optional.
+ *   residual_period: the residual index is (t*N + i) % residual_period (0 = no wrap), which lets a
+ *   [N_tokens, C] positional table be broadcast over the batch.
+ *   transpose_rows/cols: when both > 0 the output of element f (within an image of rows*cols
+ *   elements) is written at (f % rows) * cols + f / rows, i.e. the [cols, rows] matrix read in the
+ *   reference's reinterpreting reshape (mmcv_spike/transformer.py:777) is stored transposed.
+ *   ties (optional, device uint64): incremented by the number of exact .5 ties inside (0, d_max).
+ */
+S2F_API int s2f_nilif_fwd(const float* x, const float* scale, const float* shift, const float* residual,
+                  int64_t residual_period, const float* v_in, float* v_out, int8_t* levels, float* y_norm,
+                  int T, int64_t N, int C, float d_max, float norm, int transpose_rows, int transpose_cols,
+                  unsigned long long* ties, void* stream);
+
+/* Surrogate-gradient backward of the neuron for T=1, v0=0 (quant.backward, surrogate.py:531-538,
+ * then the /norm of neuron.py:197):  gx = gy / norm * 1[0 <= u <= d_max],  u as above. */
+S2F_API int s2f_nilif_bwd(const float* x, const float* scale, const float* shift, const float* residual,
+                  const float* gy, float* gx, int64_t N, int C, float d_max, float norm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (b) Convolution / linear layers with a spike (or real) activation operand and the folded
+ *     BatchNorm affine + optional residual + optional NI-LIF in the epilogue.
+ *     Replaces nn.Conv2d/Conv1d/Linear + BatchNorm (+ Q_IFNode) chains, e.g. sdtv2.py:207-219
+ *     (MS_ConvBlock), :242-255 (MS_MLP), :412-421 (MS_DownSampling), SNN_core.py:47-63, pixel_decoder.py:451-470.
+ *
+ *   A: activations [n, H, W, Cin] channels-last; a_is_spike: int8 levels (value = level * a_scale)
+ *      else fp32.  W: fp32 [Cout, KH, KW, Cin] with each row zero-padded to a multiple of 4 floats
+ *      (row stride = (KH*KW*Cin + 3)/4*4), 16-byte aligned.  Output pixel grid Ho x Wo from stride/pad.
+ *   acc = sum A*W ;  y = acc * scale[co] + shift[co] + residual[n,ho,wo,co]   (residual optional)
+ *   out_f32 (optional): y.   out_spike (optional): rint(clamp(y,0,d_max)) as int8.
+ *   out_transposed: outputs are written channel-major per image ([n, Cout, Ho*Wo]) -- the layout the
+ *   reference then reinterprets (dcnv3.py:214-215, mmcv_spike/transformer.py:781,829).
+ *   Generic A strides: a_stride_m / a_stride_k (in elements) are used when KH=KW=1 and they are
+ *   non-zero: A[m,k] = base + img*a_img_stride + m*a_stride_m + k*a_stride_k (covers transposed operands).
+ */
+typedef struct {
+  const void* a; int a_is_spike; float a_scale;
+  const float* w; const float* scale; const float* shift; const float* residual;
+  float* out_f32; int8_t* out_spike; int out_transposed;
+  int n, H, W, Cin, Cout, KH, KW, stride, pad;
+  int64_t a_img_stride, a_stride_m, a_stride_k;
+  int64_t w_img_stride;          /* != 0: a different weight matrix per image (batched matmul) */
+  float d_max;
+} s2f_conv_args;
+
+S2F_API int s2f_conv_simt(const s2f_conv_args* args, void* stream);
+
+/* tcgen05 / TMEM / TMA spike GEMM (sm_100a): A int8 levels [n,H,W,Cin]; W pre-packed by
+ * s2f_pack_weights_i8 into `pieces` int8 digit planes with a per-output-channel scale (exact int32
+ * accumulation); same epilogue as s2f_conv_simt.  KH=KW in {1,3}, stride in {1,2}. */
+typedef struct {
+  const int8_t* a; const int8_t* w_packed; const float* w_rowscale;
+  const float* scale; const float* shift; const float* residual;
+  float* out_f32; int8_t* out_spike; int out_transposed;
+  int n, H, W, Cin, Cout, KH, KW, stride, pad, pieces;
+  float a_scale, d_max;
+} s2f_gemm_tc_args;
+
+S2F_API int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream);
+
+/* Host-side helper (no GPU work): split fp32 weights [Cout, K] into `pieces` signed base-128 digit
+ * planes laid out [tile][piece][row][K] for the kernel; writes rowscale[Cout].  Returns bytes needed
+ * when w_packed == NULL. */
+S2F_API int64_t s2f_pack_weights_i8(const float* w, int Cout, int K, int pieces, int8_t* w_packed, float* w_rowscale);
+
+/* Depthwise k x k convolution (k in {3,5,7}), pad (k-1)/2, stride 1, channels-last, with the same
+ * affine / NI-LIF epilogue.  Replaces the depthwise nn.Conv2d of sdtv2.py:154-162, SNN_core.py:36-40,
+ * dcnv3.py:150-158, pixel_decoder.py:373-378.  w: fp32 tap-major [k*k, C] (the reference's
+ * [C,1,k,k] transposed by the host).  no_pad: 'valid' convolution (output shrinks by k-1).
+ * pad_value is reserved and must be NULL: the BNAndPadLayer border of sdtv2.py:48-89 never reaches
+ * the device because RepConv is re-parameterised into one dense 3x3 convolution on the host.  */
+S2F_API int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const float* w, const float* scale, const float* shift,
+               const float* pad_value, float* out_f32, int8_t* out_spike, int n, int H, int W, int C, int k,
+               int no_pad, float d_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spike-driven (linear) attention.  q,k,v: int8 levels [n, Ntok, heads*d] (value = level/norm).
+ *   kv[h] = K_h^T V_h (exact integers) ; out = (Q_h kv[h]) * out_scale ; spikes = NI-LIF(out).
+ * With out_scale = d^-0.5 / norm^3 this is MS_Attention_RepConv_qkv_id (sdtv2.py:335-336); with
+ * 1/(sqrt(C) * norm^3) it is {Cross,}MultiHeadAttentionBlock without mask, where
+ * (Q K^T / sqrt(C)) V == Q (K^T V) / sqrt(C) (mmcv_spike/transformer.py:262-270, 345-353).
+ * q has Nq tokens, k/v have Nk tokens.  kv_ws: int32 workspace [n, heads, d, d].
+ * out_f32 (optional) receives the pre-activation.
+ * q_ld / kv_ld: elements between consecutive token rows of q and of k,v (>= heads*d), so the three
+ * operands may be column slices of one fused [n, N, 3C] projection output. */
+S2F_API int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v, int32_t* kv_ws, int8_t* out_spike,
+                    float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld, float out_scale,
+                    float d_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (c) DCNv3 sampling core.  Replaces dcnv3_core_pytorch (ops_dcnv3/functions/dcnv3_func.py:147-189,
+ * F.grid_sample bilinear / zeros / align_corners=False on the 1-pixel zero-padded map).
+ *   x [n,H,W,G*Cg] fp32; offset [n,H,W,G*K*K*2] fp32 (x,y interleaved); mask int8 levels [n,H,W,G*K*K]
+ *   (value = level*mask_scale); out [n,H,W,G*Cg] fp32.  stride 1, dilation 1, pad = (K-1)/2. */
+S2F_API int s2f_dcnv3_gather(const float* x, const float* offset, const int8_t* mask, float mask_scale, float* out, int n,
+                     int H, int W, int G, int Cg, int K, float offset_scale, void* stream);
+
+/* Top-down FPN merge: spikes = NI-LIF(cur + bilinear_up(prev)), align_corners=False
+ * (pixel_decoder.py:455-462).  cur [n,H,W,C], prev [n,Hp,Wp,C] fp32. */
+S2F_API int s2f_upsample_add_lif(const float* cur, const float* prev, int8_t* out_spike, float* out_f32, int n, int H, int W,
+                         int Hp, int Wp, int C, float d_max, void* stream);
+
+/* Element-wise residual merge in the layout the reference reinterprets (mmcv_spike/transformer.py:781,829;
+ * detr_layers.py:337-338, 553-555):  y[i] = x[i]*scale[i % C] + residual[i]  (scale optional);
+ * out_f32 = y, out_spike = NI-LIF(y) (either optional).  N % 4 == 0, C % 4 == 0. */
+S2F_API int s2f_affine_add_lif(const float* x, const float* scale, const float* residual, float* out_f32,
+                       int8_t* out_spike, int64_t N, int C, float d_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Head tail.  sigmoid -> NI-LIF of the stacked decoder states (maskformer_head.py:572-573):
+ *   levels = rint(clamp(sigmoid(x), 0, d_max)). */
+S2F_API int s2f_sigmoid_lif(const float* x, int8_t* levels, int64_t N, float d_max, void* stream);
+
+/* Semantic inference (decode_heads/maskformer_head.py:163-177):
+ *   up = bilinear(mask_pred [n,Q,h,w] -> [H,W], align_corners=False); prob = softmax(cls)[..., :-1]
+ *   logits[n,c,H,W] = sum_q prob[n,q,c] * sigmoid(up[n,q,H,W]).
+ * mask_pred is given pixel-major [n, h*w, Q] (as the mask GEMM writes it); cls [n,Q,K+1]. */
+S2F_API int s2f_semantic_tail(const float* mask_pred, const float* cls, float* logits, float* prob_ws, int n, int Q, int K,
+                      int h, int w, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2F_H_ */

@@ -1,0 +1,214 @@
+// Spike-driven linear attention and the head's tail kernels.
+#include "common.cuh"
+
+namespace s2f {
+
+// ------------------------------------------------------------------------------------------------
+// kv[img, h, i, j] = sum_tok K[img, tok, h*d+i] * V[img, tok, h*d+j]      (exact int32)
+// grid (n*heads, splits); each block reduces a token slice and atomically adds its d x d partial.
+constexpr int KV_TOK = 64;   // tokens staged per smem tile
+
+__global__ void __launch_bounds__(256) kv_kernel(const int8_t* __restrict__ k, const int8_t* __restrict__ v,
+                                                 int32_t* __restrict__ kv, int Nk, int heads, int d, int ld, int tok_per_block) {
+  extern __shared__ int8_t smem[];
+  int8_t* ks = smem;                     // [KV_TOK][d]
+  int8_t* vs = smem + KV_TOK * d;        // [KV_TOK][d]
+  const int img = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int C = ld;
+  const int t_begin = blockIdx.y * tok_per_block;
+  const int t_end = min(Nk, t_begin + tok_per_block);
+  const int dd = d * d;
+  // each thread owns up to 16 (i,j) pairs: pair p = tid + r*256
+  int acc[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r] = 0;
+  const int8_t* kb = k + ((int64_t)img * Nk) * C + h * d;
+  const int8_t* vb = v + ((int64_t)img * Nk) * C + h * d;
+  for (int t0 = t_begin; t0 < t_end; t0 += KV_TOK) {
+    const int nt = min(KV_TOK, t_end - t0);
+    for (int e = threadIdx.x; e < nt * d; e += blockDim.x) {
+      const int tt = e / d, c = e % d;
+      ks[e] = kb[(int64_t)(t0 + tt) * C + c];
+      vs[e] = vb[(int64_t)(t0 + tt) * C + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int p = threadIdx.x + r * 256;
+      if (p < dd) {
+        const int i = p / d, j = p % d;
+        int s = 0;
+        for (int tt = 0; tt < nt; ++tt) s += (int)ks[tt * d + i] * (int)vs[tt * d + j];
+        acc[r] += s;
+      }
+    }
+    __syncthreads();
+  }
+  int32_t* out = kv + ((int64_t)img * heads + h) * dd;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int p = threadIdx.x + r * 256;
+    if (p < dd && acc[r] != 0) atomicAdd(out + p, acc[r]);
+  }
+}
+
+// out[img, tok, h*d+j] = (sum_i Q[img,tok,h*d+i] * kv[img,h,i,j]) * out_scale -> NI-LIF
+// block = (img, 32-token tile); kv of all heads is staged in smem.
+__global__ void __launch_bounds__(256) qkv_kernel(const int8_t* __restrict__ q, const int32_t* __restrict__ kv,
+                                                  int8_t* __restrict__ out_spike, float* __restrict__ out_f32, int Nq,
+                                                  int heads, int d, int q_ld, float out_scale, float d_max) {
+  extern __shared__ int32_t kvs[];       // [heads][d][d]
+  const int img = blockIdx.y;
+  const int C = heads * d;
+  const int tok0 = blockIdx.x * 32;
+  const int32_t* kvb = kv + (int64_t)img * heads * d * d;
+  for (int e = threadIdx.x; e < heads * d * d; e += blockDim.x) kvs[e] = kvb[e];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * C; e += blockDim.x) {
+    const int tt = e / C, c = e % C;
+    const int tok = tok0 + tt;
+    if (tok >= Nq) continue;
+    const int h = c / d, j = c % d;
+    const int8_t* qrow = q + ((int64_t)img * Nq + tok) * q_ld + h * d;
+    const int32_t* kvh = kvs + h * d * d + j;
+    long long s = 0;
+    for (int i = 0; i < d; ++i) s += (long long)qrow[i] * (long long)kvh[i * d];
+    const float y = (float)s * out_scale;
+    const int64_t o = ((int64_t)img * Nq + tok) * C + c;
+    if (out_f32) out_f32[o] = y;
+    if (out_spike) out_spike[o] = (int8_t)(int)spike_level(y, d_max);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sigmoid_lif_kernel(const float* __restrict__ x, int8_t* __restrict__ levels,
+                                                          int64_t N, float d_max) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    // sigmoid(x) in (0,1): the level is 1 iff the fp32 sigmoid exceeds 0.5 (sigmoid(0) = 0.5 ties to 0)
+    const float s = 1.f / (1.f + expf(-x[i]));
+    levels[i] = (int8_t)(int)spike_level(s, d_max);
+  }
+}
+
+// softmax over K+1 classes, drop the last ("no object") column: prob [n*Q, K]
+__global__ void __launch_bounds__(128) softmax_drop_kernel(const float* __restrict__ cls, float* __restrict__ prob,
+                                                           int rows, int K1) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const float* c = cls + (int64_t)row * K1;
+  __shared__ float red[128];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < K1; i += blockDim.x) mx = fmaxf(mx, c[i]);
+  red[threadIdx.x] = mx; __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+  mx = red[0]; __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < K1; i += blockDim.x) sum += expf(c[i] - mx);
+  red[threadIdx.x] = sum; __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+  sum = red[0];
+  for (int i = threadIdx.x; i < K1 - 1; i += blockDim.x) prob[(int64_t)row * (K1 - 1) + i] = expf(c[i] - mx) / sum;
+}
+
+// logits[n, c, Y, X] = sum_q prob[n,q,c] * sigmoid(bilinear(mask_pred[n, :, :, q])(Y, X))
+// block = 64 consecutive output pixels of one row segment; stage sigmoid(up) [64][Q] and prob [Q][K] in smem.
+constexpr int TAIL_PIX = 64;
+__global__ void __launch_bounds__(256) semantic_tail_kernel(const float* __restrict__ mask_pred,
+                                                            const float* __restrict__ prob, float* __restrict__ logits,
+                                                            int Q, int K, int h, int w, int H, int W) {
+  extern __shared__ float sm[];
+  float* S = sm;                          // [Q][TAIL_PIX + 1]
+  float* Pm = sm + Q * (TAIL_PIX + 1);    // [Q][K]
+  const int img = blockIdx.y;
+  const int64_t pix0 = (int64_t)blockIdx.x * TAIL_PIX;
+  const int64_t HW = (int64_t)H * W;
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const float* mp = mask_pred + (int64_t)img * h * w * Q;
+  for (int e = threadIdx.x; e < Q * K; e += blockDim.x) Pm[e] = prob[(int64_t)img * Q * K + e];
+  for (int e = threadIdx.x; e < TAIL_PIX * Q; e += blockDim.x) {
+    const int pp = e / Q, q = e % Q;
+    const int64_t pix = pix0 + pp;
+    float val = 0.f;
+    if (pix < HW) {
+      const int Y = (int)(pix / W), X = (int)(pix % W);
+      float sy = sh * ((float)Y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+      float sx = sw * ((float)X + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+      const float p00 = mp[((int64_t)y0 * w + x0) * Q + q], p01 = mp[((int64_t)y0 * w + x1) * Q + q];
+      const float p10 = mp[((int64_t)y1 * w + x0) * Q + q], p11 = mp[((int64_t)y1 * w + x1) * Q + q];
+      const float up = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+      val = 1.f / (1.f + expf(-up));
+    }
+    S[q * (TAIL_PIX + 1) + pp] = val;
+  }
+  __syncthreads();
+  // thread -> pixel (fastest) x class strided
+  const int pp = threadIdx.x % TAIL_PIX;
+  const int cg = threadIdx.x / TAIL_PIX;          // 0..3
+  const int64_t pix = pix0 + pp;
+  if (pix >= HW) return;
+  for (int c = cg; c < K; c += 256 / TAIL_PIX) {
+    float acc = 0.f;
+    for (int q = 0; q < Q; ++q) acc = fmaf(Pm[q * K + c], S[q * (TAIL_PIX + 1) + pp], acc);
+    logits[((int64_t)img * K + c) * HW + pix] = acc;
+  }
+}
+
+}  // namespace s2f
+
+using namespace s2f;
+
+extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v, int32_t* kv_ws, int8_t* out_spike,
+                               float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld,
+                               float out_scale, float d_max, void* stream) {
+  S2F_REQUIRE(q && k && v && kv_ws && (out_spike || out_f32), "linear_attn: null pointer");
+  S2F_REQUIRE(d >= 1 && d <= 64 && heads >= 1, "linear_attn: head dim must be <= 64");
+  S2F_REQUIRE(q_ld >= heads * d && kv_ld >= heads * d, "linear_attn: row strides smaller than heads*d");
+  S2F_REQUIRE((int64_t)64 * Nk < (1ll << 31), "linear_attn: Nk too large for int32 K^T V");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dd = d * d;
+  cudaError_t e = cudaMemsetAsync(kv_ws, 0, sizeof(int32_t) * (size_t)n * heads * dd, st);
+  if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "linear_attn memset: %s", cudaGetErrorString(e));
+  // enough token slices to fill the GPU, at least 256 tokens each
+  int splits = (int)ceil_div(148 * 4, (int64_t)n * heads);
+  const int max_splits = (int)ceil_div(Nk, 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int tok_per_block = (int)ceil_div(ceil_div(Nk, splits), KV_TOK) * KV_TOK;
+  splits = (int)ceil_div(Nk, tok_per_block);
+  kv_kernel<<<dim3(n * heads, splits), 256, 2 * KV_TOK * d, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
+  int rc = check_launch("kv_kernel");
+  if (rc) return rc;
+  const size_t sm = sizeof(int32_t) * (size_t)heads * dd;
+  S2F_REQUIRE(sm <= 200 * 1024, "linear_attn: heads*d*d too large for shared memory");
+  if (sm > 48 * 1024) cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  qkv_kernel<<<dim3((unsigned)ceil_div(Nq, 32), n), 256, sm, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld,
+                                                                   out_scale, d_max);
+  return check_launch("qkv_kernel");
+}
+
+extern "C" int s2f_sigmoid_lif(const float* x, int8_t* levels, int64_t N, float d_max, void* stream) {
+  S2F_REQUIRE(x && levels, "sigmoid_lif: null pointer");
+  if (N == 0) return S2F_OK;
+  const int64_t want = ceil_div(N, 256);
+  sigmoid_lif_kernel<<<(int)(want < 2368 ? want : 2368), 256, 0, (cudaStream_t)stream>>>(x, levels, N, d_max);
+  return check_launch("sigmoid_lif_kernel");
+}
+
+extern "C" int s2f_semantic_tail(const float* mask_pred, const float* cls, float* logits, float* prob_ws, int n, int Q,
+                                 int K, int h, int w, int H, int W, void* stream) {
+  S2F_REQUIRE(mask_pred && cls && logits && prob_ws, "semantic_tail: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  softmax_drop_kernel<<<n * Q, 128, 0, st>>>(cls, prob_ws, n * Q, K + 1);
+  int rc = check_launch("softmax_drop_kernel");
+  if (rc) return rc;
+  const size_t sm = sizeof(float) * ((size_t)Q * (TAIL_PIX + 1) + (size_t)Q * K);
+  S2F_REQUIRE(sm <= 200 * 1024, "semantic_tail: Q*K too large for shared memory");
+  if (sm > 48 * 1024) cudaFuncSetAttribute(semantic_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  const int64_t HW = (int64_t)H * W;
+  semantic_tail_kernel<<<dim3((unsigned)ceil_div(HW, TAIL_PIX), n), 256, sm, st>>>(mask_pred, prob_ws, logits, Q, K, h, w,
+                                                                                   H, W);
+  return check_launch("semantic_tail_kernel");
+}

@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# Build libs2f.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+out="$here/../libs2f.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC 
+       --expt-relaxed-constexpr -Xptxas -v)
+objs=()
+mkdir -p "$here/build"
+for src in "$here"/*.cu; do
+  obj="$here/build/$(basename "${src%.cu}").o"
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$here/common.cuh" -nt "$obj" || "$here/../../include/s2f.h" -nt "$obj" ]]; then
+    "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" 2> "$obj.log" || { cat "$obj.log"; exit 1; }
+  fi
+  objs+=("$obj")
+done
+"$NVCC" -shared -o "$out" "${objs[@]}" -lcudart_static -ldl -lpthread -lrt
+echo "built $out"

@@ -1,0 +1,44 @@
+// Shared helpers for libs2f.so (sm_100a).  No torch headers: the library is a plain C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/s2f.h"
+
+namespace s2f {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return S2F_ERR_CUDA;
+  }
+  return S2F_OK;
+}
+
+#define S2F_REQUIRE(cond, msg)                                          \
+  do {                                                                  \
+    if (!(cond)) return s2f::fail(S2F_ERR_ARG, "%s (%s)", msg, 0, 0);   \
+  } while (0)
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// round-half-to-even of clamp(v, 0, d): torch.round(torch.clamp(v, 0, d)) -- surrogate.py:529
+__device__ __forceinline__ float spike_level(float v, float d_max) { return rintf(fminf(fmaxf(v, 0.f), d_max)); }
+
+__device__ __forceinline__ bool is_tie(float v, float d_max) {
+  return (v > 0.f) && (v < d_max) && ((v - floorf(v)) == 0.5f);
+}
+
+}  // namespace s2f

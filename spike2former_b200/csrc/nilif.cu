@@ -1,0 +1,256 @@
+// Fused normalised-integer LIF neuron (kernel (a) of the north star).
+//
+// Reference arithmetic (Qtrick_architecture/clock_driven/neuron.py:459-460,115-153,166-197;
+// surrogate.py:522-529):   v = v + x ;  s = round(clamp(v, 0, D)) ;  v = v - s ;  return s / norm
+//
+// One launch does, per neuron, all T steps with the membrane in a register, folds the preceding
+// per-channel affine (BatchNorm) and an optional residual, reads fp32 with 128-bit loads and
+// writes int8 levels with 128-bit stores (16 neurons per thread).  HBM-bound: 4 B in + 1 B out
+// per neuron-step (+4 B when a residual is read).
+#include "common.cuh"
+
+namespace s2f {
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void stg_stream(int4* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w));
+}
+
+__device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d) {
+  return (uint32_t)(int)a | ((uint32_t)(int)b << 8) | ((uint32_t)(int)c << 16) | ((uint32_t)(int)d << 24);
+}
+
+// Vector kernel: N % 16 == 0, C % 4 == 0 (when affine), residual_period % 4 == 0.
+// Each thread owns 16 consecutive neurons: 4 x LDG.128 per step, 1 x STG.128 per step.
+template <bool AFFINE, bool RESID, bool STATE, bool YNORM, bool TIES>
+__global__ void __launch_bounds__(256) nilif_vec_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift,
+                                                        const float* __restrict__ residual, int64_t res_period,
+                                                        const float* __restrict__ v_in, float* __restrict__ v_out,
+                                                        int8_t* __restrict__ levels, float* __restrict__ y_norm,
+                                                        int T, int64_t N, int C, float d_max, float inv_norm,
+                                                        unsigned long long* __restrict__ ties) {
+  const int64_t nchunks = N >> 4;
+  unsigned int my_ties = 0;
+  for (int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; chunk < nchunks;
+       chunk += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = chunk << 4;
+    float v[16];
+    if (STATE && v_in != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(v_in + i0 + 4 * j);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+    float sc[16], sh[16];
+    if (AFFINE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (int)((i0 + 4 * j) % C);
+        float4 a = __ldg(reinterpret_cast<const float4*>(scale + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(shift + c));
+        sc[4 * j] = a.x; sc[4 * j + 1] = a.y; sc[4 * j + 2] = a.z; sc[4 * j + 3] = a.w;
+        sh[4 * j] = b.x; sh[4 * j + 1] = b.y; sh[4 * j + 2] = b.z; sh[4 * j + 3] = b.w;
+      }
+    }
+    for (int t = 0; t < T; ++t) {
+      const int64_t base = (int64_t)t * N + i0;
+      float u[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 q = ldg_stream(reinterpret_cast<const float4*>(x + base) + j);
+        u[4 * j] = q.x; u[4 * j + 1] = q.y; u[4 * j + 2] = q.z; u[4 * j + 3] = q.w;
+      }
+      if (AFFINE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) u[j] = __fadd_rn(__fmul_rn(u[j], sc[j]), sh[j]);
+      }
+      if (RESID) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int64_t r = base + 4 * j;
+          if (res_period > 0) r %= res_period;
+          float4 q = __ldg(reinterpret_cast<const float4*>(residual + r));
+          u[4 * j] += q.x; u[4 * j + 1] += q.y; u[4 * j + 2] += q.z; u[4 * j + 3] += q.w;
+        }
+      }
+      float s[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] += u[j];
+        if (TIES) my_ties += is_tie(v[j], d_max) ? 1u : 0u;
+        s[j] = spike_level(v[j], d_max);
+        v[j] -= s[j];
+      }
+      int4 o;
+      o.x = (int)pack4(s[0], s[1], s[2], s[3]);
+      o.y = (int)pack4(s[4], s[5], s[6], s[7]);
+      o.z = (int)pack4(s[8], s[9], s[10], s[11]);
+      o.w = (int)pack4(s[12], s[13], s[14], s[15]);
+      stg_stream(reinterpret_cast<int4*>(levels + base), o);
+      if (YNORM) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(y_norm + base + 4 * j) =
+              make_float4(s[4 * j] * inv_norm, s[4 * j + 1] * inv_norm, s[4 * j + 2] * inv_norm, s[4 * j + 3] * inv_norm);
+      }
+    }
+    if (STATE && v_out != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(v_out + i0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  if (TIES) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
+    if ((threadIdx.x & 31) == 0 && my_ties) atomicAdd(ties, (unsigned long long)my_ties);
+  }
+}
+
+// Scalar kernel: any N / C / period, optional transposed store.  Used for ragged shapes only.
+__global__ void __launch_bounds__(256) nilif_scalar_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ residual, int64_t res_period,
+                                                           const float* __restrict__ v_in, float* __restrict__ v_out,
+                                                           int8_t* __restrict__ levels, float* __restrict__ y_norm,
+                                                           int T, int64_t N, int C, float d_max, float inv_norm,
+                                                           int tr_rows, int tr_cols,
+                                                           unsigned long long* __restrict__ ties) {
+  unsigned int my_ties = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = v_in ? v_in[i] : 0.f;
+    const int c = (int)(i % C);
+    const float sc = scale ? scale[c] : 1.f, sh = scale ? shift[c] : 0.f;
+    int64_t o = i;
+    if (tr_rows > 0) {
+      const int64_t per = (int64_t)tr_rows * tr_cols;
+      const int64_t img = i / per, f = i % per;
+      o = img * per + (f % tr_rows) * tr_cols + f / tr_rows;
+    }
+    for (int t = 0; t < T; ++t) {
+      const int64_t idx = (int64_t)t * N + i;
+      float u = x[idx];
+      if (scale) u = __fadd_rn(__fmul_rn(u, sc), sh);
+      if (residual) u += residual[res_period > 0 ? idx % res_period : idx];
+      v += u;
+      if (ties) my_ties += is_tie(v, d_max) ? 1u : 0u;
+      const float s = spike_level(v, d_max);
+      v -= s;
+      levels[(int64_t)t * N + o] = (int8_t)(int)s;
+      if (y_norm) y_norm[(int64_t)t * N + o] = s * inv_norm;
+    }
+    if (v_out) v_out[i] = v;
+  }
+  if (ties) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
+    if ((threadIdx.x & 31) == 0 && my_ties) atomicAdd(ties, (unsigned long long)my_ties);
+  }
+}
+
+__global__ void __launch_bounds__(256) nilif_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift,
+                                                        const float* __restrict__ residual,
+                                                        const float* __restrict__ gy, float* __restrict__ gx, int64_t N,
+                                                        int C, float d_max, float inv_norm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float u = x[i];
+    if (scale) { const int c = (int)(i % C); u = __fadd_rn(__fmul_rn(u, scale[c]), shift[c]); }
+    if (residual) u += residual[i];
+    // quant.backward zeroes the gradient where the input is outside [min, max] (surrogate.py:531-538)
+    const float pass = (u < 0.f || u > d_max) ? 0.f : 1.f;
+    gx[i] = gy[i] * inv_norm * pass;
+  }
+}
+
+template <bool A, bool R, bool S, bool Y>
+static void launch_vec(bool ties_on, dim3 g, dim3 b, cudaStream_t st, const float* x, const float* scale,
+                       const float* shift, const float* residual, int64_t rp, const float* v_in, float* v_out,
+                       int8_t* levels, float* y_norm, int T, int64_t N, int C, float d_max, float inv_norm,
+                       unsigned long long* ties) {
+  if (ties_on)
+    nilif_vec_kernel<A, R, S, Y, true><<<g, b, 0, st>>>(x, scale, shift, residual, rp, v_in, v_out, levels, y_norm, T, N,
+                                                        C, d_max, inv_norm, ties);
+  else
+    nilif_vec_kernel<A, R, S, Y, false><<<g, b, 0, st>>>(x, scale, shift, residual, rp, v_in, v_out, levels, y_norm, T,
+                                                         N, C, d_max, inv_norm, ties);
+}
+
+}  // namespace s2f
+
+using namespace s2f;
+
+extern "C" int s2f_nilif_fwd(const float* x, const float* scale, const float* shift, const float* residual,
+                             int64_t residual_period, const float* v_in, float* v_out, int8_t* levels, float* y_norm,
+                             int T, int64_t N, int C, float d_max, float norm, int transpose_rows, int transpose_cols,
+                             unsigned long long* ties, void* stream) {
+  S2F_REQUIRE(x && levels, "nilif_fwd: x and levels are required");
+  S2F_REQUIRE(T >= 1 && N >= 0 && C >= 1, "nilif_fwd: bad T/N/C");
+  S2F_REQUIRE((scale == nullptr) == (shift == nullptr), "nilif_fwd: scale and shift come together");
+  S2F_REQUIRE(norm != 0.f && d_max > 0.f && d_max <= 127.f, "nilif_fwd: bad norm / d_max");
+  if (N == 0) return S2F_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_norm = 1.f / norm;
+  const bool transposed = transpose_rows > 0 && transpose_cols > 0;
+  if (transposed) S2F_REQUIRE(N % ((int64_t)transpose_rows * transpose_cols) == 0, "nilif_fwd: N not a multiple of rows*cols");
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool vec = !transposed && (N % 16 == 0) && aligned16(x) && aligned16(levels) && (!y_norm || aligned16(y_norm)) &&
+             (!scale || (C % 4 == 0 && aligned16(scale) && aligned16(shift))) &&
+             (!residual || (aligned16(residual) && (residual_period % 4 == 0))) && (!v_in || aligned16(v_in)) &&
+             (!v_out || aligned16(v_out));
+  const int threads = 256;
+  if (vec) {
+    const int64_t chunks = N / 16;
+    const int64_t want = ceil_div(chunks, threads);
+    const int blocks = (int)(want < 148 * 32 ? want : 148 * 32);   // grid-stride beyond 32 CTAs/SM worth of work
+    dim3 g(blocks), b(threads);
+    const bool A = scale != nullptr, R = residual != nullptr, S = (v_in != nullptr) || (v_out != nullptr),
+               Y = y_norm != nullptr, TI = ties != nullptr;
+#define S2F_DISPATCH(a, r, s, y)                                                                                    \
+  if (A == a && R == r && S == s && Y == y)                                                                         \
+    launch_vec<a, r, s, y>(TI, g, b, st, x, scale, shift, residual, residual_period, v_in, v_out, levels, y_norm, T, N, \
+                           C, d_max, inv_norm, ties);
+    S2F_DISPATCH(false, false, false, false) S2F_DISPATCH(false, false, false, true)
+    S2F_DISPATCH(false, false, true, false) S2F_DISPATCH(false, false, true, true)
+    S2F_DISPATCH(false, true, false, false) S2F_DISPATCH(false, true, false, true)
+    S2F_DISPATCH(false, true, true, false) S2F_DISPATCH(false, true, true, true)
+    S2F_DISPATCH(true, false, false, false) S2F_DISPATCH(true, false, false, true)
+    S2F_DISPATCH(true, false, true, false) S2F_DISPATCH(true, false, true, true)
+    S2F_DISPATCH(true, true, false, false) S2F_DISPATCH(true, true, false, true)
+    S2F_DISPATCH(true, true, true, false) S2F_DISPATCH(true, true, true, true)
+#undef S2F_DISPATCH
+    return check_launch("nilif_vec_kernel");
+  }
+  const int64_t want = ceil_div(N, threads);
+  const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  nilif_scalar_kernel<<<blocks, threads, 0, st>>>(x, scale, shift, residual, residual_period, v_in, v_out, levels,
+                                                  y_norm, T, N, C, d_max, inv_norm, transposed ? transpose_rows : 0,
+                                                  transposed ? transpose_cols : 0, ties);
+  return check_launch("nilif_scalar_kernel");
+}
+
+extern "C" int s2f_nilif_bwd(const float* x, const float* scale, const float* shift, const float* residual,
+                             const float* gy, float* gx, int64_t N, int C, float d_max, float norm, void* stream) {
+  S2F_REQUIRE(x && gy && gx, "nilif_bwd: x, gy, gx are required");
+  S2F_REQUIRE((scale == nullptr) == (shift == nullptr), "nilif_bwd: scale and shift come together");
+  if (N == 0) return S2F_OK;
+  const int threads = 256;
+  const int64_t want = ceil_div(N, threads);
+  const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  nilif_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(x, scale, shift, residual, gy, gx, N, C, d_max,
+                                                                 1.f / norm);
+  return check_launch("nilif_bwd_kernel");
+}

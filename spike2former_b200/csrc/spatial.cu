@@ -1,0 +1,263 @@
+// Channels-last spatial kernels: depthwise stencil, DCNv3 bilinear gather, FPN upsample-add-LIF.
+// All HBM/L2-bound; threads run over channels fastest so every warp access is a coalesced row.
+#include "common.cuh"
+
+namespace s2f {
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise k x k, stride 1, 'same' padding (or no padding when no_pad, output shrinks by k-1).
+// One thread = one output pixel x 4 channels.  Weights are given tap-major [k*k, C] so a warp reads
+// consecutive channels of one tap.  fp32 accumulate in the reference's tap order (kh, kw).
+template <typename AT, int KS>
+__global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, float a_scale,
+                                                     const float* __restrict__ w_tap, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, float* __restrict__ out_f32,
+                                                     int8_t* __restrict__ out_spike, int n, int H, int W, int C, int Ho,
+                                                     int Wo, int pad, float d_max) {
+  const int c4n = C >> 2;
+  const int64_t total = (int64_t)n * Ho * Wo * c4n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % c4n);
+    int64_t r = idx / c4n;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    const int c = c4 * 4;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const AT* base = a + (int64_t)img * H * W * C + c;
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+      const int hi = ho - pad + kh;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) {
+        const int wi = wo - pad + kw;
+        if (wi < 0 || wi >= W) continue;
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w_tap + (int64_t)(kh * KS + kw) * C + c));
+        float x0, x1, x2, x3;
+        if (sizeof(AT) == 1) {
+          const int raw = __ldg(reinterpret_cast<const int*>(reinterpret_cast<const int8_t*>(base) +
+                                                             ((int64_t)hi * W + wi) * C));
+          x0 = (float)(int8_t)(raw & 0xff); x1 = (float)(int8_t)((raw >> 8) & 0xff);
+          x2 = (float)(int8_t)((raw >> 16) & 0xff); x3 = (float)(int8_t)((raw >> 24) & 0xff);
+        } else {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) +
+                                                                  ((int64_t)hi * W + wi) * C));
+          x0 = xv.x; x1 = xv.y; x2 = xv.z; x3 = xv.w;
+        }
+        acc0 = fmaf(x0, wv.x, acc0); acc1 = fmaf(x1, wv.y, acc1);
+        acc2 = fmaf(x2, wv.z, acc2); acc3 = fmaf(x3, wv.w, acc3);
+      }
+    }
+    float y[4] = {acc0 * a_scale, acc1 * a_scale, acc2 * a_scale, acc3 * a_scale};
+    if (scale) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+      y[0] = __fadd_rn(__fmul_rn(y[0], sc.x), sh.x); y[1] = __fadd_rn(__fmul_rn(y[1], sc.y), sh.y);
+      y[2] = __fadd_rn(__fmul_rn(y[2], sc.z), sh.z); y[3] = __fadd_rn(__fmul_rn(y[3], sc.w), sh.w);
+    }
+    const int64_t o = (((int64_t)img * Ho + ho) * Wo + wo) * C + c;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_spike) {
+      const uint32_t pk = (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
+                          ((uint32_t)(int)spike_level(y[2], d_max) << 16) |
+                          ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+      *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DCNv3 core.  Follows dcnv3_core_pytorch's float op order (normalised location -> grid_sample
+// unnormalise) so sampling coordinates agree with the reference to the last bits:
+//   loc = ref + grid*os + off*os/size ; g = 2*loc - 1 ; ix = ((g + 1)*size - 1)/2   (padded image coords)
+// One thread = one (pixel, group, 4 channels).  x is read through the 1-pixel zero border analytically.
+__global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+                                                    const int8_t* __restrict__ mask, float mask_scale,
+                                                    float* __restrict__ out, int n, int H, int W, int G, int Cg, int K,
+                                                    float os) {
+  const int q4 = Cg >> 2;
+  const int C = G * Cg, P = K * K, pad = (K - 1) / 2;
+  const float Hin = (float)(H + 2 * pad), Win = (float)(W + 2 * pad);
+  const int64_t total = (int64_t)n * H * W * G * q4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % q4);
+    int64_t r = idx / q4;
+    const int g = (int)(r % G); r /= G;
+    const int wo = (int)(r % W); r /= W;
+    const int ho = (int)(r % H);
+    const int img = (int)(r / H);
+    const int64_t pix = ((int64_t)img * H + ho) * W + wo;
+    const float* off = offset + pix * (int64_t)(G * P * 2) + (int64_t)g * P * 2;
+    const int8_t* mk = mask + pix * (int64_t)(G * P) + (int64_t)g * P;
+    const float* xb = x + (int64_t)img * H * W * C + g * Cg + cq * 4;
+    const float half = (float)pad;   // dilation 1: (K-1)/2
+    const float ref_x = __fdiv_rn((float)wo + half + 0.5f, Win);
+    const float ref_y = __fdiv_rn((float)ho + half + 0.5f, Hin);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int pt = 0; pt < P; ++pt) {
+      const float m = (float)mk[pt] * mask_scale;
+      // point order of _generate_dilation_grids: x index is the slow one (dcnv3_func.py:125-137)
+      const float gx = __fdiv_rn((float)(pt / K) - half, Win);
+      const float gy = __fdiv_rn((float)(pt % K) - half, Hin);
+      const float lx = __fadd_rn(__fadd_rn(ref_x, __fmul_rn(gx, os)), __fdiv_rn(__fmul_rn(off[2 * pt], os), Win));
+      const float ly = __fadd_rn(__fadd_rn(ref_y, __fmul_rn(gy, os)), __fdiv_rn(__fmul_rn(off[2 * pt + 1], os), Hin));
+      const float sgx = __fadd_rn(__fmul_rn(2.f, lx), -1.f), sgy = __fadd_rn(__fmul_rn(2.f, ly), -1.f);
+      const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgx, 1.f), Win), -1.f), 0.5f);
+      const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgy, 1.f), Hin), -1.f), 0.5f);
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx - pad, y0 = (int)fy - pad;   // back to unpadded coordinates
+      const float tx = ix - fx, ty = iy - fy;
+      const float wnw = (1.f - tx) * (1.f - ty), wne = tx * (1.f - ty), wsw = (1.f - tx) * ty, wse = tx * ty;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      auto tap = [&](int yy, int xx, float wgt) {
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)yy * W + xx) * C));
+          s0 = fmaf(v.x, wgt, s0); s1 = fmaf(v.y, wgt, s1); s2 = fmaf(v.z, wgt, s2); s3 = fmaf(v.w, wgt, s3);
+        }
+      };
+      tap(y0, x0, wnw); tap(y0, x0 + 1, wne); tap(y0 + 1, x0, wsw); tap(y0 + 1, x0 + 1, wse);
+      a0 = fmaf(s0, m, a0); a1 = fmaf(s1, m, a1); a2 = fmaf(s2, m, a2); a3 = fmaf(s3, m, a3);
+    }
+    *reinterpret_cast<float4*>(out + pix * C + g * Cg + cq * 4) = make_float4(a0, a1, a2, a3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = cur + bilinear(prev -> HxW), align_corners=False (upsample_bilinear2d: src = (dst+0.5)*scale-0.5,
+// clamped at 0); spikes = NI-LIF(y).  One thread = one pixel x 4 channels.
+__global__ void __launch_bounds__(256) upsample_add_lif_kernel(const float* __restrict__ cur,
+                                                               const float* __restrict__ prev,
+                                                               int8_t* __restrict__ out_spike,
+                                                               float* __restrict__ out_f32, int n, int H, int W, int Hp,
+                                                               int Wp, int C, float d_max) {
+  const int c4n = C >> 2;
+  const float sh = (float)Hp / (float)H, sw = (float)Wp / (float)W;
+  const int64_t total = (int64_t)n * H * W * c4n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    int64_t r = idx / c4n;
+    const int xo = (int)(r % W); r /= W;
+    const int yo = (int)(r % H);
+    const int img = (int)(r / H);
+    float sy = sh * ((float)yo + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+    float sx = sw * ((float)xo + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < Hp - 1 ? 1 : 0), x1 = x0 + (x0 < Wp - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* pb = prev + (int64_t)img * Hp * Wp * C + c;
+    const float4 p00 = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)y0 * Wp + x0) * C));
+    const float4 p01 = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)y0 * Wp + x1) * C));
+    const float4 p10 = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)y1 * Wp + x0) * C));
+    const float4 p11 = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)y1 * Wp + x1) * C));
+    const int64_t o = (((int64_t)img * H + yo) * W + xo) * C + c;
+    const float4 cv = *reinterpret_cast<const float4*>(cur + o);
+    // ATen: hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11)
+    float y[4];
+    y[0] = cv.x + (hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x));
+    y[1] = cv.y + (hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y));
+    y[2] = cv.z + (hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z));
+    y[3] = cv.w + (hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w));
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_spike) {
+      const uint32_t pk = (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
+                          ((uint32_t)(int)spike_level(y[2], d_max) << 16) |
+                          ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+      *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) affine_add_lif_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                             const float* __restrict__ residual,
+                                                             float* __restrict__ out_f32, int8_t* __restrict__ out_spike,
+                                                             int64_t N4, int C, float d_max) {
+  for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < N4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i4 * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    if (scale) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (int)(i % C)));
+      v.x = __fmul_rn(v.x, sc.x); v.y = __fmul_rn(v.y, sc.y); v.z = __fmul_rn(v.z, sc.z); v.w = __fmul_rn(v.w, sc.w);
+    }
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + i);
+      v.x = __fadd_rn(r.x, v.x); v.y = __fadd_rn(r.y, v.y); v.z = __fadd_rn(r.z, v.z); v.w = __fadd_rn(r.w, v.w);
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + i) = v;
+    if (out_spike) {
+      const uint32_t pk = (uint32_t)(int)spike_level(v.x, d_max) | ((uint32_t)(int)spike_level(v.y, d_max) << 8) |
+                          ((uint32_t)(int)spike_level(v.z, d_max) << 16) | ((uint32_t)(int)spike_level(v.w, d_max) << 24);
+      *reinterpret_cast<uint32_t*>(out_spike + i) = pk;
+    }
+  }
+}
+
+static inline int grid_for(int64_t total, int threads) {
+  const int64_t want = ceil_div(total, threads);
+  return (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+}
+
+}  // namespace s2f
+
+using namespace s2f;
+
+extern "C" int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const float* w, const float* scale,
+                          const float* shift, const float* pad_value, float* out_f32, int8_t* out_spike, int n, int H,
+                          int W, int C, int k, int no_pad, float d_max, void* stream) {
+  S2F_REQUIRE(a && w && (out_f32 || out_spike), "dwconv: a, w and an output are required");
+  S2F_REQUIRE(pad_value == nullptr, "dwconv: pad_value is not supported (RepConv is re-parameterised on the host)");
+  S2F_REQUIRE(C % 4 == 0, "dwconv: C must be a multiple of 4");
+  S2F_REQUIRE(k == 3 || k == 5 || k == 7, "dwconv: k must be 3, 5 or 7");
+  S2F_REQUIRE((scale == nullptr) == (shift == nullptr), "dwconv: scale and shift come together");
+  const int pad = no_pad ? 0 : (k - 1) / 2;
+  const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
+  S2F_REQUIRE(Ho > 0 && Wo > 0, "dwconv: empty output");
+  const int64_t total = (int64_t)n * Ho * Wo * (C / 4);
+  const int g = grid_for(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float asc = a_is_spike ? a_scale : 1.f;
+#define S2F_DW(AT, KS)                                                                                                  \
+  dwconv_kernel<AT, KS><<<g, 256, 0, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, out_f32, out_spike, n, \
+                                           H, W, C, Ho, Wo, pad, d_max)
+  if (a_is_spike) {
+    if (k == 3) S2F_DW(int8_t, 3); else if (k == 5) S2F_DW(int8_t, 5); else S2F_DW(int8_t, 7);
+  } else {
+    if (k == 3) S2F_DW(float, 3); else if (k == 5) S2F_DW(float, 5); else S2F_DW(float, 7);
+  }
+#undef S2F_DW
+  return check_launch("dwconv_kernel");
+}
+
+extern "C" int s2f_dcnv3_gather(const float* x, const float* offset, const int8_t* mask, float mask_scale, float* out,
+                                int n, int H, int W, int G, int Cg, int K, float offset_scale, void* stream) {
+  S2F_REQUIRE(x && offset && mask && out, "dcnv3_gather: null pointer");
+  S2F_REQUIRE(Cg % 4 == 0, "dcnv3_gather: group channels must be a multiple of 4");
+  S2F_REQUIRE(K % 2 == 1 && K >= 1, "dcnv3_gather: K must be odd");
+  const int64_t total = (int64_t)n * H * W * G * (Cg / 4);
+  dcnv3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, offset, mask, mask_scale, out, n, H, W, G, Cg,
+                                                                       K, offset_scale);
+  return check_launch("dcnv3_kernel");
+}
+
+extern "C" int s2f_upsample_add_lif(const float* cur, const float* prev, int8_t* out_spike, float* out_f32, int n,
+                                    int H, int W, int Hp, int Wp, int C, float d_max, void* stream) {
+  S2F_REQUIRE(cur && prev && (out_spike || out_f32), "upsample_add_lif: null pointer");
+  S2F_REQUIRE(C % 4 == 0, "upsample_add_lif: C must be a multiple of 4");
+  const int64_t total = (int64_t)n * H * W * (C / 4);
+  upsample_add_lif_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(cur, prev, out_spike, out_f32, n, H, W,
+                                                                                  Hp, Wp, C, d_max);
+  return check_launch("upsample_add_lif_kernel");
+}
+
+extern "C" int s2f_affine_add_lif(const float* x, const float* scale, const float* residual, float* out_f32,
+                                  int8_t* out_spike, int64_t N, int C, float d_max, void* stream) {
+  S2F_REQUIRE(x && (out_f32 || out_spike), "affine_add_lif: null pointer");
+  S2F_REQUIRE(N % 4 == 0 && C % 4 == 0, "affine_add_lif: N and C must be multiples of 4");
+  if (N == 0) return S2F_OK;
+  affine_add_lif_kernel<<<grid_for(N / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, scale, residual, out_f32, out_spike,
+                                                                                N / 4, C, d_max);
+  return check_launch("affine_add_lif_kernel");
+}

@@ -1,0 +1,551 @@
+"""Execution engine: runs the Spike2Former forward on the sm_100a kernels (no torch compute ops on the path).
+
+Data layout in HBM (n = T*B images, channels-last everywhere):
+  * spikes      int8 levels 0..8          [n, H, W, C]   (1 B / neuron; reference value = level / 8)
+  * streams     fp32 residual streams     [n, H, W, C]
+  * tokens      the same buffers viewed   [n, H*W, C]
+Every kernel that produces a residual stream also emits the NI-LIF levels of that stream from its
+epilogue, because every consumer of a stream in the reference starts with a Q_IFNode.
+
+A `Plan` holds the folded / re-laid-out parameters of one model on one device.  Forward functions take
+an optional `probe` (tests only): it sees every neuron's spikes (and pre-activations) and may replace
+them, which is how the teacher-forced parity tests drive each unit with the oracle's tensors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import fold, ops
+from .ops import NORM
+
+INV = 1.0 / NORM
+
+
+# ------------------------------------------------------------------------------------------------ plan
+class Gemm:
+    """A conv / linear layer prepared for the kernels: weights [Cout, K] (Cin fastest) + folded affine."""
+
+    def __init__(self, w2d, scale, shift, cin, k=1, stride=1, pad=0, device="cuda"):
+        self.cout, self.cin, self.k, self.stride, self.pad = int(w2d.shape[0]), int(cin), k, stride, pad
+        self.w = ops.pad_rows4(fold.f32(w2d, device))
+        self.scale, self.shift = fold.f32(scale, device), fold.f32(shift, device)
+
+    def __call__(self, a, n, H, W, residual=None, f32=False, spike=False, transposed=False, a_scale=INV, **kw):
+        return ops.conv_simt(a, self.w, n=n, H=H, W=W, Cin=self.cin, Cout=self.cout, k=self.k, stride=self.stride,
+                             pad=self.pad, scale=self.scale, shift=self.shift, residual=residual, a_scale=a_scale,
+                             want_f32=f32, want_spike=spike, transposed=transposed, **kw)
+
+
+class Dw:
+    def __init__(self, w, scale, shift, device):
+        self.k, self.c = int(w.shape[-1]), int(w.shape[0])
+        self.w = fold.f32(fold.dw_taps(w), device)
+        self.scale = fold.f32(scale, device) if scale is not None else None
+        self.shift = fold.f32(shift, device) if shift is not None else None
+
+    def __call__(self, a, n, H, W, f32=False, spike=False):
+        return ops.dwconv(a, self.w, n=n, H=H, W=W, C_=self.c, k=self.k, scale=self.scale, shift=self.shift,
+                          want_f32=f32, want_spike=spike)
+
+
+def _conv_gemm(sd, conv_key, bn_key, device, k=1, stride=1, pad=0, extra_scale=None):
+    w = sd[conv_key + ".weight"]
+    s, t = fold.conv_bn(sd, conv_key, bn_key, extra_scale)
+    return Gemm(fold.w_khwc(w), s, t, w.shape[1], k, stride, pad, device)
+
+
+def _rep_gemm(sd, keys, device):
+    """One dense 3x3 for one or several RepConv(+BN) branches sharing their input (outputs concatenated)."""
+    ws, bs = zip(*(fold.repconv_dense3x3(sd, k) for k in keys))
+    w, b = torch.cat(ws, 0), torch.cat(bs, 0)
+    cin = w.shape[1] // 9
+    return Gemm(w, torch.ones_like(b), b, cin, 3, 1, 1, device)
+
+
+def _dw(sd, conv_key, bn_key, device):
+    w = sd[conv_key + ".weight"]
+    if bn_key is None:
+        return Dw(w, None, None, device)
+    s, t = fold.bn_affine(sd, bn_key)
+    return Dw(w, s, t, device)
+
+
+class BackbonePlan:
+    def __init__(self, model, device):
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        L = self.layers = {}
+        dev = device
+        L["stem"] = _conv_gemm(sd, "downsample1_1.encode_conv", "downsample1_1.encode_bn", dev, 7, 2, 3)
+        for name in ("ConvBlock1_1.0", "ConvBlock1_2.0", "ConvBlock2_1.0", "ConvBlock2_2.0"):
+            L[name + ".pw1"] = _conv_gemm(sd, name + ".Conv.pwconv1", name + ".Conv.bn1", dev)
+            L[name + ".dw"] = _dw(sd, name + ".Conv.dwconv", None, dev)
+            L[name + ".pw2"] = _conv_gemm(sd, name + ".Conv.pwconv2", name + ".Conv.bn2", dev)
+            L[name + ".conv1"] = _conv_gemm(sd, name + ".conv1", name + ".bn1", dev, 3, 1, 1)
+            L[name + ".conv2"] = _conv_gemm(sd, name + ".conv2", name + ".bn2", dev, 3, 1, 1)
+        for name, st in (("downsample1_2", 2), ("downsample2", 2), ("downsample3", 2), ("downsample4", 1)):
+            L[name] = _conv_gemm(sd, name + ".encode_conv", name + ".encode_bn", dev, 3, st, 1)
+        for name in [f"block3.{j}" for j in range(6)] + [f"block4.{j}" for j in range(2)]:
+            L[name + ".qkv"] = _rep_gemm(sd, [name + ".attn.q_conv", name + ".attn.k_conv", name + ".attn.v_conv"], dev)
+            L[name + ".proj"] = _rep_gemm(sd, [name + ".attn.proj_conv"], dev)
+            L[name + ".fc1"] = _conv_gemm(sd, name + ".mlp.fc1_conv", name + ".mlp.fc1_bn", dev)
+            L[name + ".fc2"] = _conv_gemm(sd, name + ".mlp.fc2_conv", name + ".mlp.fc2_bn", dev)
+
+
+class PixelDecoderPlan:
+    def __init__(self, model, device):
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        L = self.layers = {}
+        dev = device
+        self.num_layers = model.encoder_cfg["num_layers"]
+        sa = model.encoder_cfg["layer_cfg"]["self_attn_cfg"]
+        self.group, self.dw_k = sa["group"], sa["dw_kernel_size"]
+        L["in_proj"] = _conv_gemm(sd, "encoder_in_proj.0", "encoder_in_proj.1", dev)
+        L["out_proj"] = _conv_gemm(sd, "encoder_out_proj.0", "encoder_out_proj.1", dev)
+
+        def sepconv(prefix, key, gamma):
+            L[prefix + ".pw1"] = _conv_gemm(sd, key + ".pwconv1.0", key + ".pwconv1.1", dev)
+            L[prefix + ".dw"] = _dw(sd, key + ".dwconv.0", key + ".dwconv.1", dev)
+            L[prefix + ".pw2"] = _conv_gemm(sd, key + ".pwconv2.0", key + ".pwconv2.1", dev, extra_scale=gamma)
+
+        self.gamma3 = []
+        for l in range(self.num_layers):
+            k = f"encoder.layers.{l}"
+            sepconv(f"{l}.conv", k + ".Conv", sd[k + ".gamma1"])
+            sepconv(f"{l}.dcn_in", k + ".dcn.input_proj", None)
+            sepconv(f"{l}.dcn_out", k + ".dcn.output_proj", sd[k + ".gamma2"])
+            L[f"{l}.dcn_dw"] = _dw(sd, k + ".dcn.dw_conv.0", k + ".dcn.dw_conv.1", dev)
+            L[f"{l}.offset"] = _conv_gemm(sd, k + ".dcn.offset.0", k + ".dcn.offset.1", dev)
+            L[f"{l}.mask"] = _conv_gemm(sd, k + ".dcn.mask.0", k + ".dcn.mask.1", dev)
+            L[f"{l}.fc1"] = _conv_gemm(sd, k + ".ffn.fc1_conv", k + ".ffn.fc1_bn", dev)
+            L[f"{l}.fc2"] = _conv_gemm(sd, k + ".ffn.fc2_conv", k + ".ffn.fc2_bn", dev)
+            self.gamma3.append(fold.f32(sd[k + ".gamma3"], dev))
+        for i in range(model.num_inputs - 1):
+            L[f"lateral.{i}"] = _conv_gemm(sd, f"lateral_convs.{i}.0", f"lateral_convs.{i}.1", dev)
+            L[f"output.{i}"] = _dw(sd, f"output_convs.{i}.0", f"output_convs.{i}.1", dev)
+        L["mask_feature"] = _conv_gemm(sd, "mask_feature", None, dev)
+
+
+class HeadPlan:
+    def __init__(self, model, device):
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items() if not k.startswith("pixel_decoder.")}
+        L = self.layers = {}
+        dev = device
+        cfg = model.transformer_decoder_cfg
+        self.num_layers = cfg["num_layers"]
+        self.heads = cfg["layer_cfg"]["self_attn_cfg"]["num_heads"]
+        self.dim = cfg["layer_cfg"]["self_attn_cfg"]["embed_dims"]
+        for l in range(self.num_layers):
+            k = f"transformer_decoder.layers.{l}"
+            for blk in ("cross_attn", "self_attn"):
+                for p in ("q", "k", "v", "out"):
+                    L[f"{l}.{blk}.{p}"] = _conv_gemm(sd, f"{k}.{blk}.attn.{p}_conv.0", f"{k}.{blk}.attn.{p}_conv.1", dev)
+            L[f"{l}.fc1"] = _conv_gemm(sd, k + ".ffn.fc1", k + ".ffn.bn1", dev)
+            L[f"{l}.fc2"] = _conv_gemm(sd, k + ".ffn.fc2", k + ".ffn.bn2", dev)
+        self.query_feat = fold.f32(sd["query_feat.weight"], dev)
+        self.query_embed = fold.f32(sd["query_embed.weight"], dev)
+        self.level_embed = fold.f32(sd["level_embed.weight"], dev)
+        L["cls"] = _conv_gemm(sd, "cls_embed", None, dev)
+        L["me.fc1"] = _conv_gemm(sd, "mask_embed.fc1", None, dev)
+        L["me.fc2"] = _conv_gemm(sd, "mask_embed.fc2", None, dev)
+        L["me.out"] = _conv_gemm(sd, "mask_embed.fc_out", None, dev)
+        # shortcut: Conv1d(nq -> nq) over the query axis + BN1d(nq), times the learnable scalar w
+        wsc = float(sd["w"].item())
+        s, t = fold.bn_affine(sd, "shortcut_conv.1")
+        nq = sd["shortcut_conv.0.weight"].shape[0]
+        L["shortcut"] = Gemm(sd["shortcut_conv.0.weight"][:, :, 0], s * wsc, t * wsc, nq, device=dev)
+        self.pe_cache = {}
+        self.num_feats = model.positional_encoding_cfg["num_feats"]
+
+    def sine_pe(self, h, w, device):
+        """SinePositionalEncoding (normalize=True, all-valid mask): positional_encoding.py:60-104 -> [h*w, 2F]."""
+        key = (h, w)
+        if key not in self.pe_cache:
+            F_, temp, scale, eps = self.num_feats, 10000, 2 * math.pi, 1e-6
+            ones = torch.ones(1, h, w, dtype=torch.int)
+            y_e = ones.cumsum(1, dtype=torch.float32)
+            x_e = ones.cumsum(2, dtype=torch.float32)
+            y_e = (y_e + 0.0) / (y_e[:, -1:, :] + eps) * scale
+            x_e = (x_e + 0.0) / (x_e[:, :, -1:] + eps) * scale
+            dim_t = torch.arange(F_, dtype=torch.float32)
+            dim_t = temp ** (2 * (dim_t // 2) / F_)
+            px, py = x_e[:, :, :, None] / dim_t, y_e[:, :, :, None] / dim_t
+            px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).view(1, h, w, -1)
+            py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).view(1, h, w, -1)
+            self.pe_cache[key] = torch.cat((py, px), dim=3).reshape(h * w, 2 * F_).contiguous().to(device)
+        return self.pe_cache[key]
+
+
+def plan_of(model, kind):
+    if model._plan is None:
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("spike2former_b200: move the model to a CUDA device first (no CPU path)")
+        model._plan = kind(model, dev)
+    return model._plan
+
+
+# ------------------------------------------------------------------------------------------------ probing
+class NullProbe:
+    """Production probe: does nothing.  Layout tags tell a test probe how the reference lays the tensor out:
+    'cm'  reference is channel-major [n, C, *spatial], ours is channels-last [n, *spatial, C];
+    'same' identical flat order;  'reint_T' our buffer holds the reference's [C, nq] reinterpretation transposed."""
+    active = False
+
+    def spike(self, name, t, layout="cm"):
+        return t
+
+    def real(self, name, t, layout="cm"):
+        return t
+
+    def scoped(self, prefix):
+        return self
+
+
+NOPROBE = NullProbe()
+
+
+# ------------------------------------------------------------------------------------------------ backbone
+def _conv_block(L, name, s, sp, n, H, W, pr):
+    """MS_ConvBlock (sdtv2.py:207-219) on stream s with spike twin sp = LIF(s)."""
+    sp = pr.spike(f"{name}.Conv.spike1", sp)
+    _, a = L[name + ".pw1"](sp, n, H, W, spike=True, f32=False)
+    a = pr.spike(f"{name}.Conv.spike2", a)
+    d, _ = L[name + ".dw"](a, n, H, W, f32=True)
+    s2, sp2 = L[name + ".pw2"](d, n, H, W, residual=s, f32=True, spike=True)
+    s2 = pr.real(f"{name}.spike1", s2)
+    sp2 = pr.spike(f"{name}.spike1", sp2)
+    _, a = L[name + ".conv1"](sp2, n, H, W, spike=True)
+    a = pr.spike(f"{name}.spike2", a)
+    return L[name + ".conv2"](a, n, H, W, residual=s2, f32=True, spike=True)
+
+
+def _ms_block(L, name, s, sp, n, H, W, heads, pr):
+    """MS_Block (sdtv2.py:298-383): SDSA with the RepConv branches as one dense 3x3, then MS_MLP."""
+    C = s.shape[-1]
+    d = C // heads
+    N = H * W
+    sp = pr.spike(f"{name}.attn.head_spike", sp)
+    _, qkv = L[name + ".qkv"](sp, n, H, W, spike=True)                      # [n,H,W,3C] levels of q|k|v
+    if pr.active:
+        q, k, v = (pr.spike(f"{name}.attn.{nm}_spike", qkv[..., i * C:(i + 1) * C].contiguous())
+                   for i, nm in enumerate("qkv"))
+        ld = C
+    else:
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        ld = 3 * C
+    att, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, q_ld=ld, kv_ld=ld,
+                             out_scale=(d ** -0.5) * INV ** 3)
+    att = pr.spike(f"{name}.attn.attn_spike", att.view(n, H, W, C))
+    s2, sp2 = L[name + ".proj"](att, n, H, W, residual=s, f32=True, spike=True)
+    s2 = pr.real(f"{name}.mlp.fc1_spike", s2)
+    sp2 = pr.spike(f"{name}.mlp.fc1_spike", sp2)
+    _, a = L[name + ".fc1"](sp2, n, H, W, spike=True)
+    a = pr.spike(f"{name}.mlp.fc2_spike", a)
+    return L[name + ".fc2"](a, n, H, W, residual=s2, f32=True, spike=True)
+
+
+def backbone_forward(model, img, probe=NOPROBE):
+    """Spiking_vit_MetaFormer.forward_features (sdtv2.py:614-651).  img fp32 [B,3,H,W] (NCHW, as the reference
+    receives it).  Returns [(stream fp32 [n,h,w,C], levels int8 [n,h,w,C])] for x1..x4."""
+    plan = plan_of(model, BackbonePlan)
+    L, pr = plan.layers, probe
+    B, cin, H, W = img.shape
+    n = B * model.T
+    x = img.permute(0, 2, 3, 1).contiguous()
+    if model.T > 1:
+        x = x.unsqueeze(0).expand(model.T, -1, -1, -1, -1).reshape(n, H, W, cin).contiguous()
+    s, sp = L["stem"](x, n, H, W, f32=True, spike=True)
+    H, W = H // 2, W // 2
+    feats = []
+
+    def down(name, s, sp, H, W, stride):
+        s = pr.real(f"{name}.encode_spike", s)
+        sp = pr.spike(f"{name}.encode_spike", sp)
+        return L[name](sp, n, H, W, f32=True, spike=True)
+
+    s = pr.real("ConvBlock1_1.0.Conv.spike1", s)
+    s, sp = _conv_block(L, "ConvBlock1_1.0", s, sp, n, H, W, pr)
+    feats.append((s, sp))
+    s, sp = down("downsample1_2", s, sp, H, W, 2); H, W = H // 2, W // 2
+    s = pr.real("ConvBlock1_2.0.Conv.spike1", s)
+    s, sp = _conv_block(L, "ConvBlock1_2.0", s, sp, n, H, W, pr)
+    feats.append((s, sp))
+    s, sp = down("downsample2", s, sp, H, W, 2); H, W = H // 2, W // 2
+    s = pr.real("ConvBlock2_1.0.Conv.spike1", s)
+    s, sp = _conv_block(L, "ConvBlock2_1.0", s, sp, n, H, W, pr)
+    s = pr.real("ConvBlock2_2.0.Conv.spike1", s)
+    s, sp = _conv_block(L, "ConvBlock2_2.0", s, sp, n, H, W, pr)
+    feats.append((s, sp))
+    s, sp = down("downsample3", s, sp, H, W, 2); H, W = H // 2, W // 2
+    for j in range(6):
+        s = pr.real(f"block3.{j}.attn.head_spike", s)
+        s, sp = _ms_block(L, f"block3.{j}", s, sp, n, H, W, model.num_heads, pr)
+    s, sp = down("downsample4", s, sp, H, W, 1)
+    for j in range(2):
+        s = pr.real(f"block4.{j}.attn.head_spike", s)
+        s, sp = _ms_block(L, f"block4.{j}", s, sp, n, H, W, model.num_heads, pr)
+    feats.append((s, sp))
+    return feats
+
+
+def export_backbone_feats(model, feats):
+    """Reference output contract (sdtv2.py:639-651): 'Qsnn' -> [T,B,C,H,W]; 'snn' -> mean over T; else [T*B,C,H,W]."""
+    T = model.T
+    outs = []
+    for s, sp in feats:
+        n, h, w, c = s.shape
+        t = s.permute(0, 3, 1, 2)
+        if model.decode_mode == "Qsnn":
+            t = t.reshape(T, n // T, c, h, w)
+        elif model.decode_mode == "snn":
+            t = t.reshape(T, n // T, c, h, w).mean(0, keepdim=True)
+        t._s2f = (s, sp)
+        outs.append(t)
+    return outs
+
+
+def _import_feats(x):
+    """Public-API inputs ([T,B,C,H,W] tensors) -> internal (stream, levels) pairs."""
+    feats = []
+    for t in x:
+        cached = getattr(t, "_s2f", None)
+        if cached is not None:
+            feats.append(cached)
+            continue
+        if t.dim() == 5:
+            t = t.flatten(0, 1)
+        s = t.permute(0, 2, 3, 1).contiguous().float()
+        sp, _, _ = ops.nilif(s)
+        feats.append((s, sp))
+    return feats
+
+
+# ------------------------------------------------------------------------------------------------ pixel decoder
+def _sepconv_spike(L, prefix, key, sp, n, H, W, pr, residual=None, want_spike=True):
+    """SepConv_Spike (SNN_core.py:47-63) from the spike twin of its input; pw2 epilogue adds the residual."""
+    sp = pr.spike(key + ".spike1", sp)
+    _, a = L[prefix + ".pw1"](sp, n, H, W, spike=True)
+    a = pr.spike(key + ".spike2", a)
+    _, a = L[prefix + ".dw"](a, n, H, W, spike=True)
+    a = pr.spike(key + ".spike3", a)
+    return L[prefix + ".pw2"](a, n, H, W, residual=residual, f32=True, spike=want_spike)
+
+
+def pixel_decoder_forward(model, feats, probe=NOPROBE):
+    """DCNTransformerEncoderPixelDecoder.forward (pixel_decoder.py:417-472).
+    Returns (mask_feature fp32 [n,H1,W1,C], memory levels, [y32, y64, y128] fp32 channels-last)."""
+    plan = plan_of(model, PixelDecoderPlan)
+    L, pr = plan.layers, probe
+    pd = "pixel_decoder."
+    s4, sp4 = feats[-1]
+    n, H, W, _ = s4.shape
+    C = model.feat_channels
+    G = plan.group
+    sp4 = pr.spike(pd + "last_feat_conv_spike", sp4)
+    q, qs = L["in_proj"](sp4, n, H, W, f32=True, spike=True)
+    for l in range(plan.num_layers):
+        k = pd + f"encoder.layers.{l}"
+        q = pr.real(k + ".Conv.spike1", q)
+        q1, q1s = _sepconv_spike(L, f"{l}.conv", k + ".Conv", qs, n, H, W, pr, residual=q)
+        # ---- DCNv3 (dcnv3.py:198-233)
+        q1 = pr.real(k + ".dcn.input_proj.spike1", q1)
+        x, _ = _sepconv_spike(L, f"{l}.dcn_in", k + ".dcn.input_proj", q1s, n, H, W, pr, want_spike=False)
+        x = pr.real(k + ".dcn.x", x, "same")
+        a = pr.spike(k + ".dcn.dw_spike", q1s)
+        _, a = L[f"{l}.dcn_dw"](a, n, H, W, spike=True)
+        a = pr.spike(k + ".dcn.offset_spike", a)
+        # NCHW conv outputs reinterpreted as [n,H,W,-1]: written channel-major, read back channels-last
+        off, _ = L[f"{l}.offset"](a, n, H, W, f32=True, transposed=True)
+        off = pr.real(k + ".dcn.offset", off.view(n, H, W, -1), "same")
+        _, msk = L[f"{l}.mask"](a, n, H, W, spike=True, transposed=True)
+        msk = pr.spike(k + ".dcn.mask_spike", msk.view(n, H, W, -1), "same")
+        g = ops.dcnv3_gather(x, off, msk, n=n, H=H, W=W, G=G, Cg=C // G, K=3, offset_scale=1.0)
+        g = pr.real(k + ".dcn.output_proj.spike1", g)
+        gs, _, _ = ops.nilif(g)
+        q2, q2s = _sepconv_spike(L, f"{l}.dcn_out", k + ".dcn.output_proj", gs, n, H, W, pr, residual=q1)
+        # ---- MS_MLP with the reinterpreted output (mmcv_spike/transformer.py:817-831)
+        q2 = pr.real(k + ".ffn.fc1_spike", q2)
+        a = pr.spike(k + ".ffn.fc1_spike", q2s)
+        _, a = L[f"{l}.fc1"](a, n, H, W, spike=True)
+        a = pr.spike(k + ".ffn.fc2_spike", a)
+        r, _ = L[f"{l}.fc2"](a, n, H, W, f32=True, transposed=True)
+        q, qs = ops.affine_add_lif(r.view(n, H, W, C), plan.gamma3[l], q2)
+    q = pr.real(pd + "encoder_out_proj_spike", q)
+    memory = pr.spike(pd + "encoder_out_proj_spike", qs)
+    y, _ = L["out_proj"](memory, n, H, W, f32=True)
+    y = pr.real(pd + "y0", y)
+    outs = [y]
+    hp, wp = H, W
+    for i in range(model.num_inputs - 2, -1, -1):
+        s_i, sp_i = feats[i]
+        _, h, w, _ = s_i.shape
+        sp_i = pr.spike(pd + f"lateral_convs_spike.{i}", sp_i)
+        cur, _ = L[f"lateral.{i}"](sp_i, n, h, w, f32=True)
+        ys, yf = ops.upsample_add_lif(cur, y, n=n, H=h, W=w, Hp=hp, Wp=wp, C_=C, want_f32=pr.active)
+        if pr.active:
+            pr.real(pd + f"output_convs_spike.{i}", yf)
+        ys = pr.spike(pd + f"output_convs_spike.{i}", ys)
+        y, ysp = L[f"output.{i}"](ys, n, h, w, f32=True, spike=(i == 0))
+        y = pr.real(pd + f"y{model.num_inputs - 1 - i}", y)
+        outs.append(y)
+        hp, wp = h, w
+    y = pr.real(pd + "mask_feature_spike", y)
+    ysp = pr.spike(pd + "mask_feature_spike", ysp)
+    mf, _ = L["mask_feature"](ysp, n, hp, wp, f32=True)
+    mf = pr.real(pd + "mask_feature", mf)
+    return mf, memory, outs[:3]
+
+
+def pixel_decoder_forward_public(model, x):
+    mf, memory, outs = pixel_decoder_forward(model, _import_feats(x))
+    T = x[0].shape[0] if x[0].dim() == 5 else 1
+
+    def nchw(t):
+        n, h, w, c = t.shape
+        return t.permute(0, 3, 1, 2).reshape(T, n // T, c, h, w)
+
+    return nchw(mf), nchw(memory.float() * INV), [nchw(o) for o in outs]
+
+
+# ------------------------------------------------------------------------------------------------ decoder + SDME
+def _attention(L, key, pfx, q_sp, k_sp, v_sp, n, nq, nk, heads, dim, residual, pr, kv_cache=None):
+    """{Cross,}MultiHeadAttentionBlock (mmcv_spike/transformer.py:237-278, 318-361) from the LIF levels of
+    its three inputs.  Linear form: NI-LIF(Q (K^T V) / sqrt(dim)); out_conv epilogue adds the residual."""
+    q_sp = pr.spike(key + ".q_conv_spike", q_sp, "same")
+    _, q = L[pfx + ".q"](q_sp, n, nq, 1, spike=True)
+    q = pr.spike(key + ".q_spike", q.view(n, nq, dim), "same")
+    k_sp = pr.spike(key + ".k_conv_spike", k_sp, "same")
+    _, k = L[pfx + ".k"](k_sp, n, nk, 1, spike=True)
+    k = pr.spike(key + ".k_spike", k.view(n, nk, dim), "same")
+    v_sp = pr.spike(key + ".v_conv_spike", v_sp, "same")
+    _, v = L[pfx + ".v"](v_sp, n, nk, 1, spike=True)
+    v = pr.spike(key + ".v_spike", v.view(n, nk, dim), "same")
+    att, _ = ops.linear_attn(q, k, v, n=n, Nq=nq, Nk=nk, heads=heads, d=dim // heads,
+                             out_scale=INV ** 3 / (dim ** 0.5))
+    att = pr.spike(key + ".attn_spike", att, "same")
+    out, _ = L[pfx + ".out"](att, n, nq, 1, residual=residual, f32=True)
+    return out.view(n, nq, dim)
+
+
+def head_forward(model, feats, probe=NOPROBE, last_only=False):
+    """mmdet MaskFormerHead.forward (dense_heads/maskformer_head.py:498-586).
+    Returns (cls [L,n,nq,K+1], mask levels int8 [L,n,nq,C], mask_feature [n,h,w,C]); L = 1 when last_only."""
+    pd_model = model.pixel_decoder
+    pr = probe
+    mf, memory, ms = pixel_decoder_forward(pd_model, feats, pr)
+    plan = plan_of(model, HeadPlan)
+    L = plan.layers
+    n = mf.shape[0]
+    nq, dim, heads = model.num_queries, plan.dim, plan.heads
+    dev = mf.device
+    hd = ""
+    qe = plan.query_embed                                        # [nq, C]
+    qf = plan.query_feat.unsqueeze(0).expand(n, nq, dim).contiguous()
+    # key / value spikes per level: LIF(y + level_embed + pos) and LIF(y + level_embed) -- shared by layers i, i+3
+    lvl_k, lvl_v, lvl_n = [], [], []
+    for i in range(3):
+        y = ms[i]
+        _, h, w, _ = y.shape
+        pe = plan.sine_pe(h, w, dev)
+        ones = torch.ones(dim, dtype=torch.float32, device=dev)
+        ksp, _, _ = ops.nilif(y, scale=ones, shift=plan.level_embed[i].contiguous(), residual=pe,
+                              residual_period=pe.numel())
+        vsp, _, _ = ops.nilif(y, scale=ones, shift=plan.level_embed[i].contiguous())
+        lvl_k.append(ksp.view(n, h * w, dim)); lvl_v.append(vsp.view(n, h * w, dim)); lvl_n.append(h * w)
+    states = [qf]
+    for i in range(plan.num_layers):
+        lv = i % 3
+        k = f"transformer_decoder.layers.{i}"
+        q_sp, _, _ = ops.nilif(qf, residual=qe, residual_period=qe.numel())
+        qf = _attention(L, k + ".cross_attn.attn", f"{i}.cross_attn", q_sp, lvl_k[lv], lvl_v[lv], n, nq, lvl_n[lv], heads,
+                        dim, qf, pr)
+        qf = pr.real(k + ".self_attn.attn.v_conv_spike", qf, "same")
+        qk_sp, _, _ = ops.nilif(qf, residual=qe, residual_period=qe.numel())
+        v_sp, _, _ = ops.nilif(qf)
+        qf = _attention(L, k + ".self_attn.attn", f"{i}.self_attn", qk_sp, qk_sp, v_sp, n, nq, nq, heads, dim, qf, pr)
+        # ---- MSDA_FFN with both reinterpreting reshapes (mmcv_spike/transformer.py:768-784)
+        qf = pr.real(k + ".ffn.fc1_spike", qf, "same")
+        a, _, _ = ops.nilif(qf, transpose=(nq, dim))             # [C,nq] matrix stored as [nq(pos), C]
+        a = pr.spike(k + ".ffn.fc1_spike", a, "reint_T")
+        _, a = L[f"{i}.fc1"](a, n, nq, 1, spike=True)
+        a = pr.spike(k + ".ffn.fc2_spike", a.view(n, nq, -1), "ncl")
+        r, _ = L[f"{i}.fc2"](a, n, nq, 1, f32=True, transposed=True)
+        qf, _ = ops.affine_add_lif(r.view(n, nq, dim), None, qf, want_spike=False)
+        qf = pr.real(k + ".out", qf, "same")
+        states.append(qf)
+    # ---- SDME (maskformer_head.py:571-582)
+    if last_only and not pr.active:
+        states = states[-1:]
+    Ls = len(states)
+    od = torch.stack(states)                                     # [L, n, nq, C]
+    lv = ops.sigmoid_lif(od)
+    lv = pr.spike("decoder_out_spike", lv, "same")
+    pr.spike("shortcut_conv_spike", lv, "same")
+    rows = Ls * n
+    half = model.alpha * INV                                     # alpha * level / 8
+    cls, _ = L["cls"](lv, rows, nq, 1, f32=True, a_scale=half)
+    _, a = L["me.fc1"](lv, rows, nq, 1, spike=True, a_scale=half)
+    a = pr.spike("mask_embed.spike1", a.view(Ls, n, nq, dim), "same")
+    _, a = L["me.fc2"](a, rows, nq, 1, spike=True, a_scale=half)
+    a = pr.spike("mask_embed.spike2", a.view(Ls, n, nq, dim), "same")
+    # shortcut over the query axis: A[m=c][k=q] = lv[q*C + c]; output [q', c] = transposed store
+    sc, _ = L["shortcut"](lv, rows, dim, 1, f32=True, transposed=True, a_scale=half, a_img_stride=nq * dim,
+                          a_stride_m=1, a_stride_k=dim)
+    m_f, me = L["me.out"](a, rows, nq, 1, residual=sc.view(rows, nq, 1, dim), f32=pr.active, spike=True, a_scale=half)
+    if pr.active:
+        pr.real("mask_embed_spike", m_f.view(Ls, n, nq, dim), "same")
+    me = pr.spike("mask_embed_spike", me.view(Ls, n, nq, dim), "same")
+    cls = cls.view(Ls, n, nq, -1)
+    return cls, me, mf
+
+
+def _mask_gemm(me_l, mf, n, h, w, nq, dim, alpha, transposed):
+    """einsum('bqc,bchw->bqhw') for one decoder output: mask_feature rows x per-image spike weights."""
+    wq = (me_l.float() * (alpha * INV)).contiguous()             # [n, nq, C] fp32 weights of this image
+    out, _ = ops.conv_simt(mf, wq, n=n, H=h, W=w, Cin=dim, Cout=nq, want_f32=True, transposed=transposed,
+                           w_img_stride=nq * dim)
+    return out
+
+
+def head_forward_public(model, x):
+    feats = _import_feats(x)
+    T = x[0].shape[0] if x[0].dim() == 5 else 1
+    cls, me, mf = head_forward(model, feats)
+    Ls, n, nq, _ = cls.shape
+    _, h, w, dim = mf.shape
+    masks = torch.stack([_mask_gemm(me[l], mf, n, h, w, nq, dim, model.alpha, True).view(n, nq, h, w)
+                         for l in range(Ls)])
+    B = n // T
+    return cls.view(Ls, T, B, nq, -1).mean(1), masks.view(Ls, T, B, nq, h, w).mean(1)
+
+
+def _predict_from(model, feats, img_shape, probe=NOPROBE):
+    cls, me, mf = head_forward(model, feats, probe, last_only=True)
+    n, h, w, dim = mf.shape
+    nq = model.num_queries
+    mp = _mask_gemm(me[-1], mf, n, h, w, nq, dim, model.alpha, False)       # [n, h, w, nq] pixel-major
+    cl = cls[-1].contiguous()
+    mp = probe.real("mask_pred", mp)
+    cl = probe.real("cls_score", cl, "same")
+    return ops.semantic_tail(mp.view(n, h * w, nq), cl, n=n, Q=nq, K=model.num_classes, h=h, w=w, H=img_shape[0],
+                             W=img_shape[1])
+
+
+def head_predict(model, x, img_shape, probe=NOPROBE):
+    """mmseg MaskFormerHead.predict (decode_heads/maskformer_head.py:138-180) -> [B, K, H, W]."""
+    feats = _import_feats(x)
+    T = x[0].shape[0] if x[0].dim() == 5 else 1
+    if T != 1:
+        raise NotImplementedError("predict with T > 1: every Spike2Former config uses T = 1 (SURVEY.md section 0.3)")
+    return _predict_from(model, feats, img_shape, probe)
+
+
+def segmentor_logits(seg, img, probe=NOPROBE):
+    """EncoderDecoder.encode_decode (encoder_decoder.py:125-133): internal tensors go straight to the head."""
+    if seg.backbone.T != 1:
+        raise NotImplementedError("T > 1 end-to-end inference is not used by any Spike2Former config")
+    feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if probe.active else probe)
+    pr = probe.scoped("decode_head.") if probe.active else probe
+    return _predict_from(seg.decode_head, feats, tuple(img.shape[-2:]), pr)

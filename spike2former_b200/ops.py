@@ -1,0 +1,185 @@
+"""Operator-level Python interface over the C ABI (include/s2f.h).
+
+Each function takes torch CUDA tensors, checks dtype / device / contiguity, allocates the outputs
+with torch (device memory + stream plumbing only) and launches the kernels on the current stream.
+CPU tensors are rejected: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, GemmTcArgs, S2FError, check
+
+D_MAX = 8.0     # Quant() clamp max: surrogate.py:526
+NORM = 8.0      # hard-coded "/ 8": neuron.py:197
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise S2FError(f"{name}: CUDA tensor required (no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise S2FError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise S2FError(f"{name}: must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def launch_count() -> int:
+    return int(_lib.lib().s2f_launch_count())
+
+
+# ------------------------------------------------------------------------------------------ NI-LIF
+def nilif(x, scale=None, shift=None, residual=None, residual_period=0, v_in=None, want_v_out=False, want_norm=False,
+          T=1, C_=None, d_max=D_MAX, norm=NORM, transpose=None, ties=None, out=None):
+    """Fused NI-LIF.  x: fp32 [T, ...] (T leading when T > 1).  Returns (levels int8 same shape, v_out|None, y|None).
+
+    The reference call it replaces: `Q_IFNode(surrogate_function=Quant())(x)` -- neuron.py:462-550."""
+    _ptr(x, torch.float32, "x")
+    total = x.numel()
+    if total % T != 0:
+        raise S2FError("nilif: numel not divisible by T")
+    N = total // T
+    C_ = int(C_ if C_ is not None else x.shape[-1])
+    levels = out if out is not None else torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    v_out = torch.empty(x.shape[1:] if T > 1 else x.shape, dtype=torch.float32, device=x.device) if want_v_out else None
+    y = torch.empty_like(x) if want_norm else None
+    tr, tc = (transpose if transpose else (0, 0))
+    check(_lib.lib().s2f_nilif_fwd(_ptr(x), _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                   _ptr(residual, torch.float32, "residual"), int(residual_period),
+                                   _ptr(v_in, torch.float32, "v_in"), _ptr(v_out), _ptr(levels, torch.int8, "levels"),
+                                   _ptr(y), int(T), int(N), C_, float(d_max), float(norm), int(tr), int(tc),
+                                   _ptr(ties), _stream()), "s2f_nilif_fwd")
+    return levels, v_out, y
+
+
+def nilif_bwd(x, gy, scale=None, shift=None, residual=None, C_=None, d_max=D_MAX, norm=NORM):
+    """Surrogate gradient of the neuron (T=1): quant.backward, surrogate.py:531-538."""
+    gx = torch.empty_like(x)
+    check(_lib.lib().s2f_nilif_bwd(_ptr(x, torch.float32, "x"), _ptr(scale), _ptr(shift), _ptr(residual),
+                                   _ptr(gy, torch.float32, "gy"), _ptr(gx), x.numel(),
+                                   int(C_ if C_ is not None else x.shape[-1]), float(d_max), float(norm), _stream()),
+          "s2f_nilif_bwd")
+    return gx
+
+
+def affine_add_lif(x, scale=None, residual=None, want_f32=True, want_spike=True, d_max=D_MAX):
+    out_f = torch.empty_like(x) if want_f32 else None
+    out_s = torch.empty(x.shape, dtype=torch.int8, device=x.device) if want_spike else None
+    check(_lib.lib().s2f_affine_add_lif(_ptr(x, torch.float32, "x"), _ptr(scale, torch.float32, "scale"),
+                                        _ptr(residual, torch.float32, "residual"), _ptr(out_f), _ptr(out_s),
+                                        x.numel(), int(x.shape[-1]), float(d_max), _stream()), "s2f_affine_add_lif")
+    return out_f, out_s
+
+
+# ------------------------------------------------------------------------------------------ conv / linear
+def pad_rows4(w2d: torch.Tensor) -> torch.Tensor:
+    """[Cout, K] -> [Cout, ceil4(K)] zero padded (row layout s2f_conv_simt expects)."""
+    k = w2d.shape[1]
+    kp = (k + 3) // 4 * 4
+    if kp == k:
+        return w2d.contiguous()
+    out = torch.zeros(w2d.shape[0], kp, dtype=w2d.dtype, device=w2d.device)
+    out[:, :k] = w2d
+    return out
+
+
+def conv_simt(a, w, *, n, H, W, Cin, Cout, k=1, stride=1, pad=0, scale=None, shift=None, residual=None,
+              a_scale=1.0 / NORM, want_f32=False, want_spike=False, transposed=False, a_img_stride=0, a_stride_m=0,
+              a_stride_k=0, w_img_stride=0, d_max=D_MAX, out_f32=None, out_spike=None):
+    """General implicit-GEMM convolution (CUDA cores).  a: int8 levels or fp32, channels-last."""
+    is_spike = a.dtype == torch.int8
+    if not is_spike and a.dtype != torch.float32:
+        raise S2FError("conv_simt: a must be int8 levels or fp32")
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    shape = (n, Cout, Ho * Wo) if transposed else (n, Ho, Wo, Cout)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(shape, dtype=torch.float32, device=a.device)
+    if want_spike and out_spike is None:
+        out_spike = torch.empty(shape, dtype=torch.int8, device=a.device)
+    args = ConvArgs()
+    args.a, args.a_is_spike, args.a_scale = _ptr(a, name="a"), int(is_spike), float(a_scale)
+    args.w, args.scale, args.shift = _ptr(w, torch.float32, "w"), _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift")
+    args.residual = _ptr(residual, torch.float32, "residual")
+    args.out_f32, args.out_spike, args.out_transposed = _ptr(out_f32), _ptr(out_spike), int(transposed)
+    args.n, args.H, args.W, args.Cin, args.Cout = n, H, W, Cin, Cout
+    args.KH = args.KW = k
+    args.stride, args.pad = stride, pad
+    args.a_img_stride, args.a_stride_m, args.a_stride_k = int(a_img_stride), int(a_stride_m), int(a_stride_k)
+    args.w_img_stride, args.d_max = int(w_img_stride), float(d_max)
+    check(_lib.lib().s2f_conv_simt(C.byref(args), _stream()), "s2f_conv_simt")
+    return out_f32, out_spike
+
+
+def dwconv(a, w_tap, *, n, H, W, C_, k, scale=None, shift=None, a_scale=1.0 / NORM, want_f32=False, want_spike=False,
+           no_pad=False, d_max=D_MAX):
+    """Depthwise k x k (stride 1).  w_tap: fp32 [k*k, C]."""
+    is_spike = a.dtype == torch.int8
+    pad = 0 if no_pad else (k - 1) // 2
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    out_f = torch.empty((n, Ho, Wo, C_), dtype=torch.float32, device=a.device) if want_f32 else None
+    out_s = torch.empty((n, Ho, Wo, C_), dtype=torch.int8, device=a.device) if want_spike else None
+    check(_lib.lib().s2f_dwconv(_ptr(a, name="a"), int(is_spike), float(a_scale), _ptr(w_tap, torch.float32, "w_tap"),
+                                _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"), None,
+                                _ptr(out_f), _ptr(out_s), n, H, W, C_, k, int(no_pad), float(d_max), _stream()),
+          "s2f_dwconv")
+    return out_f, out_s
+
+
+# ------------------------------------------------------------------------------------------ attention / DCN / tail
+def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=None, want_f32=False, d_max=D_MAX):
+    """Spike-driven attention without softmax: NI-LIF((Q (K^T V)) * out_scale).  q/k/v int8 levels."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if t.dtype != torch.int8 or not t.is_cuda:
+            raise S2FError(f"linear_attn: {nm} must be CUDA int8 levels")
+    Cc = heads * d
+    ws = torch.empty((n, heads, d, d), dtype=torch.int32, device=q.device)
+    out_s = torch.empty((n, Nq, Cc), dtype=torch.int8, device=q.device)
+    out_f = torch.empty((n, Nq, Cc), dtype=torch.float32, device=q.device) if want_f32 else None
+    check(_lib.lib().s2f_linear_attn(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
+                                     _ptr(ws), _ptr(out_s), _ptr(out_f), n, Nq, Nk, heads, d, int(q_ld or Cc),
+                                     int(kv_ld or Cc), float(out_scale), float(d_max), _stream()), "s2f_linear_attn")
+    return out_s, out_f
+
+
+def dcnv3_gather(x, offset, mask, *, n, H, W, G, Cg, K=3, offset_scale=1.0, mask_scale=1.0 / NORM):
+    """DCNv3 sampling core (dcnv3_core_pytorch, dcnv3_func.py:147-189)."""
+    out = torch.empty((n, H, W, G * Cg), dtype=torch.float32, device=x.device)
+    check(_lib.lib().s2f_dcnv3_gather(_ptr(x, torch.float32, "x"), _ptr(offset, torch.float32, "offset"),
+                                      _ptr(mask, torch.int8, "mask"), float(mask_scale), _ptr(out), n, H, W, G, Cg, K,
+                                      float(offset_scale), _stream()), "s2f_dcnv3_gather")
+    return out
+
+
+def upsample_add_lif(cur, prev, *, n, H, W, Hp, Wp, C_, want_f32=False, d_max=D_MAX):
+    out_s = torch.empty((n, H, W, C_), dtype=torch.int8, device=cur.device)
+    out_f = torch.empty((n, H, W, C_), dtype=torch.float32, device=cur.device) if want_f32 else None
+    check(_lib.lib().s2f_upsample_add_lif(_ptr(cur, torch.float32, "cur"), _ptr(prev, torch.float32, "prev"),
+                                          _ptr(out_s), _ptr(out_f), n, H, W, Hp, Wp, C_, float(d_max), _stream()),
+          "s2f_upsample_add_lif")
+    return out_s, out_f
+
+
+def sigmoid_lif(x, d_max=D_MAX):
+    out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    check(_lib.lib().s2f_sigmoid_lif(_ptr(x, torch.float32, "x"), _ptr(out), x.numel(), float(d_max), _stream()),
+          "s2f_sigmoid_lif")
+    return out
+
+
+def semantic_tail(mask_pred, cls, *, n, Q, K, h, w, H, W):
+    """softmax(cls)[..., :-1] x sigmoid(bilinear(mask_pred)) -> logits [n, K, H, W]."""
+    logits = torch.empty((n, K, H, W), dtype=torch.float32, device=cls.device)
+    prob = torch.empty((n, Q, K), dtype=torch.float32, device=cls.device)
+    check(_lib.lib().s2f_semantic_tail(_ptr(mask_pred, torch.float32, "mask_pred"), _ptr(cls, torch.float32, "cls"),
+                                       _ptr(logits), _ptr(prob), n, Q, K, h, w, H, W, _stream()), "s2f_semantic_tail")
+    return logits
