@@ -197,6 +197,7 @@ extern "C" int s2f_nilif_fwd(const float* x, const float* scale, const float* sh
                              int64_t residual_period, const float* v_in, float* v_out, int8_t* levels, float* y_norm,
                              int T, int64_t N, int C, float d_max, float norm, int transpose_rows, int transpose_cols,
                              unsigned long long* ties, void* stream) {
+  if (N == 0) return S2F_OK;
   S2F_REQUIRE(x && levels, "nilif_fwd: x and levels are required");
   S2F_REQUIRE(T >= 1 && N >= 0 && C >= 1, "nilif_fwd: bad T/N/C");
   S2F_REQUIRE((scale == nullptr) == (shift == nullptr), "nilif_fwd: scale and shift come together");

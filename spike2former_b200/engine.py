@@ -470,7 +470,7 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
         a, _, _ = ops.nilif(qf, transpose=(nq, dim))             # [C,nq] matrix stored as [nq(pos), C]
         a = pr.spike(k + ".ffn.fc1_spike", a, "reint_T")
         _, a = L[f"{i}.fc1"](a, n, nq, 1, spike=True)
-        a = pr.spike(k + ".ffn.fc2_spike", a.view(n, nq, -1), "ncl")
+        a = pr.spike(k + ".ffn.fc2_spike", a.view(n, nq, -1), "cm")
         r, _ = L[f"{i}.fc2"](a, n, nq, 1, f32=True, transposed=True)
         qf, _ = ops.affine_add_lif(r.view(n, nq, dim), None, qf, want_spike=False)
         qf = pr.real(k + ".out", qf, "same")

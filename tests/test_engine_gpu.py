@@ -52,3 +52,33 @@ def test_tiny_teacher_forced():
     agree = float((logits.argmax(1) == ref.argmax(1)).float().mean())
     print("argmax agreement", agree, "classes", ref.argmax(1).unique().numel())
     assert agree >= 0.999
+
+
+def test_ade20k_teacher_forced_512():
+    """The graded configuration (SDTv2 + DCN pixel decoder, ADE20K shape 512x512), unit-by-unit parity."""
+    cfg = s2f.configs.ade20k()
+    pr, logits, ref, taps = _run(cfg, 512, 512)
+    s = _report(pr)
+    assert s["unknown"] == []
+    assert s["neurons"] == 270 and s["spike_elems"] == 187913216       # SURVEY.md appendix A census
+    assert s["unexplained"] == 0 and s["maxdev"] <= 1
+    assert s["flips"] <= 1e-5 * s["spike_elems"]
+    assert s["worst_rel"] < 1e-4, s["worst_real"]
+    rel = float((logits - ref).abs().max() / ref.abs().max())
+    agree = float((logits.argmax(1) == ref.argmax(1)).float().mean())
+    ncls = ref.argmax(1).unique().numel()
+    print(f"ADE20K 512: logits rel err {rel:.3e}, argmax agreement {agree:.6f}, classes in oracle argmax {ncls}")
+    assert rel < 1e-2 and agree >= 0.999 and ncls >= 20
+
+
+def test_free_running_report():
+    """No forcing: reports how spike flips grow through the (chaotic, random-init) network."""
+    cfg = s2f.configs.tiny()
+    pr, logits, ref, taps = _run(cfg, 64, 64, force=False)
+    sp = [e for e in pr.log if e["kind"] == "spike" and "flips" in e]
+    first = sp[:12]
+    print("free-running flips per neuron (first 12):", [(e["name"].split(".")[-1], e["flips"]) for e in first])
+    print("free-running total flips", sum(e["flips"] for e in sp), "of", sum(e["numel"] for e in sp))
+    print("free-running logits rel err", float((logits - ref).abs().max() / ref.abs().max()))
+    assert torch.isfinite(logits).all()
+    assert sum(e["flips"] for e in sp[:4]) <= 4          # the first units still see identical inputs

@@ -1,0 +1,229 @@
+"""GPU parity of every C-ABI kernel against the oracle / a plain fp32 torch restatement, on seeded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import port
+from spike2former_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def gen(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def tie_vector():
+    """Every rounding tie inside the clamp range plus the values around the clamps."""
+    ties = [k + 0.5 for k in range(9)]
+    eps = [0.5 - 2 ** -24, 0.5 + 2 ** -23, 7.5 - 2 ** -21, 7.5 + 2 ** -21]
+    edge = [-0.0, 0.0, -1.0, 8.0, 8.25, 8.5, 9.0, 100.0, -100.0, 1e-30, 7.999999]
+    return torch.tensor(ties + eps + edge, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------------- NI-LIF
+@pytest.mark.parametrize("shape", [(16,), (4, 64, 256), (3, 1000), (1, 7, 360), (2, 33, 33, 20), (0,)])
+def test_nilif_bit_exact(shape):
+    x = torch.rand(shape, generator=gen(1)) * 12 - 2                       # U(-2, 10): both clamps
+    if x.numel() >= 32:
+        tv = tie_vector()
+        x.view(-1)[: tv.numel()] = tv
+    want = torch.round(torch.clamp(0.0 + x, 0, 8)).to(torch.int8)          # Q_IFNode after reset
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    got, _, y = ops.nilif(x.cuda(), want_norm=True, C_=max(1, shape[-1]), ties=cnt.view(torch.int64))
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(y.cpu(), want.float() / 8)                          # the reference's "/ 8" output
+    assert int(cnt.item()) == port.count_ties(x)
+
+
+def test_nilif_known_answers():
+    """SURVEY.md section 0.4 [probed]: Q_IFNode on [0.5,1.5,2.5,3.5,7.5] gives levels [0,2,2,4,8]."""
+    x = torch.tensor([0.5, 1.5, 2.5, 3.5, 7.5] + [0.0] * 11)
+    got, _, _ = ops.nilif(x.cuda())
+    assert got.cpu()[:5].tolist() == [0, 2, 2, 4, 8]
+
+
+@pytest.mark.parametrize("C,N", [(64, 64 * 50), (360, 360 * 9), (20, 20 * 7)])
+@pytest.mark.parametrize("d_max", [8.0, 4.0])
+def test_nilif_affine_residual(C, N, d_max):
+    g = gen(2)
+    x = torch.rand(N, generator=g) * 12 - 2
+    sc = torch.rand(C, generator=g) * 1.5 + 0.5
+    sh = torch.rand(C, generator=g) * 2 - 1
+    res = torch.randn(N, generator=g)
+    u = (x.view(-1, C) * sc + sh).view(-1) + res
+    want = torch.round(torch.clamp(u, 0, d_max)).to(torch.int8)
+    got, _, _ = ops.nilif(x.cuda(), scale=sc.cuda(), shift=sh.cuda(), residual=res.cuda(), C_=C, d_max=d_max)
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("T,shape", [(4, (65, 15, 511)), (3, (8, 256)), (2, (5, 7))])
+def test_nilif_multistep_membrane(T, shape):
+    """Multi-step generalisation: membrane carried in registers over T, soft reset (neuron.py:133-153).
+    Input pattern of neuron_kernel.py:1264-1310: (rand - 0.5) * 3, scaled up to reach several levels."""
+    x = (torch.rand((T,) + shape, generator=gen(3)) - 0.5) * 6
+    v0 = torch.rand(shape, generator=gen(4))
+    want, v_want = port.nilif_reference(x, v0=v0, T=T)
+    got, v, _ = ops.nilif(x.cuda(), v_in=v0.cuda(), want_v_out=True, T=T, C_=shape[-1])
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(v.cpu(), v_want)
+    # stateful across calls == one longer call (MemoryModule semantics, base.py:25-52)
+    g1, v1, _ = ops.nilif(x[:1].cuda(), v_in=v0.cuda(), want_v_out=True, T=1, C_=shape[-1])
+    g2, v2, _ = ops.nilif(x[1:].cuda(), v_in=v1, want_v_out=True, T=T - 1, C_=shape[-1])
+    assert torch.equal(torch.cat([g1, g2]).cpu(), want) and torch.equal(v2.cpu().view_as(v_want), v_want)
+
+
+def test_nilif_positional_broadcast_and_transpose():
+    g = gen(5)
+    n, N, C = 3, 40, 32
+    x = torch.randn(n, N, C, generator=g) * 3
+    pos = torch.randn(N, C, generator=g)
+    lvl = torch.randn(C, generator=g)
+    want = torch.round(torch.clamp((x + lvl) + pos, 0, 8)).to(torch.int8)
+    got, _, _ = ops.nilif(x.cuda(), scale=torch.ones(C).cuda(), shift=lvl.cuda(), residual=pos.cuda(),
+                          residual_period=pos.numel())
+    assert torch.equal(got.cpu(), want)
+    # MSDA_FFN's reinterpreting reshape (mmcv_spike/transformer.py:777): [n,nq,C] read as [n,C,nq], stored transposed
+    s = torch.round(torch.clamp(x, 0, 8)).to(torch.int8)
+    want_t = s.reshape(n, C, N).permute(0, 2, 1).contiguous()
+    got_t, _, _ = ops.nilif(x.cuda(), transpose=(N, C))
+    assert torch.equal(got_t.cpu().view(n, N, C), want_t)
+
+
+def test_nilif_backward_ste():
+    """quant.backward (surrogate.py:531-538) through the reference's own autograd graph."""
+    g = gen(6)
+    x = (torch.rand(4096, generator=g) * 12 - 2).requires_grad_(True)
+    x.data[:4] = torch.tensor([0.0, 8.0, -1e-6, 8.000001])
+    gy = torch.randn(4096, generator=g)
+
+    class Q(torch.autograd.Function):            # restatement of `quant`
+        @staticmethod
+        def forward(ctx, i):
+            ctx.save_for_backward(i)
+            return torch.round(torch.clamp(i, 0, 8))
+
+        @staticmethod
+        def backward(ctx, go):
+            (i,) = ctx.saved_tensors
+            gi = go.clone()
+            gi[i < 0] = 0
+            gi[i > 8] = 0
+            return gi
+
+    (Q.apply(x) / 8).backward(gy)
+    got = ops.nilif_bwd(x.detach().cuda(), gy.cuda(), C_=1)
+    assert torch.equal(got.cpu(), x.grad)
+
+
+# --------------------------------------------------------------------------------------------- conv / linear
+def _levels(shape, g, hi=9):
+    return torch.randint(0, hi, shape, generator=g, dtype=torch.int8)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", [(32, 64, 1, 1, 16, 16), (16, 48, 3, 1, 12, 20), (32, 64, 3, 2, 16, 16),
+                                                   (360, 100, 1, 1, 8, 8), (3, 32, 7, 2, 32, 32), (20, 20, 1, 1, 5, 1)])
+def test_conv_simt_vs_torch(cin, cout, k, stride, H, W):
+    g = gen(7)
+    n = 2
+    real_input = cin == 3
+    a = torch.randn(n, H, W, cin, generator=g) if real_input else _levels((n, H, W, cin), g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    sc = torch.rand(cout, generator=g) + 0.5
+    sh = torch.randn(cout, generator=g)
+    pad = (k - 1) // 2
+    xin = (a.float() if real_input else a.float() / 8).permute(0, 3, 1, 2)
+    ref = F.conv2d(xin.double(), w.double(), stride=stride, padding=pad) * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)
+    Ho, Wo = ref.shape[-2:]
+    res = torch.randn(n, Ho, Wo, cout, generator=g)
+    ref = ref.permute(0, 2, 3, 1) + res.double()
+    w2d = ops.pad_rows4(w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda())
+    of, os_ = ops.conv_simt(a.cuda(), w2d, n=n, H=H, W=W, Cin=cin, Cout=cout, k=k, stride=stride, pad=pad,
+                            scale=sc.cuda(), shift=sh.cuda(), residual=res.cuda(), want_f32=True, want_spike=True)
+    err = (of.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), err
+    # spikes are the NI-LIF of the kernel's own fp32 output, bit for bit
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+    # transposed (channel-major) store
+    oft, _ = ops.conv_simt(a.cuda(), w2d, n=n, H=H, W=W, Cin=cin, Cout=cout, k=k, stride=stride, pad=pad,
+                           scale=sc.cuda(), shift=sh.cuda(), want_f32=True, transposed=True)
+    of2, _ = ops.conv_simt(a.cuda(), w2d, n=n, H=H, W=W, Cin=cin, Cout=cout, k=k, stride=stride, pad=pad,
+                           scale=sc.cuda(), shift=sh.cuda(), want_f32=True)
+    assert torch.equal(oft.cpu().view(n, cout, Ho * Wo).permute(0, 2, 1), of2.cpu().view(n, Ho * Wo, cout))
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+@pytest.mark.parametrize("spike_in", [True, False])
+def test_dwconv_vs_torch(k, spike_in):
+    g = gen(8)
+    n, H, W, C = 2, 19, 23, 24
+    a = _levels((n, H, W, C), g) if spike_in else torch.randn(n, H, W, C, generator=g)
+    w = torch.randn(C, 1, k, k, generator=g) / k
+    sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    xin = (a.float() / 8 if spike_in else a).permute(0, 3, 1, 2)
+    ref = F.conv2d(xin.double(), w.double(), padding=(k - 1) // 2, groups=C) * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)
+    w_tap = w.reshape(C, k * k).t().contiguous().cuda()
+    of, os_ = ops.dwconv(a.cuda(), w_tap, n=n, H=H, W=W, C_=C, k=k, scale=sc.cuda(), shift=sh.cuda(), want_f32=True,
+                         want_spike=True)
+    assert (of.cpu().double() - ref.permute(0, 2, 3, 1)).abs().max().item() < 2e-5
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+
+
+@pytest.mark.parametrize("n,Nq,Nk,heads,d", [(2, 64, 64, 4, 16), (1, 20, 300, 4, 16), (2, 100, 1024, 8, 32), (1, 64, 64, 8, 45)])
+def test_linear_attn_exact(n, Nq, Nk, heads, d):
+    """(Q K^T) V == Q (K^T V) on integer levels; compared with the reference's op order in float64."""
+    g = gen(9)
+    C = heads * d
+    q, k, v = _levels((n, Nq, C), g), _levels((n, Nk, C), g), _levels((n, Nk, C), g)
+    scale = d ** -0.5 / 512
+    hs = lambda t, N: t.double().view(n, N, heads, d).permute(0, 2, 1, 3)
+    kv = hs(k, Nk).transpose(-2, -1) @ hs(v, Nk)
+    ref = (hs(q, Nq) @ kv).permute(0, 2, 1, 3).reshape(n, Nq, C) * scale
+    os_, of = ops.linear_attn(q.cuda(), k.cuda(), v.cuda(), n=n, Nq=Nq, Nk=Nk, heads=heads, d=d, out_scale=scale,
+                              want_f32=True)
+    assert (of.cpu().double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+
+
+@pytest.mark.parametrize("n,H,W,G,Cg", [(2, 8, 8, 4, 16), (1, 32, 32, 32, 8), (2, 5, 9, 8, 8)])
+def test_dcnv3_gather_vs_reference_core(n, H, W, G, Cg):
+    """Pattern of ops_dcnv3/test.py:33-60 (seed 3, inputs*0.01, offsets*10, K=3, pad 1), fp32 tolerance of that
+    file (rtol 1e-2 / atol 1e-3) tightened to 1e-5; the oracle is the port of dcnv3_core_pytorch."""
+    g = gen(3)
+    K = 3
+    x = torch.rand(n, H, W, G * Cg, generator=g) * 0.01
+    off = torch.rand(n, H, W, G * K * K * 2, generator=g) * 10 - 5
+    mask = _levels((n, H, W, G * K * K), g)
+    for os_ in (1.0, 2.0):
+        ref = port.dcnv3_core(x, off, mask.float() / 8, K, 1, 1, 1, G, Cg, os_)
+        got = ops.dcnv3_gather(x.cuda(), off.cuda(), mask.cuda(), n=n, H=H, W=W, G=G, Cg=Cg, K=K, offset_scale=os_)
+        assert (got.cpu() - ref).abs().max().item() < 1e-5 * max(ref.abs().max().item(), 1e-3)
+
+
+def test_upsample_add_lif_vs_torch():
+    g = gen(10)
+    n, C, Hp, Wp = 2, 16, 6, 10
+    prev = torch.randn(n, Hp, Wp, C, generator=g) * 3
+    cur = torch.randn(n, 2 * Hp, 2 * Wp, C, generator=g) * 3
+    up = F.interpolate(prev.permute(0, 3, 1, 2), size=(2 * Hp, 2 * Wp), mode="bilinear", align_corners=False)
+    ref = cur + up.permute(0, 2, 3, 1)
+    sp, f = ops.upsample_add_lif(cur.cuda(), prev.cuda(), n=n, H=2 * Hp, W=2 * Wp, Hp=Hp, Wp=Wp, C_=C, want_f32=True)
+    assert (f.cpu() - ref).abs().max().item() < 1e-5
+    assert torch.equal(sp.cpu(), torch.round(torch.clamp(f.cpu(), 0, 8)).to(torch.int8))
+
+
+def test_semantic_tail_vs_torch():
+    g = gen(11)
+    n, Q, K, h, w = 2, 20, 11, 12, 16
+    mp = torch.randn(n, Q, h, w, generator=g) * 3
+    cls = torch.randn(n, Q, K + 1, generator=g) * 4
+    up = F.interpolate(mp, size=(2 * h, 2 * w), mode="bilinear", align_corners=False)
+    ref = torch.einsum("bqc,bqhw->bchw", F.softmax(cls, -1)[..., :-1], up.sigmoid())
+    got = ops.semantic_tail(mp.permute(0, 2, 3, 1).contiguous().cuda(), cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=2 * h,
+                            W=2 * w)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(RuntimeError):
+        ops.nilif(torch.zeros(16))
