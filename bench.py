@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""bench.py -- Spike2Former 512x512 batch-sharded inference on N B200s (BASELINE.json metric: imgs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One "step" = one forward pass of the whole hot path (SDTv2 backbone + DCN pixel decoder + MaskFormer
+head -> seg logits [B,150,512,512]) over one batch of B synthetic 512x512 images per GPU.
+  value : whole-job images/s with the input batches already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the public API with HOST buffers: pinned fp32 images -> H2D -> forward ->
+          argmax label map (uint8) -> D2H, every step, inside the timed region
+  roofline : the dominant kernel class (spike GEMM / conv) timed live with CUDA events on the launch stream
+  cpu_baseline : the oracle port (CPU restatement of the reference, pinned bit-exact to it) on this box's host
+          cores over a bounded sample, rank 0, N=1 only
+`--impl reference` times that CPU path alone with the same JSON contract.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H = W = 512
+WORKLOAD = "Spike2Former SDTv2 + DCN pixel decoder, ADE20K-shape 512x512 inference (150 classes, 100 queries)"
+ALG_GFLOP_PER_IMG = 131.0      # 142 GFLOP minus the six discarded mask einsums (inference uses [-1])
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        return dict(sm_mhz=statistics.median(self.samples) if self.samples else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(steps, warmup):
+    """The reference's CPU implementation of the path: oracle/port.py (bit-exact restatement, see tests/golden)."""
+    from oracle import port
+    from spike2former_b200 import configs, synth
+
+    cfg = configs.ade20k()
+    P = synth.synthetic_checkpoint("ade20k", cfg)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3, H, W, generator=g)
+    with torch.no_grad():
+        for _ in range(warmup):
+            port.predict(port.Ctx(P), cfg, x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            port.predict(port.Ctx(P), cfg, x)
+        dt = time.perf_counter() - t0
+    return dict(value=steps / dt, unit="images/s", cores=cores, kind="port",
+                sample=f"{steps} forwards of one 512x512 image (batch 1), fp32, torch CPU {torch.__version__}, "
+                       f"{cores} threads, after {warmup} warm-up"), dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+        cb, ms = cpu_reference_run(steps, warm)
+        print(json.dumps({
+            "impl": "reference", "metric": "images_per_second", "value": cb["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": 1, "device": "host CPU"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    import spike2former_b200 as s2f
+    from spike2former_b200 import engine, ops, synth
+
+    cfg = s2f.configs.ade20k()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint("ade20k", cfg), strict=True)
+    seg = seg.to(dev)
+    B = args.batch
+    NBUF = 4                                   # rotate input batches: 4 x B x 3 MB > L2 for B >= 12; the per-step
+    g = torch.Generator().manual_seed(1000 + rank)   # working set (GBs of activations) thrashes L2 anyway
+    host = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(NBUF)]
+    devin = [h.to(dev) for h in host]
+    host_out = torch.empty(B, H, W, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        with torch.no_grad():
+            return seg.encode_decode(devin[i % NBUF])
+
+    def step_e2e(i):
+        with torch.no_grad():
+            x = host[i % NBUF].to(dev, non_blocking=True)
+            labels = seg.predict_labels(x).to(torch.uint8)
+            host_out.copy_(labels, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return host_out
+
+    # ------------------------------------------------------------------ device-resident timing
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ------------------------------------------------------------------ end-to-end (host buffers) timing
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel class
+    roof = engine.profile_dominant(seg, devin[0], steps=min(args.steps, 3)) if rank == 0 else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    out = {
+        "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": roof["dtype"] if roof else "int8xf32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
+                   "weights": "seeded random init + shipped calibration statistics (spike2former_b200/synth.py)",
+                   "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2",
+                   "alg_gflop_per_image": ALG_GFLOP_PER_IMG},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
+                "d2h_bytes_per_step": B * H * W},
+        "gpu_launches": int(launches),
+        "model_tflops": value * ALG_GFLOP_PER_IMG / 1e3,
+    }
+    if roof:
+        peak = pk["bf16_sustained"] if roof["bound"] == "tensor" else pk["hbm"]
+        out["roofline"] = {"bound": roof["bound"], "achieved": roof["achieved"], "peak": peak, "unit": roof["unit"],
+                           "frac": roof["achieved"] / peak, "traffic": None, "kernel": roof["kernel"],
+                           "share_of_step": roof["share"], "launches_per_step": roof["launches"],
+                           "peak_source": pk["src"] + (" bf16 sustained (inside a long step)" if roof["bound"] == "tensor" else " copy"),
+                           "per_class_ms": roof["per_class_ms"]}
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_reference_run(6, 1)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -542,6 +542,34 @@ def head_predict(model, x, img_shape, probe=NOPROBE):
     return _predict_from(model, feats, img_shape, probe)
 
 
+HBM_CLASSES = ("nilif", "dwconv", "dcn_gather", "upsample_add_lif", "elementwise", "linear_attn")
+
+
+def profile_dominant(seg, img, steps=2):
+    """Time every launch of `steps` forwards with CUDA events on the launch stream and report the kernel
+    class that takes the largest share of the step (bench.py's `roofline` object)."""
+    prof = ops.Profiler()
+    with torch.no_grad():
+        segmentor_logits(seg, img)                      # warm
+        torch.cuda.synchronize()
+        ops.set_profiler(prof)
+        try:
+            for _ in range(steps):
+                segmentor_logits(seg, img)
+        finally:
+            ops.set_profiler(None)
+    agg = prof.summary()
+    total = sum(a["ms"] for a in agg.values())
+    name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    tensor = name.startswith("gemm") or name == "semantic_tail"
+    sec = top["ms"] / 1e3
+    return dict(kernel=name, bound="tensor" if tensor else "hbm",
+                achieved=(top["flops"] / sec / 1e12) if tensor else (top["bytes"] / sec / 1e9),
+                unit="TFLOP/s" if tensor else "GB/s", share=top["ms"] / total, launches=top["launches"] // steps,
+                dtype="f32 (int8 spikes x fp32 weights)" if name == "gemm_simt" else "int8 spikes x int8 weight digits",
+                per_class_ms={k: round(v["ms"] / steps, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])})
+
+
 def segmentor_logits(seg, img, probe=NOPROBE):
     """EncoderDecoder.encode_decode (encoder_decoder.py:125-133): internal tensors go straight to the head."""
     if seg.backbone.T != 1:

@@ -37,6 +37,49 @@ def launch_count() -> int:
     return int(_lib.lib().s2f_launch_count())
 
 
+class Profiler:
+    """Per-launch CUDA-event timing on the launch stream, grouped by kernel class (bench.py's roofline)."""
+
+    def __init__(self):
+        self.records = []          # (class, ev0, ev1, alg_flops, alg_bytes)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for cls, e0, e1, fl, by in self.records:
+            a = agg.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            a["ms"] += e0.elapsed_time(e1); a["flops"] += fl; a["bytes"] += by; a["launches"] += 1
+        return agg
+
+
+_PROF = None
+
+
+def set_profiler(p):
+    global _PROF
+    _PROF = p
+
+
+def _p0():
+    if _PROF is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _p1(e0, cls, flops=0.0, nbytes=0.0):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    _PROF.records.append((cls, e0, e1, float(flops), float(nbytes)))
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 # ------------------------------------------------------------------------------------------ NI-LIF
 def nilif(x, scale=None, shift=None, residual=None, residual_period=0, v_in=None, want_v_out=False, want_norm=False,
           T=1, C_=None, d_max=D_MAX, norm=NORM, transpose=None, ties=None, out=None):
@@ -53,11 +96,13 @@ def nilif(x, scale=None, shift=None, residual=None, residual_period=0, v_in=None
     v_out = torch.empty(x.shape[1:] if T > 1 else x.shape, dtype=torch.float32, device=x.device) if want_v_out else None
     y = torch.empty_like(x) if want_norm else None
     tr, tc = (transpose if transpose else (0, 0))
+    e0 = _p0()
     check(_lib.lib().s2f_nilif_fwd(_ptr(x), _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
                                    _ptr(residual, torch.float32, "residual"), int(residual_period),
                                    _ptr(v_in, torch.float32, "v_in"), _ptr(v_out), _ptr(levels, torch.int8, "levels"),
                                    _ptr(y), int(T), int(N), C_, float(d_max), float(norm), int(tr), int(tc),
                                    _ptr(ties), _stream()), "s2f_nilif_fwd")
+    _p1(e0, "nilif", 0, _nb(x, levels, v_in, v_out, y) + (x.numel() * 4 if residual is not None else 0))
     return levels, v_out, y
 
 
@@ -74,9 +119,11 @@ def nilif_bwd(x, gy, scale=None, shift=None, residual=None, C_=None, d_max=D_MAX
 def affine_add_lif(x, scale=None, residual=None, want_f32=True, want_spike=True, d_max=D_MAX):
     out_f = torch.empty_like(x) if want_f32 else None
     out_s = torch.empty(x.shape, dtype=torch.int8, device=x.device) if want_spike else None
+    e0 = _p0()
     check(_lib.lib().s2f_affine_add_lif(_ptr(x, torch.float32, "x"), _ptr(scale, torch.float32, "scale"),
                                         _ptr(residual, torch.float32, "residual"), _ptr(out_f), _ptr(out_s),
                                         x.numel(), int(x.shape[-1]), float(d_max), _stream()), "s2f_affine_add_lif")
+    _p1(e0, "elementwise", 0, _nb(x, residual, out_f, out_s))
     return out_f, out_s
 
 
@@ -116,7 +163,9 @@ def conv_simt(a, w, *, n, H, W, Cin, Cout, k=1, stride=1, pad=0, scale=None, shi
     args.stride, args.pad = stride, pad
     args.a_img_stride, args.a_stride_m, args.a_stride_k = int(a_img_stride), int(a_stride_m), int(a_stride_k)
     args.w_img_stride, args.d_max = int(w_img_stride), float(d_max)
+    e0 = _p0()
     check(_lib.lib().s2f_conv_simt(C.byref(args), _stream()), "s2f_conv_simt")
+    _p1(e0, "gemm_simt", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * 4)
     return out_f32, out_spike
 
 
@@ -128,10 +177,12 @@ def dwconv(a, w_tap, *, n, H, W, C_, k, scale=None, shift=None, a_scale=1.0 / NO
     Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
     out_f = torch.empty((n, Ho, Wo, C_), dtype=torch.float32, device=a.device) if want_f32 else None
     out_s = torch.empty((n, Ho, Wo, C_), dtype=torch.int8, device=a.device) if want_spike else None
+    e0 = _p0()
     check(_lib.lib().s2f_dwconv(_ptr(a, name="a"), int(is_spike), float(a_scale), _ptr(w_tap, torch.float32, "w_tap"),
                                 _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"), None,
                                 _ptr(out_f), _ptr(out_s), n, H, W, C_, k, int(no_pad), float(d_max), _stream()),
           "s2f_dwconv")
+    _p1(e0, "dwconv", 2.0 * n * Ho * Wo * C_ * k * k, _nb(a, out_f, out_s))
     return out_f, out_s
 
 
@@ -145,34 +196,42 @@ def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=Non
     ws = torch.empty((n, heads, d, d), dtype=torch.int32, device=q.device)
     out_s = torch.empty((n, Nq, Cc), dtype=torch.int8, device=q.device)
     out_f = torch.empty((n, Nq, Cc), dtype=torch.float32, device=q.device) if want_f32 else None
+    e0 = _p0()
     check(_lib.lib().s2f_linear_attn(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
                                      _ptr(ws), _ptr(out_s), _ptr(out_f), n, Nq, Nk, heads, d, int(q_ld or Cc),
                                      int(kv_ld or Cc), float(out_scale), float(d_max), _stream()), "s2f_linear_attn")
+    _p1(e0, "linear_attn", 2.0 * n * heads * d * d * (Nq + Nk), n * (Nq + 2 * Nk) * Cc + _nb(out_s, out_f))
     return out_s, out_f
 
 
 def dcnv3_gather(x, offset, mask, *, n, H, W, G, Cg, K=3, offset_scale=1.0, mask_scale=1.0 / NORM):
     """DCNv3 sampling core (dcnv3_core_pytorch, dcnv3_func.py:147-189)."""
     out = torch.empty((n, H, W, G * Cg), dtype=torch.float32, device=x.device)
+    e0 = _p0()
     check(_lib.lib().s2f_dcnv3_gather(_ptr(x, torch.float32, "x"), _ptr(offset, torch.float32, "offset"),
                                       _ptr(mask, torch.int8, "mask"), float(mask_scale), _ptr(out), n, H, W, G, Cg, K,
                                       float(offset_scale), _stream()), "s2f_dcnv3_gather")
+    _p1(e0, "dcn_gather", 0, _nb(x, offset, mask, out))
     return out
 
 
 def upsample_add_lif(cur, prev, *, n, H, W, Hp, Wp, C_, want_f32=False, d_max=D_MAX):
     out_s = torch.empty((n, H, W, C_), dtype=torch.int8, device=cur.device)
     out_f = torch.empty((n, H, W, C_), dtype=torch.float32, device=cur.device) if want_f32 else None
+    e0 = _p0()
     check(_lib.lib().s2f_upsample_add_lif(_ptr(cur, torch.float32, "cur"), _ptr(prev, torch.float32, "prev"),
                                           _ptr(out_s), _ptr(out_f), n, H, W, Hp, Wp, C_, float(d_max), _stream()),
           "s2f_upsample_add_lif")
+    _p1(e0, "upsample_add_lif", 0, _nb(cur, prev, out_s, out_f))
     return out_s, out_f
 
 
 def sigmoid_lif(x, d_max=D_MAX):
     out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    e0 = _p0()
     check(_lib.lib().s2f_sigmoid_lif(_ptr(x, torch.float32, "x"), _ptr(out), x.numel(), float(d_max), _stream()),
           "s2f_sigmoid_lif")
+    _p1(e0, "elementwise", 0, _nb(x, out))
     return out
 
 
@@ -180,6 +239,8 @@ def semantic_tail(mask_pred, cls, *, n, Q, K, h, w, H, W):
     """softmax(cls)[..., :-1] x sigmoid(bilinear(mask_pred)) -> logits [n, K, H, W]."""
     logits = torch.empty((n, K, H, W), dtype=torch.float32, device=cls.device)
     prob = torch.empty((n, Q, K), dtype=torch.float32, device=cls.device)
+    e0 = _p0()
     check(_lib.lib().s2f_semantic_tail(_ptr(mask_pred, torch.float32, "mask_pred"), _ptr(cls, torch.float32, "cls"),
                                        _ptr(logits), _ptr(prob), n, Q, K, h, w, H, W, _stream()), "s2f_semantic_tail")
+    _p1(e0, "semantic_tail", 2.0 * n * H * W * Q * K, _nb(mask_pred, logits))
     return logits

@@ -1,0 +1,97 @@
+"""CPU: drop-in boundary (registry, constructor keys, state_dict names), host-side folding, C ABI exports."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import spike2former_b200 as s2f
+from oracle import port
+from spike2former_b200 import _lib, fold, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_builds_reference_config_names():
+    cfg = s2f.configs.ade20k()
+    seg = s2f.MODELS.build({k: v for k, v in cfg.items() if k != "data_preprocessor"})
+    assert type(seg.backbone).__name__ == "Spiking_vit_MetaFormer"
+    assert type(seg.decode_head).__name__ == "MaskFormerHead"
+    assert type(seg.decode_head.pixel_decoder).__name__ == "DCNTransformerEncoderPixelDecoder"
+    assert "mmdet.DCNTransformerEncoderPixelDecoder" in s2f.MODELS
+    assert (seg.align_corners, seg.num_classes, seg.out_channels) == (False, 150, 150)   # encoder_decoder.py:104-106
+    n_params = sum(p.numel() for p in seg.parameters())
+    assert n_params == 34361112                                                           # 34.36 M
+    assert len(seg.backbone.state_dict()) == 823
+
+
+def test_state_dict_names_cover_reference_checkpoint_keys():
+    """golden_tiny.pt's calibration keys were written from the REFERENCE's own state_dict names."""
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "golden_tiny.pt"))
+    seg = s2f.build_segmentor(s2f.configs.tiny())
+    sd = seg.state_dict()
+    assert set(g["calib"]) <= set(sd)
+    seg.load_state_dict(synth.random_state(s2f.configs.tiny()), strict=True)
+
+
+def test_error_conventions():
+    with pytest.raises(AssertionError):                       # sdtv2.py:271-273
+        s2f.Spiking_vit_MetaFormer(embed_dim=[64, 128, 250, 360], num_heads=8, mlp_ratios=4, in_channels=3)
+    cfg = s2f.configs.tiny()
+    cfg["decode_head"]["pixel_decoder"]["encoder"]["layer_cfg"]["self_attn_cfg"]["group"] = 7
+    with pytest.raises(ValueError):                           # dcnv3.py:125-127
+        s2f.build_segmentor(cfg)
+    seg = s2f.build_segmentor(s2f.configs.tiny())
+    with pytest.raises(RuntimeError):                         # no CPU path
+        seg.encode_decode(torch.zeros(1, 3, 64, 64))
+    for m in seg.modules():                                   # ResetModelHook duck-typing (resetmodel_hook.py:17-37)
+        if hasattr(m, "reset"):
+            m.reset()
+    names = dict(seg.named_modules())
+    assert "backbone.block3.0.attn.q_spike" in names and "decode_head.pixel_decoder.mask_feature_spike" in names
+
+
+def test_bn_fold_and_repconv_reparameterisation_match_the_oracle():
+    """fold.repconv_dense3x3: conv1x1 -> BN+pad -> dw3x3 -> conv1x1 -> BN -> BN == ONE dense 3x3 (zero pad)."""
+    cfg = s2f.configs.tiny()
+    P = synth.synthetic_checkpoint("tiny", cfg)
+    key = "backbone.block3.0.attn.q_conv"
+    c = P[key + ".1.weight"].numel()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 9, (2, c, 9, 7), generator=g).float() / 8
+    ref = port.rep_conv(port.Ctx(P), key, x)
+    sd = {k[len("backbone."):]: v for k, v in P.items() if k.startswith("backbone.")}
+    wm, b = fold.repconv_dense3x3(sd, key[len("backbone."):])
+    w = wm.reshape(c, 3, 3, c).permute(0, 3, 1, 2)
+    got = F.conv2d(x.double(), w, b, padding=1)
+    assert (got - ref.double()).abs().max() < 2e-5 * ref.abs().max()
+    # plain conv + BN fold
+    s, t = fold.conv_bn(sd, "downsample2.encode_conv", "downsample2.encode_bn")
+    xin = torch.randn(1, sd["downsample2.encode_conv.weight"].shape[1], 8, 8, generator=g)
+    ref = port.downsample(port.Ctx(P), "backbone.downsample2", xin, 2, 1, True)
+    got = F.conv2d(xin.double(), sd["downsample2.encode_conv.weight"].double(), None, 2, 1) * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)
+    assert (got - ref.double()).abs().max() < 1e-5 * ref.abs().max()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "s2f.h")).read()
+    declared = set(re.findall(r"S2F_API\s+[\w\s\*]+?\b(s2f_\w+)\s*\(", hdr))
+    assert len(declared) >= 14
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert os.path.exists(_lib.LIB_PATH), "libs2f.so not built: run __graft_entry__.build()"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    lib = _lib.lib()                       # loads, sets signatures, checks the ABI version; no compute call
+    assert lib.s2f_abi_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.ConvArgs) == 144 or ctypes.sizeof(_lib.ConvArgs) > 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "spike2former_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn

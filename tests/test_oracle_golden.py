@@ -1,0 +1,94 @@
+"""CPU: the oracle port against fixtures produced by THE REFERENCE ITSELF (tests/golden/make_golden.py)."""
+import os
+
+import pytest
+import torch
+
+from oracle import port, ref_loader, weights
+from spike2former_b200 import configs, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _state_from(cfg, calib, gain):
+    P = synth.random_state(cfg)
+    calib = dict(calib)
+    calib[synth.CALIBRATED_EXTRA[2]] = torch.tensor(gain)
+    return synth.apply_calibration(P, calib)
+
+
+def test_neuron_known_answers_from_reference_qifnode():
+    """golden_nilif.pt holds outputs of the reference's Q_IFNode(Quant()) incl. a second, stateful call."""
+    g = torch.load(os.path.join(GOLD, "golden_nilif.pt"))
+    x = g["x"]
+    cx = port.Ctx({})
+    assert torch.equal(port.lif(cx, "n", x), g["y1"])
+    assert (g["y1"][:9] * 8).tolist() == [0, 2, 2, 4, 4, 6, 6, 8, 8]     # k+0.5 ties round half to even
+    lv, v = port.nilif_reference(torch.stack([x, x]), T=2)               # membrane carried over two steps
+    assert torch.equal(lv[0].float() / 8, g["y1"]) and torch.equal(lv[1].float() / 8, g["y2"])
+    assert torch.equal(v, g["v2"])
+
+
+def test_port_matches_reference_golden_tiny():
+    g = torch.load(os.path.join(GOLD, "golden_tiny.pt"))
+    cfg = configs.tiny()
+    P = _state_from(cfg, g["calib"], g["mask_gain"])
+    seen = {}
+    cx = port.Ctx(P, tap=lambda n, x, s: seen.__setitem__(n, s.to(torch.int8)))
+    with torch.no_grad():
+        logits = port.predict(cx, cfg, weights.test_image(cfg, 64, 64))
+    assert set(seen) == set(g["levels"])
+    flips = sum(int((seen[n].reshape(-1) != g["levels"][n].reshape(-1)).sum()) for n in seen)
+    total = sum(v.numel() for v in seen.values())
+    # identical on the build container's CPU; a different host ISA may reorder oneDNN sums (a few near-tie flips)
+    assert flips <= 1e-4 * total, (flips, total)
+    if flips == 0:
+        assert torch.equal(logits, g["logits"])
+    assert (logits - g["logits"]).abs().max() <= 1e-2 * g["logits"].abs().max()
+
+
+def test_port_matches_reference_golden_ade20k_512():
+    """The graded config: all 270 neurons' checksums (sum of levels, non-zeros, exact ties) + a logits crop."""
+    g = torch.load(os.path.join(GOLD, "golden_ade20k.pt"))
+    cfg = configs.ade20k()
+    P = synth.synthetic_checkpoint("ade20k", cfg)
+    got = {}
+    cx = port.Ctx(P, tap=lambda n, x, s: got.__setitem__(n, (int(s.sum()), int((s > 0).sum()), port.count_ties(x), tuple(x.shape))))
+    with torch.no_grad():
+        logits = port.predict(cx, cfg, weights.test_image(cfg, 512, 512))
+    assert len(got) == 270 and cx.elems == 187913216                     # SURVEY.md appendix A census
+    assert set(got) == set(g["checks"])
+    import math
+    exact = all(got[n][:3] == tuple(g["checks"][n][:3]) for n in got)
+    # the reference keeps [T,B,...]; the port flattens T*B: same element count, same order
+    assert all(math.prod(got[n][3]) == math.prod(g["checks"][n][3]) for n in got)
+    if exact:
+        assert torch.equal(logits[:, :, 224:288, 224:288], g["logits_crop"])
+        assert torch.equal(torch.bincount(logits.argmax(1).flatten(), minlength=150), g["argmax_hist"])
+    else:   # other host ISA: the network is chaotic, so only the early layers are comparable
+        first = list(g["checks"])[:8]
+        for n in first:
+            assert abs(got[n][0] - g["checks"][n][0]) <= 1e-4 * max(1, g["checks"][n][0])
+    assert int((g["argmax_hist"] > 0).sum()) >= 20                       # the argmax check is not vacuous
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present")
+def test_port_bit_exact_against_live_reference_tiny():
+    cfg = configs.tiny()
+    P = weights.calibrated_state(cfg, 64, 64)
+    bb, hd = ref_loader.build_reference(cfg)
+    bb.load_state_dict({k[9:]: v for k, v in P.items() if k.startswith("backbone.")}, strict=True)
+    hd.load_state_dict({k[12:]: v for k, v in P.items() if k.startswith("decode_head.")}, strict=True)
+    img = weights.test_image(cfg, 64, 64, batch=2)
+    tap = ref_loader.SpikeTap(bb, hd)
+    ref = ref_loader.reference_predict(bb, hd, img)
+    tap.close()
+    recs = []
+    with torch.no_grad():
+        out = port.predict(port.Ctx(P, tap=lambda n, x, s: recs.append((n, x, s))), cfg, img)
+    assert [r[0] for r in recs] == [r[0] for r in tap.records]
+    for (n, x, s), (_, xr, orf) in zip(recs, tap.records):
+        assert torch.equal(x.reshape(-1), xr.reshape(-1)), n
+        assert torch.equal(s.reshape(-1), (orf * 8).reshape(-1)), n
+    assert torch.equal(out, ref)
