@@ -92,23 +92,29 @@ typedef struct {
 
 S2F_API int s2f_conv_simt(const s2f_conv_args* args, void* stream);
 
-/* tcgen05 / TMEM / TMA spike GEMM (sm_100a): A int8 levels [n,H,W,Cin]; W pre-packed by
- * s2f_pack_weights_i8 into `pieces` int8 digit planes with a per-output-channel scale (exact int32
- * accumulation); same epilogue as s2f_conv_simt.  KH=KW in {1,3}, stride in {1,2}. */
+/* tcgen05 / TMEM / TMA spike GEMM (sm_100a).  A: int8 levels [n,H,W,Cin] channels-last (Cin >= 32, Cin % 16 == 0).
+ * w_packed: the layer's fp32 weights split by s2f_pack_weights_i8 into `pieces` signed base-128 int8 digit planes;
+ * one tcgen05.mma.kind::i8 (M=128, N=64*pieces, K=32) accumulates all planes exactly in int32 (TMEM) and the epilogue
+ * recombines them: acc = sum_p plane_p * 128^(pieces-1-p).  Then, as in s2f_conv_simt,
+ *   y = acc * scale[co] + shift[co] + residual ; out_f32 = y ; out_spike = rint(clamp(y, 0, d_max)).
+ * `scale[co]` must already contain the packer's w_rowscale[co] and the spike normaliser (1/8), both powers of two,
+ * besides the folded BatchNorm scale.  KH=KW in {1,3}; stride in {1,2}; out_transposed as in s2f_conv_simt. */
 typedef struct {
-  const int8_t* a; const int8_t* w_packed; const float* w_rowscale;
+  const int8_t* a; const int8_t* w_packed;
   const float* scale; const float* shift; const float* residual;
   float* out_f32; int8_t* out_spike; int out_transposed;
   int n, H, W, Cin, Cout, KH, KW, stride, pad, pieces;
-  float a_scale, d_max;
+  float d_max;
 } s2f_gemm_tc_args;
 
 S2F_API int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream);
 
-/* Host-side helper (no GPU work): split fp32 weights [Cout, K] into `pieces` signed base-128 digit
- * planes laid out [tile][piece][row][K] for the kernel; writes rowscale[Cout].  Returns bytes needed
- * when w_packed == NULL. */
-S2F_API int64_t s2f_pack_weights_i8(const float* w, int Cout, int K, int pieces, int8_t* w_packed, float* w_rowscale);
+/* Host-side helper (no GPU work): split fp32 weights [Cout, taps*Cin] (Cin fastest) into `pieces` (1..3) digit planes
+ * in the tile layout the kernel's TMA expects (rows = ceil(Cout/64) * pieces * 64, row length taps * cin_pad bytes)
+ * and write w_rowscale[Cout] (powers of two).  Returns the packed size in bytes (also when w_packed == NULL), -1 on
+ * bad arguments. */
+S2F_API int64_t s2f_pack_weights_i8(const float* w, int Cout, int taps, int Cin, int pieces, int8_t* w_packed,
+                            float* w_rowscale);
 
 /* Depthwise k x k convolution (k in {3,5,7}), pad (k-1)/2, stride 1, channels-last, with the same
  * affine / NI-LIF epilogue.  Replaces the depthwise nn.Conv2d of sdtv2.py:154-162, SNN_core.py:36-40,
@@ -129,10 +135,11 @@ S2F_API int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const float
  * q has Nq tokens, k/v have Nk tokens.  kv_ws: int32 workspace [n, heads, d, d].
  * out_f32 (optional) receives the pre-activation.
  * q_ld / kv_ld: elements between consecutive token rows of q and of k,v (>= heads*d), so the three
- * operands may be column slices of one fused [n, N, 3C] projection output. */
+ * operands may be column slices of one fused [n, N, 3C] projection output.  out_ld: elements per output row;
+ * columns [heads*d, out_ld) are written as zeros (channel padding to the 16-byte rows TMA needs). */
 S2F_API int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v, int32_t* kv_ws, int8_t* out_spike,
-                    float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld, float out_scale,
-                    float d_max, void* stream);
+                    float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld, int out_ld,
+                    float out_scale, float d_max, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (c) DCNv3 sampling core.  Replaces dcnv3_core_pytorch (ops_dcnv3/functions/dcnv3_func.py:147-189,

@@ -35,7 +35,14 @@ def record_oracle(P, cfg, img):
 
 
 def to_engine_layout(o: torch.Tensor, mine_shape, layout: str) -> torch.Tensor:
-    """Oracle tensor -> the engine's layout (see engine.NullProbe)."""
+    """Oracle tensor -> the engine's layout (see engine.NullProbe).  The engine may carry zero-padded channels
+    (last dim rounded up to 16 for TMA); the oracle tensor is zero-padded to match."""
+    mine_shape = tuple(mine_shape)
+    c_ref = o.shape[1] if layout == "cm" else o.shape[-1]
+    if layout in ("cm", "same") and mine_shape[-1] > c_ref and (mine_shape[-1] - c_ref) < 16 and \
+            o.numel() // c_ref * mine_shape[-1] == int(torch.tensor(mine_shape).prod()):
+        core = to_engine_layout(o, mine_shape[:-1] + (c_ref,), layout)
+        return torch.nn.functional.pad(core, (0, mine_shape[-1] - c_ref))
     if layout == "same":
         return o.reshape(mine_shape)
     if layout == "cm":
@@ -50,7 +57,10 @@ def to_engine_layout(o: torch.Tensor, mine_shape, layout: str) -> torch.Tensor:
 class TeacherProbe:
     active = True
 
-    def __init__(self, taps, marks, device, prefix="", force=True, tie_tol=2e-5, rtol=2e-5, log=None):
+    # tie_tol: the reference accumulates its convolutions in fp32 (K up to 3312 terms, then a BatchNorm scale of
+    # ~10), so ITS pre-activations carry ~1e-5 of rounding noise; a flip within 1e-4 of a rounding boundary is
+    # indistinguishable from that noise.  The engine's int32 accumulation is exact (error 2^-21 per weight row).
+    def __init__(self, taps, marks, device, prefix="", force=True, tie_tol=1e-4, rtol=2e-5, log=None):
         self.taps, self.marks, self.device, self.prefix = taps, marks, device, prefix
         self.force, self.tie_tol, self.rtol = force, tie_tol, rtol
         self.log = log if log is not None else []       # shared between scoped copies
@@ -82,8 +92,11 @@ class TeacherProbe:
                (pre_m < 8.0 + 0.5 + self.tie_tol)
         unexplained = int((diff & ~near).sum())
         maxdev = int((got.int() - want.int()).abs().max()) if got.numel() else 0
-        self._entry("spike", full, numel=got.numel(), flips=nflip, unexplained=unexplained, maxdev=maxdev,
-                    near_ties=int(near.sum()), rate=float(want.float().mean()))
+        # distance of the worst flipped element from its rounding boundary, relative to max(1, |pre|)
+        gap = float(((frac - 0.5).abs() / pre_m.abs().clamp(min=1.0))[diff].max()) if nflip else 0.0
+        n_ref = lv.numel()                                  # reference element count (without channel padding)
+        self._entry("spike", full, numel=n_ref, flips=nflip, unexplained=unexplained, maxdev=maxdev,
+                    near_ties=int(near.sum()), rate=float(want.float().mean()), worst_gap=gap)
         return want.to(self.device) if self.force else t
 
     def real(self, name, t, layout="cm"):

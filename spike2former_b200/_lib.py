@@ -26,12 +26,12 @@ class ConvArgs(C.Structure):
 class GemmTcArgs(C.Structure):
     """s2f_gemm_tc_args (include/s2f.h)."""
     _fields_ = [
-        ("a", C.c_void_p), ("w_packed", C.c_void_p), ("w_rowscale", C.c_void_p),
+        ("a", C.c_void_p), ("w_packed", C.c_void_p),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
         ("out_f32", C.c_void_p), ("out_spike", C.c_void_p), ("out_transposed", C.c_int),
         ("n", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
         ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("pieces", C.c_int),
-        ("a_scale", C.c_float), ("d_max", C.c_float),
+        ("d_max", C.c_float),
     ]
 
 
@@ -46,9 +46,9 @@ SIGNATURES = {
     "s2f_nilif_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P]),
     "s2f_conv_simt": (_I, [C.POINTER(ConvArgs), _P]),
     "s2f_gemm_i8_tc": (_I, [C.POINTER(GemmTcArgs), _P]),
-    "s2f_pack_weights_i8": (_L, [_P, _I, _I, _I, _P, _P]),
+    "s2f_pack_weights_i8": (_L, [_P, _I, _I, _I, _I, _P, _P]),
     "s2f_dwconv": (_I, [_P, _I, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
-    "s2f_linear_attn": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "s2f_linear_attn": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "s2f_affine_add_lif": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "s2f_dcnv3_gather": (_I, [_P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "s2f_upsample_add_lif": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) kv_kernel(const int8_t* __restrict__ k, c
 // block = (img, 32-token tile); kv of all heads is staged in smem.
 __global__ void __launch_bounds__(256) qkv_kernel(const int8_t* __restrict__ q, const int32_t* __restrict__ kv,
                                                   int8_t* __restrict__ out_spike, float* __restrict__ out_f32, int Nq,
-                                                  int heads, int d, int q_ld, float out_scale, float d_max) {
+                                                  int heads, int d, int q_ld, int out_ld, float out_scale, float d_max) {
   extern __shared__ int32_t kvs[];       // [heads][d][d]
   const int img = blockIdx.y;
   const int C = heads * d;
@@ -64,17 +64,23 @@ __global__ void __launch_bounds__(256) qkv_kernel(const int8_t* __restrict__ q, 
   const int32_t* kvb = kv + (int64_t)img * heads * d * d;
   for (int e = threadIdx.x; e < heads * d * d; e += blockDim.x) kvs[e] = kvb[e];
   __syncthreads();
-  for (int e = threadIdx.x; e < 32 * C; e += blockDim.x) {
-    const int tt = e / C, c = e % C;
+  for (int e = threadIdx.x; e < 32 * out_ld; e += blockDim.x) {
+    const int tt = e / out_ld, c = e % out_ld;
     const int tok = tok0 + tt;
     if (tok >= Nq) continue;
+    if (c >= C) {                                    // channel padding of the output row (TMA needs 16-byte rows)
+      const int64_t oz = ((int64_t)img * Nq + tok) * out_ld + c;
+      if (out_f32) out_f32[oz] = 0.f;
+      if (out_spike) out_spike[oz] = 0;
+      continue;
+    }
     const int h = c / d, j = c % d;
     const int8_t* qrow = q + ((int64_t)img * Nq + tok) * q_ld + h * d;
     const int32_t* kvh = kvs + h * d * d + j;
     long long s = 0;
     for (int i = 0; i < d; ++i) s += (long long)qrow[i] * (long long)kvh[i * d];
     const float y = (float)s * out_scale;
-    const int64_t o = ((int64_t)img * Nq + tok) * C + c;
+    const int64_t o = ((int64_t)img * Nq + tok) * out_ld + c;
     if (out_f32) out_f32[o] = y;
     if (out_spike) out_spike[o] = (int8_t)(int)spike_level(y, d_max);
   }
@@ -162,10 +168,10 @@ using namespace s2f;
 
 extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v, int32_t* kv_ws, int8_t* out_spike,
                                float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld,
-                               float out_scale, float d_max, void* stream) {
+                               int out_ld, float out_scale, float d_max, void* stream) {
   S2F_REQUIRE(q && k && v && kv_ws && (out_spike || out_f32), "linear_attn: null pointer");
   S2F_REQUIRE(d >= 1 && d <= 64 && heads >= 1, "linear_attn: head dim must be <= 64");
-  S2F_REQUIRE(q_ld >= heads * d && kv_ld >= heads * d, "linear_attn: row strides smaller than heads*d");
+  S2F_REQUIRE(q_ld >= heads * d && kv_ld >= heads * d && out_ld >= heads * d, "linear_attn: row strides smaller than heads*d");
   S2F_REQUIRE((int64_t)64 * Nk < (1ll << 31), "linear_attn: Nk too large for int32 K^T V");
   cudaStream_t st = (cudaStream_t)stream;
   const int dd = d * d;
@@ -185,7 +191,7 @@ extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v
   S2F_REQUIRE(sm <= 200 * 1024, "linear_attn: heads*d*d too large for shared memory");
   if (sm > 48 * 1024) cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   qkv_kernel<<<dim3((unsigned)ceil_div(Nq, 32), n), 256, sm, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld,
-                                                                   out_scale, d_max);
+                                                                   out_ld, out_scale, d_max);
   return check_launch("qkv_kernel");
 }
 

@@ -1,14 +1,422 @@
-// tcgen05 / TMEM / TMA int8 spike GEMM -- placeholder until the kernel lands (returns UNSUPPORTED, never a fallback).
+// Spike GEMM / implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a).
+//
+//   A  int8 spike levels, channels-last, fetched by TMA (2D for 1x1, 4D boxes with zero-filled halos for
+//      3x3 / strided convolutions) into 128B/64B/32B-swizzled K-major shared-memory tiles;
+//   B  fp32 weights split on the host into `pieces` signed base-128 digit planes (int8) with one power-of-two
+//      scale per output channel; the planes of a 64-channel tile are stacked along N, so ONE
+//      tcgen05.mma.kind::i8 (M=128, N=64*pieces, K=32) feeds all planes and the int32 accumulation is exact;
+//   D  int32 accumulators in TMEM, read back with tcgen05.ld by four epilogue warps that recombine the digit
+//      planes, apply the folded BatchNorm affine (+ residual) and emit fp32 and/or NI-LIF int8 levels.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Two CTAs fit on one SM, so one CTA's epilogue
+// overlaps the other's main loop.
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
+
+namespace s2f {
+
+constexpr int TC_BM = 128;        // rows (pixels / tokens) per tile == UMMA M
+constexpr int TC_BN = 64;         // output channels per tile
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;
+
+__host__ __device__ inline int tc_bk(int cin) { return cin >= 128 ? 128 : (cin >= 64 ? 64 : 32); }
+__host__ __device__ inline int tc_cin_pad(int cin) { const int bk = tc_bk(cin); return (cin + bk - 1) / bk * bk; }
+
+struct TcParams {
+  const float* scale; const float* shift; const float* residual;
+  float* out_f32; int8_t* out_spike;
+  int M_total;          // n * Ho * Wo
+  int M_img;            // Ho * Wo
+  int Ho, Wo, Cout;
+  int mode_conv;        // 0: 2D rows, 1: 4D boxes
+  int taps_w, taps;     // KW, KH*KW
+  int stride, pad;
+  int TW, TH, tiles_w, tiles_h;
+  int cin_chunks;       // ceil(Cin / BK)
+  int bk;               // bytes of K per stage (32 / 64 / 128)
+  int pieces, stages;
+  int out_transposed;
+  float d_max;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | SBO>>4 @32 | version=1 @46 | layout @61
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int bk) {
+  const uint64_t layout = bk == 128 ? 2 : (bk == 64 ? 4 : 6);       // SWIZZLE_128B / 64B / 32B
+  const uint64_t sbo = (uint64_t)(8 * bk) >> 4;                       // 8 rows of one swizzle span
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nB = TC_BN * p.pieces;                    // MMA N
+  const int a_bytes = TC_BM * p.bk, b_bytes = nB * p.bk;
+  const int stage_bytes = a_bytes + b_bytes;          // multiples of 1024
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int num_chunks = p.taps * p.cin_chunks;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile origin
+  int img = 0, ho0 = 0, wo0 = 0;
+  if (p.mode_conv) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    img = tile_m / per_img;
+    const int t = tile_m % per_img;
+    ho0 = (t / p.tiles_w) * p.TH;
+    wo0 = (t % p.tiles_w) * p.TW;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      int stage = 0, phase = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+        const int tap = c / p.cin_chunks, cc = c % p.cin_chunks;
+        if (p.mode_conv) {
+          const int kh = tap / p.taps_w, kw = tap % p.taps_w;
+          tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, wo0 * p.stride - p.pad + kw, ho0 * p.stride - p.pad + kh, img);
+        } else {
+          tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, tile_m * TC_BM);
+        }
+        tma_load_2d(sb, &map_b, &full[stage], c * p.bk, tile_n * nB);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nB >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, phase = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint64_t da = smem_desc(sa, p.bk), db = smem_desc(sa + a_bytes, p.bk);
+        const int nk = p.bk / 32;
+        for (int k = 0; k < nk; ++k)
+          umma_i8(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);   // +32 B per K step
+        umma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32); thread = one output row
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    int64_t m;            // flat output row (n*Ho*Wo index), -1 if outside
+    if (p.mode_conv) {
+      const int ho = ho0 + r / p.TW, wo = wo0 + r % p.TW;
+      m = (ho < p.Ho && wo < p.Wo) ? ((int64_t)img * p.Ho + ho) * p.Wo + wo : -1;
+    } else {
+      m = (int64_t)tile_m * TC_BM + r;
+      if (m >= p.M_total) m = -1;
+    }
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int co_base = tile_n * TC_BN;
+#pragma unroll 1
+    for (int j0 = 0; j0 < TC_BN; j0 += 16) {
+      if (co_base + j0 >= p.Cout) break;               // warp-uniform
+      uint32_t d0[16], d1[16], d2[16];
+      tmem_ld16(trow + j0, d0);
+      if (p.pieces > 1) tmem_ld16(trow + TC_BN + j0, d1);
+      if (p.pieces > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
+      tmem_ld_wait();
+      if (m < 0) continue;
+      float y[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = (float)(int)d0[j];
+        if (p.pieces > 1) v = fmaf(v, 128.f, (float)(int)d1[j]);
+        if (p.pieces > 2) v = fmaf(v, 128.f, (float)(int)d2[j]);
+        y[j] = v;
+      }
+      const int co0 = co_base + j0;
+      const int nvalid = min(16, p.Cout - co0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < nvalid) y[j] = __fadd_rn(__fmul_rn(y[j], __ldg(p.scale + co0 + j)), __ldg(p.shift + co0 + j));
+      }
+      const int64_t row_off = m * p.Cout + co0;
+      if (p.residual) {
+        if (nvalid == 16 && (p.Cout & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 rv = *reinterpret_cast<const float4*>(p.residual + row_off + 4 * q);
+            y[4 * q] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
+          }
+        } else {
+          for (int j = 0; j < nvalid; ++j) y[j] += p.residual[row_off + j];
+        }
+      }
+      if (!p.out_transposed) {
+        if (p.out_f32) {
+          if (nvalid == 16 && (p.Cout & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(p.out_f32 + row_off + 4 * q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) p.out_f32[row_off + j] = y[j];
+          }
+        }
+        if (p.out_spike) {
+          if (nvalid == 16 && (p.Cout & 15) == 0) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              w[q] = (uint32_t)(int)spike_level(y[4 * q], p.d_max) | ((uint32_t)(int)spike_level(y[4 * q + 1], p.d_max) << 8) |
+                     ((uint32_t)(int)spike_level(y[4 * q + 2], p.d_max) << 16) | ((uint32_t)(int)spike_level(y[4 * q + 3], p.d_max) << 24);
+            *reinterpret_cast<uint4*>(p.out_spike + row_off) = make_uint4(w[0], w[1], w[2], w[3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) p.out_spike[row_off + j] = (int8_t)(int)spike_level(y[j], p.d_max);
+          }
+        }
+      } else {
+        const int64_t im = m / p.M_img, pm = m % p.M_img;
+        const int64_t tbase = im * (int64_t)p.M_img * p.Cout + pm;
+        for (int j = 0; j < nvalid; ++j) {
+          const int64_t o = tbase + (int64_t)(co0 + j) * p.M_img;
+          if (p.out_f32) p.out_f32[o] = y[j];
+          if (p.out_spike) p.out_spike[o] = (int8_t)(int)spike_level(y[j], p.d_max);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swz_for(int bk) {
+  return bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+}  // namespace s2f
 
 using namespace s2f;
 
-extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream) {
-  (void)args; (void)stream;
-  return fail(S2F_ERR_UNSUPPORTED, "gemm_i8_tc: %s", "not built in this revision");
+extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
+  S2F_REQUIRE(a && a->a && a->w_packed && a->scale && a->shift, "gemm_i8_tc: a, w_packed, scale, shift are required");
+  S2F_REQUIRE(a->out_f32 || a->out_spike, "gemm_i8_tc: no output requested");
+  S2F_REQUIRE(a->pieces >= 1 && a->pieces <= 3, "gemm_i8_tc: pieces must be 1..3");
+  S2F_REQUIRE(a->Cin >= 32 && a->Cin % 16 == 0, "gemm_i8_tc: Cin must be >= 32 and a multiple of 16");
+  S2F_REQUIRE((a->KH == 1 && a->KW == 1) || (a->KH == 3 && a->KW == 3), "gemm_i8_tc: 1x1 or 3x3 only");
+  S2F_REQUIRE(a->stride == 1 || a->stride == 2, "gemm_i8_tc: stride 1 or 2");
+  S2F_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0,
+              "gemm_i8_tc: operands must be 16-byte aligned");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(S2F_ERR_CUDA, "gemm_i8_tc: %s", "cuTensorMapEncodeTiled entry point not found");
+
+  TcParams p{};
+  const int Ho = (a->H + 2 * a->pad - a->KH) / a->stride + 1, Wo = (a->W + 2 * a->pad - a->KW) / a->stride + 1;
+  S2F_REQUIRE(Ho > 0 && Wo > 0, "gemm_i8_tc: empty output");
+  p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out_f32 = a->out_f32; p.out_spike = a->out_spike;
+  p.Ho = Ho; p.Wo = Wo; p.Cout = a->Cout; p.M_img = Ho * Wo; p.M_total = a->n * Ho * Wo;
+  p.taps_w = a->KW; p.taps = a->KH * a->KW; p.stride = a->stride; p.pad = a->pad;
+  p.bk = tc_bk(a->Cin); p.cin_chunks = (a->Cin + p.bk - 1) / p.bk;
+  p.pieces = a->pieces; p.out_transposed = a->out_transposed; p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
+  p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
+  const int nB = TC_BN * p.pieces;
+  const int stage_bytes = (TC_BM + nB) * p.bk;
+  p.stages = 100 * 1024 / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) p.stages = 2;
+  const int tiles_n = (a->Cout + TC_BN - 1) / TC_BN;
+  const int kpad = p.taps * tc_cin_pad(a->Cin);
+
+  CUtensorMap map_a, map_b;
+  int tiles_m;
+  if (p.mode_conv) {
+    p.TW = 16; while (p.TW / 2 >= Wo && p.TW > 1) p.TW /= 2;
+    p.TH = TC_BM / p.TW;
+    p.tiles_w = (Wo + p.TW - 1) / p.TW; p.tiles_h = (Ho + p.TH - 1) / p.TH;
+    tiles_m = a->n * p.tiles_w * p.tiles_h;
+    cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->n};
+    cuuint64_t strides[3] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W * a->Cin, (cuuint64_t)a->H * a->W * a->Cin};
+    cuuint32_t box[4] = {(cuuint32_t)p.bk, (cuuint32_t)(p.TW * a->stride), (cuuint32_t)(p.TH * a->stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
+    S2F_REQUIRE(box[1] <= 256 && box[2] <= 256, "gemm_i8_tc: box too large");
+    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(a->a), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(p.bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(A,4D) failed (%s) code %lld", "", (long long)r);
+  } else {
+    tiles_m = (p.M_total + TC_BM - 1) / TC_BM;
+    cuuint64_t dims[2] = {(cuuint64_t)a->Cin, (cuuint64_t)p.M_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a->Cin};
+    cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)TC_BM};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(a->a), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(p.bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(A,2D) failed (%s) code %lld", "", (long long)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)tiles_n * nB};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad};
+    cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)nB};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(a->w_packed), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(p.bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(B) failed (%s) code %lld", "", (long long)r);
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "gemm_i8_tc: smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
+  gemm_i8_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  return check_launch("gemm_i8_tc_kernel");
 }
 
-extern "C" int64_t s2f_pack_weights_i8(const float* w, int Cout, int K, int pieces, int8_t* w_packed, float* w_rowscale) {
-  (void)w; (void)Cout; (void)K; (void)pieces; (void)w_packed; (void)w_rowscale;
-  return -1;
+// Split fp32 weights [Cout, taps*Cin] (Cin fastest) into `pieces` signed base-128 digit planes.
+// Packed layout: rows = tiles_n * pieces * 64 (tile-major, then plane, then channel-in-tile), row length
+// taps * cin_pad bytes, zero padded.  rowscale[co] = 2^(e - (7*pieces - 1)) so that w ~= rowscale * sum_p digit_p * 128^(pieces-1-p).
+extern "C" int64_t s2f_pack_weights_i8(const float* w, int Cout, int taps, int Cin, int pieces, int8_t* w_packed,
+                                       float* w_rowscale) {
+  if (Cout <= 0 || taps <= 0 || Cin <= 0 || pieces < 1 || pieces > 3) return -1;
+  const int cin_pad = tc_cin_pad(Cin);
+  const int64_t kpad = (int64_t)taps * cin_pad;
+  const int tiles_n = (Cout + TC_BN - 1) / TC_BN;
+  const int64_t bytes = (int64_t)tiles_n * pieces * TC_BN * kpad;
+  if (!w_packed) return bytes;
+  if (!w || !w_rowscale) return -1;
+  memset(w_packed, 0, (size_t)bytes);
+  const int F = 7 * pieces - 1;
+  for (int co = 0; co < Cout; ++co) {
+    const float* row = w + (int64_t)co * taps * Cin;
+    float mx = 0.f;
+    for (int64_t k = 0; k < (int64_t)taps * Cin; ++k) mx = fmaxf(mx, fabsf(row[k]));
+    int e = 0;
+    if (mx > 0.f) { frexpf(mx, &e); if (ldexpf(1.f, e - 1) == mx) e -= 1; }   // smallest e with mx <= 2^e
+    const double inv = ldexp(1.0, F - e);
+    w_rowscale[co] = (float)ldexp(1.0, e - F);
+    const int tile = co / TC_BN, r = co % TC_BN;
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < Cin; ++c) {
+        long long I = llrint((double)row[(int64_t)t * Cin + c] * inv);
+        int digit[3] = {0, 0, 0};
+        for (int pz = pieces - 1; pz >= 1; --pz) {
+          int lo = (int)(((I + 64) % 128 + 128) % 128) - 64;
+          digit[pz] = lo;
+          I = (I - lo) / 128;
+        }
+        digit[0] = (int)I;     // |I| <= 64
+        for (int pz = 0; pz < pieces; ++pz)
+          w_packed[((int64_t)(tile * pieces + pz) * TC_BN + r) * kpad + (int64_t)t * cin_pad + c] = (int8_t)digit[pz];
+      }
+  }
+  return bytes;
 }

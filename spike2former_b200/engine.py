@@ -21,18 +21,40 @@ from . import fold, ops
 from .ops import NORM
 
 INV = 1.0 / NORM
+USE_TC = True            # spike-operand layers run on the tcgen05 kernel (the CUDA-core kernel covers the rest)
+TC_PIECES = 3            # int8 digit planes per weight: 21-bit fixed point per output channel, exact accumulation
+TC_MIN_ROWS = 1024       # below this many output rows a 128-row tile grid cannot fill the GPU
 
 
 # ------------------------------------------------------------------------------------------------ plan
 class Gemm:
     """A conv / linear layer prepared for the kernels: weights [Cout, K] (Cin fastest) + folded affine."""
 
-    def __init__(self, w2d, scale, shift, cin, k=1, stride=1, pad=0, device="cuda"):
+    def __init__(self, w2d, scale, shift, cin, k=1, stride=1, pad=0, device="cuda", spike_in=True):
         self.cout, self.cin, self.k, self.stride, self.pad = int(w2d.shape[0]), int(cin), k, stride, pad
         self.w = ops.pad_rows4(fold.f32(w2d, device))
         self.scale, self.shift = fold.f32(scale, device), fold.f32(shift, device)
+        # tensor-core form: int8 digit planes + scale with the packer's power-of-two row scale folded in
+        self.tc = None
+        if spike_in and USE_TC and ops.tc_eligible(self.cin, k, stride) and pad == (k - 1) // 2:
+            packed, rowscale = ops.pack_weights_i8(w2d.to(torch.float32), k * k, self.cin, TC_PIECES)
+            self.tc = (packed.to(device), fold.f32(scale.double().cpu() * rowscale.double(), device))
 
     def __call__(self, a, n, H, W, residual=None, f32=False, spike=False, transposed=False, a_scale=INV, **kw):
+        if self.tc is not None and a.dtype == torch.int8 and not kw and n * H * W >= TC_MIN_ROWS:
+            sc = self.tc[1] if a_scale == 1.0 else self._scaled(a_scale)
+            return ops.gemm_tc(a, self.tc[0], n=n, H=H, W=W, Cin=self.cin, Cout=self.cout, scale=sc, shift=self.shift,
+                               k=self.k, stride=self.stride, pad=self.pad, pieces=TC_PIECES, residual=residual,
+                               want_f32=f32, want_spike=spike, transposed=transposed)
+        return self._simt(a, n, H, W, residual, f32, spike, transposed, a_scale, **kw)
+
+    def _scaled(self, a_scale):
+        cache = self.__dict__.setdefault("_sc", {})
+        if a_scale not in cache:
+            cache[a_scale] = (self.tc[1] * a_scale).contiguous()
+        return cache[a_scale]
+
+    def _simt(self, a, n, H, W, residual=None, f32=False, spike=False, transposed=False, a_scale=INV, **kw):
         return ops.conv_simt(a, self.w, n=n, H=H, W=W, Cin=self.cin, Cout=self.cout, k=self.k, stride=self.stride,
                              pad=self.pad, scale=self.scale, shift=self.shift, residual=residual, a_scale=a_scale,
                              want_f32=f32, want_spike=spike, transposed=transposed, **kw)
@@ -50,18 +72,38 @@ class Dw:
                           want_f32=f32, want_spike=spike)
 
 
-def _conv_gemm(sd, conv_key, bn_key, device, k=1, stride=1, pad=0, extra_scale=None):
+def pad16(c):
+    """Channel counts are padded to 16 so that every int8 activation row is a legal TMA row (16-byte strides)."""
+    return (c + 15) // 16 * 16
+
+
+def _pad_channels(w2d, s, t, taps, cin_pad=None, cout_pad=None):
+    """Zero-pad input channels (per tap) and output channels; padded outputs compute exactly 0 -> level 0."""
+    cout = w2d.shape[0]
+    cin = w2d.shape[1] // taps
+    cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
+    if cin_pad == cin and cout_pad == cout:
+        return w2d, s, t, cin
+    w = torch.zeros(cout_pad, taps, cin_pad, dtype=w2d.dtype)
+    w[:cout, :, :cin] = w2d.reshape(cout, taps, cin)
+    s2, t2 = torch.zeros(cout_pad, dtype=s.dtype), torch.zeros(cout_pad, dtype=t.dtype)
+    s2[:cout], t2[:cout] = s, t
+    return w.reshape(cout_pad, taps * cin_pad), s2, t2, cin_pad
+
+
+def _conv_gemm(sd, conv_key, bn_key, device, k=1, stride=1, pad=0, extra_scale=None, cin_pad=None, cout_pad=None):
     w = sd[conv_key + ".weight"]
     s, t = fold.conv_bn(sd, conv_key, bn_key, extra_scale)
-    return Gemm(fold.w_khwc(w), s, t, w.shape[1], k, stride, pad, device)
+    w2d, s, t, cin = _pad_channels(fold.w_khwc(w), s, t, k * k, cin_pad, cout_pad)
+    return Gemm(w2d, s, t, cin, k, stride, pad, device)
 
 
-def _rep_gemm(sd, keys, device):
+def _rep_gemm(sd, keys, device, cin_pad=None, cout_pad=None):
     """One dense 3x3 for one or several RepConv(+BN) branches sharing their input (outputs concatenated)."""
     ws, bs = zip(*(fold.repconv_dense3x3(sd, k) for k in keys))
     w, b = torch.cat(ws, 0), torch.cat(bs, 0)
-    cin = w.shape[1] // 9
-    return Gemm(w, torch.ones_like(b), b, cin, 3, 1, 1, device)
+    w, s, b, cin = _pad_channels(w, torch.ones_like(b), b, 9, cin_pad, cout_pad)
+    return Gemm(w, s, b, cin, 3, 1, 1, device)
 
 
 def _dw(sd, conv_key, bn_key, device):
@@ -84,13 +126,19 @@ class BackbonePlan:
             L[name + ".pw2"] = _conv_gemm(sd, name + ".Conv.pwconv2", name + ".Conv.bn2", dev)
             L[name + ".conv1"] = _conv_gemm(sd, name + ".conv1", name + ".bn1", dev, 3, 1, 1)
             L[name + ".conv2"] = _conv_gemm(sd, name + ".conv2", name + ".bn2", dev, 3, 1, 1)
+        # every stage width is kept at a multiple of 16 channels in HBM (stage 4: 360 -> 368, zero padded)
+        e = model.embed_dim
+        self.width = {"block3": e[2], "block4": e[3]}
         for name, st in (("downsample1_2", 2), ("downsample2", 2), ("downsample3", 2), ("downsample4", 1)):
-            L[name] = _conv_gemm(sd, name + ".encode_conv", name + ".encode_bn", dev, 3, st, 1)
+            L[name] = _conv_gemm(sd, name + ".encode_conv", name + ".encode_bn", dev, 3, st, 1,
+                                 cout_pad=pad16(e[3]) if name == "downsample4" else None)
         for name in [f"block3.{j}" for j in range(6)] + [f"block4.{j}" for j in range(2)]:
-            L[name + ".qkv"] = _rep_gemm(sd, [name + ".attn.q_conv", name + ".attn.k_conv", name + ".attn.v_conv"], dev)
-            L[name + ".proj"] = _rep_gemm(sd, [name + ".attn.proj_conv"], dev)
-            L[name + ".fc1"] = _conv_gemm(sd, name + ".mlp.fc1_conv", name + ".mlp.fc1_bn", dev)
-            L[name + ".fc2"] = _conv_gemm(sd, name + ".mlp.fc2_conv", name + ".mlp.fc2_bn", dev)
+            cp = pad16(self.width[name.split(".")[0]])
+            L[name + ".qkv"] = _rep_gemm(sd, [name + ".attn.q_conv", name + ".attn.k_conv", name + ".attn.v_conv"], dev,
+                                         cin_pad=cp)
+            L[name + ".proj"] = _rep_gemm(sd, [name + ".attn.proj_conv"], dev, cin_pad=cp, cout_pad=cp)
+            L[name + ".fc1"] = _conv_gemm(sd, name + ".mlp.fc1_conv", name + ".mlp.fc1_bn", dev, cin_pad=cp)
+            L[name + ".fc2"] = _conv_gemm(sd, name + ".mlp.fc2_conv", name + ".mlp.fc2_bn", dev, cout_pad=cp)
 
 
 class PixelDecoderPlan:
@@ -101,7 +149,8 @@ class PixelDecoderPlan:
         self.num_layers = model.encoder_cfg["num_layers"]
         sa = model.encoder_cfg["layer_cfg"]["self_attn_cfg"]
         self.group, self.dw_k = sa["group"], sa["dw_kernel_size"]
-        L["in_proj"] = _conv_gemm(sd, "encoder_in_proj.0", "encoder_in_proj.1", dev)
+        self.cin_last = pad16(model.in_channels[-1])
+        L["in_proj"] = _conv_gemm(sd, "encoder_in_proj.0", "encoder_in_proj.1", dev, cin_pad=self.cin_last)
         L["out_proj"] = _conv_gemm(sd, "encoder_out_proj.0", "encoder_out_proj.1", dev)
 
         def sepconv(prefix, key, gamma):
@@ -221,9 +270,10 @@ def _conv_block(L, name, s, sp, n, H, W, pr):
     return L[name + ".conv2"](a, n, H, W, residual=s2, f32=True, spike=True)
 
 
-def _ms_block(L, name, s, sp, n, H, W, heads, pr):
-    """MS_Block (sdtv2.py:298-383): SDSA with the RepConv branches as one dense 3x3, then MS_MLP."""
-    C = s.shape[-1]
+def _ms_block(L, name, s, sp, n, H, W, heads, pr, C):
+    """MS_Block (sdtv2.py:298-383): SDSA with the RepConv branches as one dense 3x3, then MS_MLP.
+    C is the reference width; the stream / spike buffers carry pad16(C) channels (zeros beyond C)."""
+    CP = s.shape[-1]
     d = C // heads
     N = H * W
     sp = pr.spike(f"{name}.attn.head_spike", sp)
@@ -235,9 +285,9 @@ def _ms_block(L, name, s, sp, n, H, W, heads, pr):
     else:
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         ld = 3 * C
-    att, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, q_ld=ld, kv_ld=ld,
+    att, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, q_ld=ld, kv_ld=ld, out_ld=CP,
                              out_scale=(d ** -0.5) * INV ** 3)
-    att = pr.spike(f"{name}.attn.attn_spike", att.view(n, H, W, C))
+    att = pr.spike(f"{name}.attn.attn_spike", att.view(n, H, W, CP))
     s2, sp2 = L[name + ".proj"](att, n, H, W, residual=s, f32=True, spike=True)
     s2 = pr.real(f"{name}.mlp.fc1_spike", s2)
     sp2 = pr.spike(f"{name}.mlp.fc1_spike", sp2)
@@ -281,11 +331,11 @@ def backbone_forward(model, img, probe=NOPROBE):
     s, sp = down("downsample3", s, sp, H, W, 2); H, W = H // 2, W // 2
     for j in range(6):
         s = pr.real(f"block3.{j}.attn.head_spike", s)
-        s, sp = _ms_block(L, f"block3.{j}", s, sp, n, H, W, model.num_heads, pr)
+        s, sp = _ms_block(L, f"block3.{j}", s, sp, n, H, W, model.num_heads, pr, plan.width["block3"])
     s, sp = down("downsample4", s, sp, H, W, 1)
     for j in range(2):
         s = pr.real(f"block4.{j}.attn.head_spike", s)
-        s, sp = _ms_block(L, f"block4.{j}", s, sp, n, H, W, model.num_heads, pr)
+        s, sp = _ms_block(L, f"block4.{j}", s, sp, n, H, W, model.num_heads, pr, plan.width["block4"])
     feats.append((s, sp))
     return feats
 
@@ -294,9 +344,10 @@ def export_backbone_feats(model, feats):
     """Reference output contract (sdtv2.py:639-651): 'Qsnn' -> [T,B,C,H,W]; 'snn' -> mean over T; else [T*B,C,H,W]."""
     T = model.T
     outs = []
-    for s, sp in feats:
-        n, h, w, c = s.shape
-        t = s.permute(0, 3, 1, 2)
+    widths = [model.embed_dim[0] // 2, model.embed_dim[0], model.embed_dim[1], model.embed_dim[3]]
+    for (s, sp), c in zip(feats, widths):
+        n, h, w, _ = s.shape
+        t = s[..., :c].permute(0, 3, 1, 2)
         if model.decode_mode == "Qsnn":
             t = t.reshape(T, n // T, c, h, w)
         elif model.decode_mode == "snn":
@@ -343,6 +394,8 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE):
     n, H, W, _ = s4.shape
     C = model.feat_channels
     G = plan.group
+    if sp4.shape[-1] != plan.cin_last:            # public-API input with the reference's 360 channels
+        sp4 = torch.nn.functional.pad(sp4, (0, plan.cin_last - sp4.shape[-1]))
     sp4 = pr.spike(pd + "last_feat_conv_spike", sp4)
     q, qs = L["in_proj"](sp4, n, H, W, f32=True, spike=True)
     for l in range(plan.num_layers):

@@ -169,6 +169,53 @@ def conv_simt(a, w, *, n, H, W, Cin, Cout, k=1, stride=1, pad=0, scale=None, shi
     return out_f32, out_spike
 
 
+def pack_weights_i8(w2d: torch.Tensor, taps: int, cin: int, pieces: int = 3):
+    """Host-side: fp32 [Cout, taps*cin] (cin fastest) -> (int8 digit planes in the kernel's tile layout, rowscale[Cout])."""
+    w = w2d.detach().to("cpu", torch.float32).contiguous()
+    cout = w.shape[0]
+    if w.shape[1] != taps * cin:
+        raise S2FError("pack_weights_i8: weight row length != taps * cin")
+    lib = _lib.lib()
+    nbytes = lib.s2f_pack_weights_i8(None, cout, taps, cin, pieces, None, None)
+    if nbytes <= 0:
+        raise S2FError("pack_weights_i8: bad arguments")
+    packed = torch.empty(nbytes, dtype=torch.int8)
+    rowscale = torch.empty(cout, dtype=torch.float32)
+    got = lib.s2f_pack_weights_i8(C.c_void_p(w.data_ptr()), cout, taps, cin, pieces, C.c_void_p(packed.data_ptr()),
+                                  C.c_void_p(rowscale.data_ptr()))
+    if got != nbytes:
+        raise S2FError("pack_weights_i8 failed")
+    return packed, rowscale
+
+
+def tc_eligible(cin: int, k: int, stride: int) -> bool:
+    return cin >= 32 and cin % 16 == 0 and k in (1, 3) and stride in (1, 2)
+
+
+def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad=0, pieces=3, residual=None,
+            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX):
+    """tcgen05 spike GEMM.  a: int8 levels channels-last; `scale` already contains rowscale * 1/8."""
+    if a.dtype != torch.int8:
+        raise S2FError("gemm_tc: a must be int8 levels")
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    shape = (n, Cout, Ho * Wo) if transposed else (n, Ho, Wo, Cout)
+    out_f32 = torch.empty(shape, dtype=torch.float32, device=a.device) if want_f32 else None
+    out_spike = torch.empty(shape, dtype=torch.int8, device=a.device) if want_spike else None
+    args = GemmTcArgs()
+    args.a, args.w_packed = _ptr(a, torch.int8, "a"), _ptr(w_packed, torch.int8, "w_packed")
+    args.scale, args.shift = _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift")
+    args.residual = _ptr(residual, torch.float32, "residual")
+    args.out_f32, args.out_spike, args.out_transposed = _ptr(out_f32), _ptr(out_spike), int(transposed)
+    args.n, args.H, args.W, args.Cin, args.Cout = n, H, W, Cin, Cout
+    args.KH = args.KW = k
+    args.stride, args.pad, args.pieces, args.d_max = stride, pad, pieces, float(d_max)
+    e0 = _p0()
+    check(_lib.lib().s2f_gemm_i8_tc(C.byref(args), _stream()), "s2f_gemm_i8_tc")
+    _p1(e0, "gemm_tc", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces)
+    return out_f32, out_spike
+
+
 def dwconv(a, w_tap, *, n, H, W, C_, k, scale=None, shift=None, a_scale=1.0 / NORM, want_f32=False, want_spike=False,
            no_pad=False, d_max=D_MAX):
     """Depthwise k x k (stride 1).  w_tap: fp32 [k*k, C]."""
@@ -187,19 +234,21 @@ def dwconv(a, w_tap, *, n, H, W, C_, k, scale=None, shift=None, a_scale=1.0 / NO
 
 
 # ------------------------------------------------------------------------------------------ attention / DCN / tail
-def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=None, want_f32=False, d_max=D_MAX):
+def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=None, out_ld=None, want_f32=False,
+                d_max=D_MAX):
     """Spike-driven attention without softmax: NI-LIF((Q (K^T V)) * out_scale).  q/k/v int8 levels."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         if t.dtype != torch.int8 or not t.is_cuda:
             raise S2FError(f"linear_attn: {nm} must be CUDA int8 levels")
     Cc = heads * d
     ws = torch.empty((n, heads, d, d), dtype=torch.int32, device=q.device)
-    out_s = torch.empty((n, Nq, Cc), dtype=torch.int8, device=q.device)
-    out_f = torch.empty((n, Nq, Cc), dtype=torch.float32, device=q.device) if want_f32 else None
+    out_ld = int(out_ld or Cc)
+    out_s = torch.empty((n, Nq, out_ld), dtype=torch.int8, device=q.device)
+    out_f = torch.empty((n, Nq, out_ld), dtype=torch.float32, device=q.device) if want_f32 else None
     e0 = _p0()
     check(_lib.lib().s2f_linear_attn(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
                                      _ptr(ws), _ptr(out_s), _ptr(out_f), n, Nq, Nk, heads, d, int(q_ld or Cc),
-                                     int(kv_ld or Cc), float(out_scale), float(d_max), _stream()), "s2f_linear_attn")
+                                     int(kv_ld or Cc), out_ld, float(out_scale), float(d_max), _stream()), "s2f_linear_attn")
     _p1(e0, "linear_attn", 2.0 * n * heads * d * d * (Nq + Nk), n * (Nq + 2 * Nk) * Cc + _nb(out_s, out_f))
     return out_s, out_f
 

@@ -29,6 +29,11 @@ def _report(pr):
     s = pr.summary()
     worst = sorted((e for e in pr.log if e["kind"] == "spike" and "flips" in e), key=lambda e: -e["flips"])[:5]
     print("summary", s)
+    print("  worst flip gap (relative distance of a flipped pre-activation from k+0.5):",
+          max([e.get("worst_gap", 0.0) for e in pr.log if e["kind"] == "spike"] or [0.0]))
+    for e in pr.log:
+        if e["kind"] == "spike" and e.get("unexplained", 0) > 0:
+            print("  UNEXPLAINED:", e)
     for e in worst:
         print("  most flips:", e)
     for e in sorted((e for e in pr.log if e["kind"] == "real" and "rel" in e), key=lambda e: -e["rel"])[:5]:

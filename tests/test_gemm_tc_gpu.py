@@ -1,0 +1,95 @@
+"""GPU parity of the tcgen05 int8 spike GEMM against a float64 restatement (and the CUDA-core kernel)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from spike2former_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(cin, cout, k, stride, H, W, n=2, pieces=3, seed=0, transposed=False, residual=True):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    w[0, 0, 0, 0] = 0.75          # exact power-of-two-ish row maxima exercise the packer's exponent choice
+    sc = torch.rand(cout, generator=g) + 0.5
+    sh = torch.randn(cout, generator=g)
+    pad = (k - 1) // 2
+    ref = F.conv2d((a.double() / 8).permute(0, 3, 1, 2), w.double(), stride=stride, padding=pad)
+    ref = ref * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)
+    Ho, Wo = ref.shape[-2:]
+    ref = ref.permute(0, 2, 3, 1)
+    res = torch.randn(n, Ho, Wo, cout, generator=g) if residual else None
+    if residual:
+        ref = ref + res.double()
+    w2d = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    packed, rowscale = ops.pack_weights_i8(w2d, k * k, cin, pieces)
+    scale_tc = (sc.double() * rowscale.double() / 8).float().cuda()
+    of, os_ = ops.gemm_tc(a.cuda(), packed.cuda(), n=n, H=H, W=W, Cin=cin, Cout=cout, scale=scale_tc, shift=sh.cuda(),
+                          k=k, stride=stride, pad=pad, pieces=pieces, residual=res.cuda() if residual else None,
+                          want_f32=True, want_spike=True, transposed=transposed)
+    torch.cuda.synchronize()
+    of, os_ = of.cpu(), os_.cpu()
+    if transposed:
+        of = of.view(n, cout, Ho * Wo).permute(0, 2, 1).reshape(n, Ho, Wo, cout)
+        os_ = os_.view(n, cout, Ho * Wo).permute(0, 2, 1).reshape(n, Ho, Wo, cout)
+    return of, os_, ref
+
+
+SHAPES = [
+    # cin, cout, k, stride, H, W
+    (32, 64, 1, 1, 16, 16),       # SWIZZLE_32B, exact tiles
+    (64, 128, 1, 1, 16, 24),      # SWIZZLE_64B
+    (128, 64, 1, 1, 8, 16),       # SWIZZLE_128B, one chunk
+    (256, 256, 1, 1, 32, 32),     # stage-3 1x1
+    (368, 100, 1, 1, 10, 10),     # ragged K chunk (368 = 2*128 + 112), ragged Cout, M tail (200 rows)
+    (1024, 256, 1, 1, 32, 32),    # MLP fc2: 8 chunks
+    (32, 128, 3, 1, 32, 32),      # ConvBlock1_1.conv1 shape class
+    (128, 32, 3, 1, 16, 16),      # conv2: Cout 32 (half-empty N tile)
+    (64, 64, 3, 1, 12, 20),       # spatial sizes that are not tile multiples
+    (32, 64, 3, 2, 32, 32),       # strided downsample (TMA element strides)
+    (128, 256, 3, 2, 16, 16),
+    (256, 768, 3, 1, 32, 32),     # merged q|k|v RepConv
+    (48, 80, 3, 1, 9, 7),         # odd everything
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", SHAPES)
+def test_gemm_tc_matches_float64(cin, cout, k, stride, H, W):
+    of, os_, ref = _case(cin, cout, k, stride, H, W)
+    scale = max(1.0, ref.abs().max().item())
+    err = (of.double() - ref).abs().max().item()
+    assert err < 5e-6 * scale, (err, scale)
+    assert torch.equal(os_, torch.round(torch.clamp(of, 0, 8)).to(torch.int8))
+
+
+@pytest.mark.parametrize("pieces,tol", [(1, 3e-2), (2, 3e-4), (3, 5e-6)])
+def test_gemm_tc_digit_planes(pieces, tol):
+    of, _, ref = _case(256, 128, 1, 1, 16, 16, pieces=pieces)
+    assert (of.double() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_tc_transposed_and_no_residual():
+    of, os_, ref = _case(256, 288, 1, 1, 32, 32, transposed=True, residual=False)
+    assert (of.double() - ref).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item())
+    assert torch.equal(os_, torch.round(torch.clamp(of, 0, 8)).to(torch.int8))
+
+
+def test_gemm_tc_matches_cuda_core_kernel_bitwise_spikes():
+    """Same inputs through both kernels: fp32 outputs agree to fp32 rounding, spikes differ only at near-ties."""
+    g = torch.Generator().manual_seed(5)
+    n, H, W, cin, cout = 4, 32, 32, 256, 256
+    a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8).cuda()
+    w = (torch.randn(cout, cin, generator=g) / 16)
+    sc, sh = (torch.rand(cout, generator=g) + 0.5), torch.randn(cout, generator=g) + 1
+    packed, rowscale = ops.pack_weights_i8(w, 1, cin, 3)
+    f_tc, s_tc = ops.gemm_tc(a, packed.cuda(), n=n, H=H, W=W, Cin=cin, Cout=cout, scale=(sc * rowscale / 8).cuda(),
+                             shift=sh.cuda(), want_f32=True, want_spike=True)
+    f_cc, s_cc = ops.conv_simt(a, ops.pad_rows4(w.cuda()), n=n, H=H, W=W, Cin=cin, Cout=cout, scale=sc.cuda(),
+                               shift=sh.cuda(), want_f32=True, want_spike=True)
+    assert (f_tc - f_cc).abs().max().item() < 1e-5
+    diff = (s_tc != s_cc)
+    frac = (f_cc - f_cc.floor() - 0.5).abs()
+    assert int((diff & (frac > 1e-4)).sum()) == 0
+    assert int(diff.sum()) <= 1e-4 * diff.numel()
