@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);
+S2F_API int s2f_abi_version(void);   /* currently 2 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -105,6 +105,7 @@ typedef struct {
   float* out_f32; int8_t* out_spike; int out_transposed;
   int n, H, W, Cin, Cout, KH, KW, stride, pad, pieces;
   float d_max;
+  int per_image_weights;   /* 1: w_packed / scale / shift hold one matrix per image (1x1, Ho*Wo % 128 == 0) */
 } s2f_gemm_tc_args;
 
 S2F_API int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream);
@@ -115,6 +116,14 @@ S2F_API int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream);
  * bad arguments. */
 S2F_API int64_t s2f_pack_weights_i8(const float* w, int Cout, int taps, int Cin, int pieces, int8_t* w_packed,
                             float* w_rowscale);
+
+/* Device-side packer for weights computed on the GPU (e.g. the per-image mask-embedding x mask_feature product):
+ * w fp32 [n_img*rows_per_img, ld] (first K columns are weights), one matrix of rows_per_img rows per image ->
+ * digit planes in the kernel's per-image tile layout (buffer must be zero-initialised: padding rows are not written),
+ * scale_out[row] = rowscale * post_scale, shift_out[row] = bias_col[row*ld] (or 0). */
+S2F_API int s2f_pack_rows_i8_device(const float* w, int ld, int n_img, int rows_per_img, int K, int pieces,
+                            int8_t* packed, float* scale_out, float* shift_out, const float* bias_col,
+                            float post_scale, void* stream);
 
 /* Depthwise k x k convolution (k in {3,5,7}), pad (k-1)/2, stride 1, channels-last, with the same
  * affine / NI-LIF epilogue.  Replaces the depthwise nn.Conv2d of sdtv2.py:154-162, SNN_core.py:36-40,
@@ -171,6 +180,14 @@ S2F_API int s2f_sigmoid_lif(const float* x, int8_t* levels, int64_t N, float d_m
  * mask_pred is given pixel-major [n, h*w, Q] (as the mask GEMM writes it); cls [n,Q,K+1]. */
 S2F_API int s2f_semantic_tail(const float* mask_pred, const float* cls, float* logits, float* prob_ws, int n, int Q, int K,
                       int h, int w, int H, int W, void* stream);
+
+/* The same on the tensor cores (tcgen05 kind::f16, bf16 hi+lo split operands, fp32 accumulation in TMEM):
+ * Q <= 128, K <= 256.  logits (fp32 [n,K,H,W]) and/or labels (uint8 [n,H,W] = argmax over classes, first maximum,
+ * i.e. BaseSegmentor.postprocess_result's argmax, segmentors/base.py:177-188) may be requested.
+ * ws: device workspace of s2f_semantic_tail_ws_bytes(n, K) bytes. */
+S2F_API int64_t s2f_semantic_tail_ws_bytes(int n, int K);
+S2F_API int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, float* logits, uint8_t* labels, void* ws,
+                         int n, int Q, int K, int h, int w, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

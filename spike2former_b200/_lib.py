@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2f.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ConvArgs(C.Structure):
@@ -31,7 +31,7 @@ class GemmTcArgs(C.Structure):
         ("out_f32", C.c_void_p), ("out_spike", C.c_void_p), ("out_transposed", C.c_int),
         ("n", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
         ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("pieces", C.c_int),
-        ("d_max", C.c_float),
+        ("d_max", C.c_float), ("per_image_weights", C.c_int),
     ]
 
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "s2f_conv_simt": (_I, [C.POINTER(ConvArgs), _P]),
     "s2f_gemm_i8_tc": (_I, [C.POINTER(GemmTcArgs), _P]),
     "s2f_pack_weights_i8": (_L, [_P, _I, _I, _I, _I, _P, _P]),
+    "s2f_pack_rows_i8_device": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P]),
     "s2f_dwconv": (_I, [_P, _I, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "s2f_linear_attn": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "s2f_affine_add_lif": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "s2f_upsample_add_lif": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "s2f_sigmoid_lif": (_I, [_P, _P, _L, _F, _P]),
     "s2f_semantic_tail": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "s2f_semantic_tail_ws_bytes": (_L, [_I, _I]),
+    "s2f_semantic_tail_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -41,6 +41,8 @@ struct TcParams {
   int bk;               // bytes of K per stage (32 / 64 / 128)
   int pieces, stages;
   int out_transposed;
+  int w_img_rows;       // packed weight rows per image (0: one weight matrix for all images)
+  int ss_img_stride;    // scale/shift elements per image (0: shared)
   float d_max;
 };
 
@@ -146,7 +148,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int t = tile_m % per_img;
     ho0 = (t / p.tiles_w) * p.TH;
     wo0 = (t % p.tiles_w) * p.TW;
+  } else if (p.w_img_rows) {
+    img = (tile_m * TC_BM) / p.M_img;        // M_img % 128 == 0 is required for per-image weights
   }
+  const int w_row0 = p.w_img_rows ? img * p.w_img_rows : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -164,7 +169,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         } else {
           tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, tile_m * TC_BM);
         }
-        tma_load_2d(sb, &map_b, &full[stage], c * p.bk, tile_n * nB);
+        tma_load_2d(sb, &map_b, &full[stage], c * p.bk, w_row0 + tile_n * nB);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -203,6 +208,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int co_base = tile_n * TC_BN;
+    const float* sc_ptr = p.scale + (int64_t)img * p.ss_img_stride;
+    const float* sh_ptr = p.shift + (int64_t)img * p.ss_img_stride;
 #pragma unroll 1
     for (int j0 = 0; j0 < TC_BN; j0 += 16) {
       if (co_base + j0 >= p.Cout) break;               // warp-uniform
@@ -224,7 +231,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int nvalid = min(16, p.Cout - co0);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        if (j < nvalid) y[j] = __fadd_rn(__fmul_rn(y[j], __ldg(p.scale + co0 + j)), __ldg(p.shift + co0 + j));
+        if (j < nvalid) y[j] = __fadd_rn(__fmul_rn(y[j], __ldg(sc_ptr + co0 + j)), __ldg(sh_ptr + co0 + j));
       }
       const int64_t row_off = m * p.Cout + co0;
       if (p.residual) {
@@ -323,6 +330,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   p.taps_w = a->KW; p.taps = a->KH * a->KW; p.stride = a->stride; p.pad = a->pad;
   p.bk = tc_bk(a->Cin); p.cin_chunks = (a->Cin + p.bk - 1) / p.bk;
   p.pieces = a->pieces; p.out_transposed = a->out_transposed; p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
+  const int per_img_w = a->per_image_weights ? 1 : 0;
   p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
   const int nB = TC_BN * p.pieces;
   const int stage_bytes = (TC_BM + nB) * p.bk;
@@ -330,6 +338,11 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) p.stages = 2;
   const int tiles_n = (a->Cout + TC_BN - 1) / TC_BN;
+  if (per_img_w) {
+    S2F_REQUIRE(!p.mode_conv && p.M_img % TC_BM == 0, "gemm_i8_tc: per-image weights need a 1x1 layer with Ho*Wo % 128 == 0");
+    p.w_img_rows = tiles_n * nB;
+    p.ss_img_stride = a->Cout;
+  }
   const int kpad = p.taps * tc_cin_pad(a->Cin);
 
   CUtensorMap map_a, map_b;
@@ -360,7 +373,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
     if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(A,2D) failed (%s) code %lld", "", (long long)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)tiles_n * nB};
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)tiles_n * nB * (per_img_w ? a->n : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)kpad};
     cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)nB};
     cuuint32_t es[2] = {1, 1};
@@ -379,6 +392,56 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
   gemm_i8_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("gemm_i8_tc_kernel");
+}
+
+// Device-side packer for weights that are produced on the GPU (one matrix per image): one block per row.
+namespace s2f {
+__global__ void __launch_bounds__(128) pack_rows_i8_kernel(const float* __restrict__ w, int ld, int rows_per_img, int K,
+                                                           int kpad, int pieces, int8_t* __restrict__ packed,
+                                                           float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                                           const float* __restrict__ bias_col, float post_scale) {
+  const int row = blockIdx.x;                       // global row = img * rows_per_img + r
+  const int img = row / rows_per_img, r = row % rows_per_img;
+  const float* src = w + (int64_t)row * ld;
+  __shared__ float red[128];
+  float mx = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, fabsf(src[k]));
+  red[threadIdx.x] = mx; __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+  mx = red[0];
+  int e = 0;
+  if (mx > 0.f) { frexpf(mx, &e); if (ldexpf(1.f, e - 1) == mx) e -= 1; }
+  const int F = 7 * pieces - 1;
+  const float inv = ldexpf(1.f, F - e);
+  const int tiles_n = (rows_per_img + TC_BN - 1) / TC_BN;
+  const int tile = r / TC_BN, rr = r % TC_BN;
+  int8_t* base = packed + (int64_t)img * tiles_n * pieces * TC_BN * kpad;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    int I = __float2int_rn(src[k] * inv);
+    int digit[3] = {0, 0, 0};
+    for (int pz = pieces - 1; pz >= 1; --pz) {
+      const int lo = (((I + 64) % 128 + 128) % 128) - 64;
+      digit[pz] = lo;
+      I = (I - lo) / 128;
+    }
+    digit[0] = I;
+    for (int pz = 0; pz < pieces; ++pz) base[((int64_t)(tile * pieces + pz) * TC_BN + rr) * kpad + k] = (int8_t)digit[pz];
+  }
+  if (threadIdx.x == 0) {
+    scale_out[row] = ldexpf(1.f, e - F) * post_scale;
+    shift_out[row] = bias_col ? bias_col[(int64_t)row * ld] : 0.f;
+  }
+}
+}  // namespace s2f
+
+extern "C" int s2f_pack_rows_i8_device(const float* w, int ld, int n_img, int rows_per_img, int K, int pieces,
+                                       int8_t* packed, float* scale_out, float* shift_out, const float* bias_col,
+                                       float post_scale, void* stream) {
+  S2F_REQUIRE(w && packed && scale_out && shift_out, "pack_rows_i8_device: null pointer");
+  S2F_REQUIRE(pieces >= 1 && pieces <= 3 && K >= 32 && K % tc_bk(K) == 0, "pack_rows_i8_device: K must be a multiple of its K block");
+  pack_rows_i8_kernel<<<n_img * rows_per_img, 128, 0, (cudaStream_t)stream>>>(w, ld, rows_per_img, K, K, pieces, packed,
+                                                                              scale_out, shift_out, bias_col, post_scale);
+  return check_launch("pack_rows_i8_kernel");
 }
 
 // Split fp32 weights [Cout, taps*Cin] (Cin fastest) into `pieces` signed base-128 digit planes.

@@ -174,6 +174,12 @@ class PixelDecoderPlan:
             L[f"lateral.{i}"] = _conv_gemm(sd, f"lateral_convs.{i}.0", f"lateral_convs.{i}.1", dev)
             L[f"output.{i}"] = _dw(sd, f"output_convs.{i}.0", f"output_convs.{i}.1", dev)
         L["mask_feature"] = _conv_gemm(sd, "mask_feature", None, dev)
+        # einsum(mask_embed, mask_feature(s)) == (mask_embed W_mf) s + mask_embed b: the per-image product
+        # [nq, C] x [W_mf^T ; b] is a tiny GEMM, after which mask_feature never has to be materialised.
+        wmf = sd["mask_feature.weight"][:, :, 0, 0].double()                      # [C_out, C_in]
+        waug = torch.cat([wmf.t(), sd["mask_feature.bias"].double()[None, :]], 0)  # [C_in + 1, C_out]
+        L["mask_fold"] = Gemm(waug, torch.ones(waug.shape[0], dtype=torch.float64),
+                              torch.zeros(waug.shape[0], dtype=torch.float64), waug.shape[1], device=dev)
 
 
 class HeadPlan:
@@ -384,7 +390,7 @@ def _sepconv_spike(L, prefix, key, sp, n, H, W, pr, residual=None, want_spike=Tr
     return L[prefix + ".pw2"](a, n, H, W, residual=residual, f32=True, spike=want_spike)
 
 
-def pixel_decoder_forward(model, feats, probe=NOPROBE):
+def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True):
     """DCNTransformerEncoderPixelDecoder.forward (pixel_decoder.py:417-472).
     Returns (mask_feature fp32 [n,H1,W1,C], memory levels, [y32, y64, y128] fp32 channels-last)."""
     plan = plan_of(model, PixelDecoderPlan)
@@ -446,9 +452,11 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE):
         hp, wp = h, w
     y = pr.real(pd + "mask_feature_spike", y)
     ysp = pr.spike(pd + "mask_feature_spike", ysp)
-    mf, _ = L["mask_feature"](ysp, n, hp, wp, f32=True)
-    mf = pr.real(pd + "mask_feature", mf)
-    return mf, memory, outs[:3]
+    mf = None
+    if want_mask_feature or pr.active:
+        mf, _ = L["mask_feature"](ysp, n, hp, wp, f32=True)
+        mf = pr.real(pd + "mask_feature", mf)
+    return (mf if want_mask_feature else ysp), memory, outs[:3]
 
 
 def pixel_decoder_forward_public(model, x):
@@ -487,7 +495,7 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
     Returns (cls [L,n,nq,K+1], mask levels int8 [L,n,nq,C], mask_feature [n,h,w,C]); L = 1 when last_only."""
     pd_model = model.pixel_decoder
     pr = probe
-    mf, memory, ms = pixel_decoder_forward(pd_model, feats, pr)
+    mf, memory, ms = pixel_decoder_forward(pd_model, feats, pr, want_mask_feature=False)   # mf: mask_feature_spike levels
     plan = plan_of(model, HeadPlan)
     L = plan.layers
     n = mf.shape[0]
@@ -554,36 +562,44 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
     return cls, me, mf
 
 
-def _mask_gemm(me_l, mf, n, h, w, nq, dim, alpha, transposed):
-    """einsum('bqc,bchw->bqhw') for one decoder output: mask_feature rows x per-image spike weights."""
-    wq = (me_l.float() * (alpha * INV)).contiguous()             # [n, nq, C] fp32 weights of this image
-    out, _ = ops.conv_simt(mf, wq, n=n, H=h, W=w, Cin=dim, Cout=nq, want_f32=True, transposed=transposed,
-                           w_img_stride=nq * dim)
+def _mask_pred(model, me_rows, ysp, transposed):
+    """einsum('bqc,bchw->bqhw', mask_embed, mask_feature) (maskformer_head.py:581) with the 1x1 mask_feature
+    convolution folded into the per-image weights: mask = (m W_mf) s + m b, m = alpha*level/8.
+    me_rows: int8 levels [n, R, C]; ysp: int8 levels of mask_feature_spike [n, h, w, C_in]."""
+    pdl = plan_of(model.pixel_decoder, PixelDecoderPlan).layers
+    n, R, dim = me_rows.shape
+    _, h, w, cin = ysp.shape
+    wb, _ = pdl["mask_fold"](me_rows.contiguous(), 1, n * R, 1, f32=True, a_scale=model.alpha * INV)   # [1, n*R, 1, cin+1]
+    packed, sc, sh = ops.pack_rows_i8_device(wb.view(n * R, cin + 1), n_img=n, rows_per_img=R, K=cin, pieces=TC_PIECES,
+                                             post_scale=INV, bias_col=cin)
+    out, _ = ops.gemm_tc(ysp, packed, n=n, H=h, W=w, Cin=cin, Cout=R, scale=sc, shift=sh, pieces=TC_PIECES,
+                         want_f32=True, transposed=transposed, per_image=True)
     return out
 
 
 def head_forward_public(model, x):
     feats = _import_feats(x)
     T = x[0].shape[0] if x[0].dim() == 5 else 1
-    cls, me, mf = head_forward(model, feats)
-    Ls, n, nq, _ = cls.shape
-    _, h, w, dim = mf.shape
-    masks = torch.stack([_mask_gemm(me[l], mf, n, h, w, nq, dim, model.alpha, True).view(n, nq, h, w)
-                         for l in range(Ls)])
+    cls, me, ysp = head_forward(model, feats)
+    Ls, n, nq, dim = me.shape
+    _, h, w, _ = ysp.shape
+    rows = me.permute(1, 0, 2, 3).reshape(n, Ls * nq, dim)
+    masks = _mask_pred(model, rows, ysp, True).view(n, Ls, nq, h, w).permute(1, 0, 2, 3, 4)
     B = n // T
     return cls.view(Ls, T, B, nq, -1).mean(1), masks.view(Ls, T, B, nq, h, w).mean(1)
 
 
-def _predict_from(model, feats, img_shape, probe=NOPROBE):
-    cls, me, mf = head_forward(model, feats, probe, last_only=True)
-    n, h, w, dim = mf.shape
+def _predict_from(model, feats, img_shape, probe=NOPROBE, labels=False):
+    cls, me, ysp = head_forward(model, feats, probe, last_only=True)
+    n, h, w, _ = ysp.shape
     nq = model.num_queries
-    mp = _mask_gemm(me[-1], mf, n, h, w, nq, dim, model.alpha, False)       # [n, h, w, nq] pixel-major
+    mp = _mask_pred(model, me[-1], ysp, False)                              # [n, h, w, nq] pixel-major
     cl = cls[-1].contiguous()
     mp = probe.real("mask_pred", mp)
     cl = probe.real("cls_score", cl, "same")
-    return ops.semantic_tail(mp.view(n, h * w, nq), cl, n=n, Q=nq, K=model.num_classes, h=h, w=w, H=img_shape[0],
-                             W=img_shape[1])
+    logits, lab = ops.semantic_tail(mp.view(n, h * w, nq), cl, n=n, Q=nq, K=model.num_classes, h=h, w=w,
+                                    H=img_shape[0], W=img_shape[1], want_logits=not labels, want_labels=labels)
+    return lab if labels else logits
 
 
 def head_predict(model, x, img_shape, probe=NOPROBE):
@@ -623,10 +639,10 @@ def profile_dominant(seg, img, steps=2):
                 per_class_ms={k: round(v["ms"] / steps, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])})
 
 
-def segmentor_logits(seg, img, probe=NOPROBE):
+def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
     """EncoderDecoder.encode_decode (encoder_decoder.py:125-133): internal tensors go straight to the head."""
     if seg.backbone.T != 1:
         raise NotImplementedError("T > 1 end-to-end inference is not used by any Spike2Former config")
     feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if probe.active else probe)
     pr = probe.scoped("decode_head.") if probe.active else probe
-    return _predict_from(seg.decode_head, feats, tuple(img.shape[-2:]), pr)
+    return _predict_from(seg.decode_head, feats, tuple(img.shape[-2:]), pr, labels)

@@ -198,7 +198,10 @@ class EncoderDecoder(_Engined):
     @torch.no_grad()
     def predict_labels(self, inputs):
         """argmax over classes, as BaseSegmentor.postprocess_result (segmentors/base.py:177-188)."""
-        return self.encode_decode(inputs).argmax(dim=1)
+        _require_cuda(inputs, type(self).__name__)
+        from . import engine
+
+        return engine.segmentor_logits(self, inputs, labels=True)      # argmax fused into the tail kernel (uint8)
 
 
 def build_segmentor(cfg) -> EncoderDecoder:

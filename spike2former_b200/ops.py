@@ -192,8 +192,25 @@ def tc_eligible(cin: int, k: int, stride: int) -> bool:
     return cin >= 32 and cin % 16 == 0 and k in (1, 3) and stride in (1, 2)
 
 
+def pack_rows_i8_device(w, *, n_img, rows_per_img, K, pieces=3, post_scale=1.0, bias_col=None):
+    """Device-side packer for per-image weight matrices: w fp32 [n_img*rows_per_img, ld] on the GPU ->
+    (digit planes in the per-image tile layout, scale [rows], shift [rows])."""
+    _ptr(w, torch.float32, "w")
+    ld = w.shape[1]
+    tiles_n = (rows_per_img + 63) // 64
+    packed = torch.zeros(n_img * tiles_n * pieces * 64 * K, dtype=torch.int8, device=w.device)
+    sc = torch.empty(n_img * rows_per_img, dtype=torch.float32, device=w.device)
+    sh = torch.empty_like(sc)
+    bias_ptr = C.c_void_p(w.data_ptr() + 4 * bias_col) if bias_col is not None else None
+    e0 = _p0()
+    check(_lib.lib().s2f_pack_rows_i8_device(_ptr(w), ld, n_img, rows_per_img, K, pieces, _ptr(packed), _ptr(sc), _ptr(sh),
+                                             bias_ptr, float(post_scale), _stream()), "s2f_pack_rows_i8_device")
+    _p1(e0, "elementwise", 0, _nb(w, packed))
+    return packed, sc, sh
+
+
 def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad=0, pieces=3, residual=None,
-            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX):
+            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX, per_image=False):
     """tcgen05 spike GEMM.  a: int8 levels channels-last; `scale` already contains rowscale * 1/8."""
     if a.dtype != torch.int8:
         raise S2FError("gemm_tc: a must be int8 levels")
@@ -210,6 +227,7 @@ def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad
     args.n, args.H, args.W, args.Cin, args.Cout = n, H, W, Cin, Cout
     args.KH = args.KW = k
     args.stride, args.pad, args.pieces, args.d_max = stride, pad, pieces, float(d_max)
+    args.per_image_weights = int(per_image)
     e0 = _p0()
     check(_lib.lib().s2f_gemm_i8_tc(C.byref(args), _stream()), "s2f_gemm_i8_tc")
     _p1(e0, "gemm_tc", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces)
@@ -284,8 +302,27 @@ def sigmoid_lif(x, d_max=D_MAX):
     return out
 
 
-def semantic_tail(mask_pred, cls, *, n, Q, K, h, w, H, W):
-    """softmax(cls)[..., :-1] x sigmoid(bilinear(mask_pred)) -> logits [n, K, H, W]."""
+def semantic_tail(mask_pred, cls, *, n, Q, K, h, w, H, W, want_logits=True, want_labels=False):
+    """Tensor-core tail: softmax(cls)[..., :-1] x sigmoid(bilinear(mask_pred)) -> (logits [n,K,H,W] | None,
+    labels uint8 [n,H,W] | None).  Falls outside the tcgen05 kernel's shape range only for Q > 128 or K > 256."""
+    if Q > 128 or K > 256:
+        if want_labels:
+            raise S2FError("semantic_tail: fused labels need Q <= 128 and K <= 256")
+        return semantic_tail_simt(mask_pred, cls, n=n, Q=Q, K=K, h=h, w=w, H=H, W=W), None
+    lib = _lib.lib()
+    logits = torch.empty((n, K, H, W), dtype=torch.float32, device=cls.device) if want_logits else None
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=cls.device) if want_labels else None
+    ws = torch.empty(lib.s2f_semantic_tail_ws_bytes(n, K), dtype=torch.uint8, device=cls.device)
+    e0 = _p0()
+    check(lib.s2f_semantic_tail_tc(_ptr(mask_pred, torch.float32, "mask_pred"), _ptr(cls, torch.float32, "cls"),
+                                   _ptr(logits), _ptr(labels), _ptr(ws), n, Q, K, h, w, H, W, _stream()),
+          "s2f_semantic_tail_tc")
+    _p1(e0, "semantic_tail", 2.0 * n * H * W * Q * K, _nb(mask_pred, logits, labels))
+    return logits, labels
+
+
+def semantic_tail_simt(mask_pred, cls, *, n, Q, K, h, w, H, W):
+    """CUDA-core version (any Q / K): softmax(cls)[..., :-1] x sigmoid(bilinear(mask_pred)) -> logits [n, K, H, W]."""
     logits = torch.empty((n, K, H, W), dtype=torch.float32, device=cls.device)
     prob = torch.empty((n, Q, K), dtype=torch.float32, device=cls.device)
     e0 = _p0()

@@ -219,9 +219,14 @@ def test_semantic_tail_vs_torch():
     cls = torch.randn(n, Q, K + 1, generator=g) * 4
     up = F.interpolate(mp, size=(2 * h, 2 * w), mode="bilinear", align_corners=False)
     ref = torch.einsum("bqc,bqhw->bchw", F.softmax(cls, -1)[..., :-1], up.sigmoid())
-    got = ops.semantic_tail(mp.permute(0, 2, 3, 1).contiguous().cuda(), cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=2 * h,
-                            W=2 * w)
+    mpp = mp.permute(0, 2, 3, 1).contiguous().cuda()
+    got = ops.semantic_tail_simt(mpp, cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=2 * h, W=2 * w)
     assert (got.cpu() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    # tensor-core tail: bf16 hi+lo split operands keep ~16 mantissa bits
+    got_tc, lab = ops.semantic_tail(mpp, cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=2 * h, W=2 * w, want_labels=True)
+    assert (got_tc.cpu() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(lab.cpu().long(), got_tc.cpu().argmax(1))
+    assert (lab.cpu().long() == ref.argmax(1)).float().mean().item() > 0.999
 
 
 def test_cpu_tensors_are_rejected():
