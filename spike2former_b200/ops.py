@@ -46,7 +46,7 @@ class Profiler:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for cls, e0, e1, fl, by in self.records:
+        for cls, e0, e1, fl, by, _ in self.records:
             a = agg.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
             a["ms"] += e0.elapsed_time(e1); a["flops"] += fl; a["bytes"] += by; a["launches"] += 1
         return agg
@@ -68,12 +68,12 @@ def _p0():
     return e
 
 
-def _p1(e0, cls, flops=0.0, nbytes=0.0):
+def _p1(e0, cls, flops=0.0, nbytes=0.0, detail=""):
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    _PROF.records.append((cls, e0, e1, float(flops), float(nbytes)))
+    _PROF.records.append((cls, e0, e1, float(flops), float(nbytes), detail))
 
 
 def _nb(*ts):
@@ -165,7 +165,8 @@ def conv_simt(a, w, *, n, H, W, Cin, Cout, k=1, stride=1, pad=0, scale=None, shi
     args.w_img_stride, args.d_max = int(w_img_stride), float(d_max)
     e0 = _p0()
     check(_lib.lib().s2f_conv_simt(C.byref(args), _stream()), "s2f_conv_simt")
-    _p1(e0, "gemm_simt", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * 4)
+    _p1(e0, "gemm_simt", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * 4,
+        f"{n}x{H}x{W} {Cin}->{Cout} k{k}s{stride} {a.dtype}")
     return out_f32, out_spike
 
 
@@ -230,7 +231,8 @@ def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad
     args.per_image_weights = int(per_image)
     e0 = _p0()
     check(_lib.lib().s2f_gemm_i8_tc(C.byref(args), _stream()), "s2f_gemm_i8_tc")
-    _p1(e0, "gemm_tc", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces)
+    _p1(e0, "gemm_tc", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces,
+        f"{n}x{H}x{W} {Cin}->{Cout} k{k}s{stride} f32={int(want_f32)} sp={int(want_spike)} res={int(residual is not None)} tr={int(transposed)}")
     return out_f32, out_spike
 
 
