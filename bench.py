@@ -190,6 +190,8 @@ def main():
     e1.record()
     barrier()
     launches = ops.launch_count() - l0
+    if launches == 0:      # CUDA-graph replay: the library's counter only sees the capture; one replay = that many kernels
+        launches = args.steps * sum(g.launches for k, g in seg._graphs.items() if not k[2])
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     t = torch.tensor([ms], device=dev)

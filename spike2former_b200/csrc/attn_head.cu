@@ -87,6 +87,181 @@ __global__ void __launch_bounds__(256) qkv_kernel(const int8_t* __restrict__ q, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path (d % 4 == 0, 4-byte aligned rows): K^T V on the int8 tensor-core path.
+//   kv[i][j] = sum_tok K[tok][i] V[tok][j] is a GEMM whose reduction axis (tokens) is the slow axis of both operands in
+//   memory, so a block first transposes 128-token tiles of K and V into shared memory (4 tokens x 4 channels per
+//   thread, a 4x4 byte transpose with PRMT), after which every mma.sync.m16n8k32.s8 fragment is one 32-bit LDS.
+//   Each of the 4 warps reduces its own 32 tokens of the tile into the full d x d accumulator; warps are summed
+//   through shared memory and one atomicAdd per entry goes to the global workspace.
+constexpr int KT_TOK = 128;                    // tokens per staged tile
+constexpr int KT_LD = KT_TOK + 16;             // bytes per transposed row (36 words: conflict-free fragment loads)
+
+__device__ __forceinline__ void mma_s8(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int MT>      // MT = ceil(d / 16) row tiles; column tiles NT = 2 * MT
+__global__ void __launch_bounds__(128) kv_mma_kernel(const int8_t* __restrict__ k, const int8_t* __restrict__ v,
+                                                     int32_t* __restrict__ kv, int Nk, int heads, int d, int ld,
+                                                     int tok_per_block) {
+  constexpr int NT = 2 * MT;
+  constexpr int DP = 16 * MT;                  // padded head dim
+  __shared__ __align__(16) uint8_t tiles[2 * DP * KT_LD];
+  uint8_t* kt = tiles;
+  uint8_t* vt = tiles + DP * KT_LD;
+  const int img = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.y * tok_per_block;
+  const int t_end = min(Nk, t_begin + tok_per_block);
+  const int8_t* kb = k + ((int64_t)img * Nk) * ld + h * d;
+  const int8_t* vb = v + ((int64_t)img * Nk) * ld + h * d;
+  // rows d..DP-1 of the transposed tiles are never written by the loader: clear them once
+  for (int e = threadIdx.x; e < (DP - d) * KT_LD / 4; e += blockDim.x) {
+    reinterpret_cast<uint32_t*>(kt + d * KT_LD)[e] = 0u;
+    reinterpret_cast<uint32_t*>(vt + d * KT_LD)[e] = 0u;
+  }
+  int acc[MT][NT][4];
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = acc[mi][ni][2] = acc[mi][ni][3] = 0;
+  const int cgn = d >> 2;                      // channel groups of 4
+  const int gid = lane >> 2, tig = lane & 3;
+  for (int t0 = t_begin; t0 < t_end; t0 += KT_TOK) {
+    __syncthreads();                           // previous tile fully consumed
+    for (int e = threadIdx.x; e < (KT_TOK / 4) * cgn; e += blockDim.x) {
+      const int cg = e % cgn, tg = e / cgn;
+      const int tok = t0 + tg * 4;
+      uint32_t wk[4], wv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool ok = tok + r < t_end;
+        wk[r] = ok ? __ldg(reinterpret_cast<const uint32_t*>(kb + (int64_t)(tok + r) * ld + cg * 4)) : 0u;
+        wv[r] = ok ? __ldg(reinterpret_cast<const uint32_t*>(vb + (int64_t)(tok + r) * ld + cg * 4)) : 0u;
+      }
+      auto tr = [&](const uint32_t (&w)[4], uint8_t* dst) {
+        const uint32_t a_lo = __byte_perm(w[0], w[1], 0x5140), a_hi = __byte_perm(w[0], w[1], 0x7362);
+        const uint32_t b_lo = __byte_perm(w[2], w[3], 0x5140), b_hi = __byte_perm(w[2], w[3], 0x7362);
+        uint8_t* o = dst + (cg * 4) * KT_LD + tg * 4;
+        *reinterpret_cast<uint32_t*>(o) = __byte_perm(a_lo, b_lo, 0x5410);
+        *reinterpret_cast<uint32_t*>(o + KT_LD) = __byte_perm(a_lo, b_lo, 0x7632);
+        *reinterpret_cast<uint32_t*>(o + 2 * KT_LD) = __byte_perm(a_hi, b_hi, 0x5410);
+        *reinterpret_cast<uint32_t*>(o + 3 * KT_LD) = __byte_perm(a_hi, b_hi, 0x7632);
+      };
+      tr(wk, kt);
+      tr(wv, vt);
+    }
+    __syncthreads();
+    const int tb = warp * 32;                  // this warp's 32 tokens of the tile
+    uint32_t bf[NT][2];
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+      const uint8_t* pv = vt + (ni * 8 + gid) * KT_LD + tb + tig * 4;
+      bf[ni][0] = *reinterpret_cast<const uint32_t*>(pv);
+      bf[ni][1] = *reinterpret_cast<const uint32_t*>(pv + 16);
+    }
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+      uint32_t af[4];
+      const uint8_t* pk = kt + (mi * 16 + gid) * KT_LD + tb + tig * 4;
+      af[0] = *reinterpret_cast<const uint32_t*>(pk);
+      af[1] = *reinterpret_cast<const uint32_t*>(pk + 8 * KT_LD);
+      af[2] = *reinterpret_cast<const uint32_t*>(pk + 16);
+      af[3] = *reinterpret_cast<const uint32_t*>(pk + 8 * KT_LD + 16);
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) mma_s8(acc[mi][ni], af, bf[ni]);
+    }
+  }
+  // cross-warp sum through shared memory (the transposed tiles are dead by now)
+  __syncthreads();
+  int32_t* red = reinterpret_cast<int32_t*>(tiles);       // [DP][DP] int32: DP*DP*4 bytes <= 2*DP*KT_LD
+  static_assert(DP * 4 <= 2 * KT_LD, "reduction buffer must fit in the two transposed tiles");
+  for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) red[e] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+      const int r0 = mi * 16 + gid, c0 = ni * 8 + tig * 2;
+      atomicAdd(&red[r0 * DP + c0], acc[mi][ni][0]);
+      atomicAdd(&red[r0 * DP + c0 + 1], acc[mi][ni][1]);
+      atomicAdd(&red[(r0 + 8) * DP + c0], acc[mi][ni][2]);
+      atomicAdd(&red[(r0 + 8) * DP + c0 + 1], acc[mi][ni][3]);
+    }
+  __syncthreads();
+  int32_t* out = kv + ((int64_t)img * heads + h) * d * d;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e % d;
+    const int val = red[i * DP + j];
+    if (val != 0) atomicAdd(out + e, val);
+  }
+}
+
+// out[img, tok, h*d + j..j+3] for one (token, 4 channels) per thread: q as 32-bit words, kv rows as int4 from smem.
+// WIDE = 64-bit accumulation (needed only when 8 * 64 * Nk * d can exceed 2^31).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) qkv_fast_kernel(const int8_t* __restrict__ q, const int32_t* __restrict__ kv,
+                                                       int8_t* __restrict__ out_spike, float* __restrict__ out_f32,
+                                                       int Nq, int heads, int d, int q_ld, int out_ld, float out_scale,
+                                                       float d_max, int tok_per_block) {
+  extern __shared__ __align__(16) int32_t kvs4[];     // [heads][d][d]
+  const int img = blockIdx.y;
+  const int C = heads * d;
+  const int32_t* kvb = kv + (int64_t)img * heads * d * d;
+  for (int e = threadIdx.x; e < heads * d * d / 4; e += blockDim.x)
+    reinterpret_cast<int4*>(kvs4)[e] = __ldg(reinterpret_cast<const int4*>(kvb) + e);
+  __syncthreads();
+  const int g4n = out_ld >> 2;                         // 4-channel groups per output row (incl. padding columns)
+  const int tok0 = blockIdx.x * tok_per_block;
+  const int ntok = min(tok_per_block, Nq - tok0);
+  for (int e = threadIdx.x; e < ntok * g4n; e += blockDim.x) {
+    const int tok = tok0 + e / g4n, c = (e % g4n) * 4;
+    const int64_t o = ((int64_t)img * Nq + tok) * out_ld + c;
+    if (c >= C) {
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (out_spike) *reinterpret_cast<uint32_t*>(out_spike + o) = 0u;
+      continue;
+    }
+    const int h = c / d, j = c % d;
+    const int8_t* qrow = q + ((int64_t)img * Nq + tok) * q_ld + h * d;
+    const int32_t* kvh = kvs4 + h * d * d + j;
+    float y[4];
+    if (WIDE) {
+      long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      for (int i = 0; i < d; i += 4) {
+        const uint32_t qw = __ldg(reinterpret_cast<const uint32_t*>(qrow + i));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const long long qi = (int8_t)((qw >> (8 * b)) & 0xff);
+          const int4 kr = *reinterpret_cast<const int4*>(kvh + (i + b) * d);
+          s0 += qi * kr.x; s1 += qi * kr.y; s2 += qi * kr.z; s3 += qi * kr.w;
+        }
+      }
+      y[0] = (float)s0 * out_scale; y[1] = (float)s1 * out_scale; y[2] = (float)s2 * out_scale; y[3] = (float)s3 * out_scale;
+    } else {
+      int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      for (int i = 0; i < d; i += 4) {
+        const uint32_t qw = __ldg(reinterpret_cast<const uint32_t*>(qrow + i));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int qi = (int8_t)((qw >> (8 * b)) & 0xff);
+          const int4 kr = *reinterpret_cast<const int4*>(kvh + (i + b) * d);
+          s0 += qi * kr.x; s1 += qi * kr.y; s2 += qi * kr.z; s3 += qi * kr.w;
+        }
+      }
+      y[0] = (float)s0 * out_scale; y[1] = (float)s1 * out_scale; y[2] = (float)s2 * out_scale; y[3] = (float)s3 * out_scale;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_spike)
+      *reinterpret_cast<uint32_t*>(out_spike + o) =
+          (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
+          ((uint32_t)(int)spike_level(y[2], d_max) << 16) | ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sigmoid_lif_kernel(const float* __restrict__ x, int8_t* __restrict__ levels,
                                                           int64_t N, float d_max) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
@@ -177,18 +352,56 @@ extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v
   const int dd = d * d;
   cudaError_t e = cudaMemsetAsync(kv_ws, 0, sizeof(int32_t) * (size_t)n * heads * dd, st);
   if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "linear_attn memset: %s", cudaGetErrorString(e));
-  // enough token slices to fill the GPU, at least 256 tokens each
-  int splits = (int)ceil_div(148 * 4, (int64_t)n * heads);
-  const int max_splits = (int)ceil_div(Nk, 256);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  const int tok_per_block = (int)ceil_div(ceil_div(Nk, splits), KV_TOK) * KV_TOK;
-  splits = (int)ceil_div(Nk, tok_per_block);
-  kv_kernel<<<dim3(n * heads, splits), 256, 2 * KV_TOK * d, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
-  int rc = check_launch("kv_kernel");
+  auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; };
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool fast_kv = d % 4 == 0 && kv_ld % 4 == 0 && al4(k) && al4(v);
+  int rc;
+  if (fast_kv) {
+    // token slices of >= 512 tokens, enough blocks for ~2 per SM
+    int splits = (int)ceil_div(148 * 2, (int64_t)n * heads);
+    const int max_splits = (int)ceil_div(Nk, 512);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int tok_per_block = (int)ceil_div(ceil_div(Nk, splits), KT_TOK) * KT_TOK;
+    splits = (int)ceil_div(Nk, tok_per_block);
+    const dim3 grid(n * heads, splits);
+    if (d <= 16) kv_mma_kernel<1><<<grid, 128, 0, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
+    else if (d <= 32) kv_mma_kernel<2><<<grid, 128, 0, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
+    else if (d <= 48) kv_mma_kernel<3><<<grid, 128, 0, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
+    else kv_mma_kernel<4><<<grid, 128, 0, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
+    rc = check_launch("kv_mma_kernel");
+  } else {
+    // enough token slices to fill the GPU, at least 256 tokens each
+    int splits = (int)ceil_div(148 * 4, (int64_t)n * heads);
+    const int max_splits = (int)ceil_div(Nk, 256);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int tok_per_block = (int)ceil_div(ceil_div(Nk, splits), KV_TOK) * KV_TOK;
+    splits = (int)ceil_div(Nk, tok_per_block);
+    kv_kernel<<<dim3(n * heads, splits), 256, 2 * KV_TOK * d, st>>>(k, v, kv_ws, Nk, heads, d, kv_ld, tok_per_block);
+    rc = check_launch("kv_kernel");
+  }
   if (rc) return rc;
   const size_t sm = sizeof(int32_t) * (size_t)heads * dd;
   S2F_REQUIRE(sm <= 200 * 1024, "linear_attn: heads*d*d too large for shared memory");
+  const bool fast_q = d % 4 == 0 && q_ld % 4 == 0 && out_ld % 4 == 0 && al4(q) && al16(kv_ws) && (!out_f32 || al16(out_f32)) &&
+                      (!out_spike || al4(out_spike));
+  if (fast_q) {
+    const bool wide = (double)8 * 64 * (double)Nk * d >= 2147483648.0;
+    // tokens per block: amortise the kv staging, keep >= ~2 blocks per SM
+    int tpb = (int)ceil_div((int64_t)Nq * n, 148 * 2);
+    if (tpb < 8) tpb = 8;
+    if (tpb > 64) tpb = 64;
+    const dim3 grid((unsigned)ceil_div(Nq, tpb), n);
+    if (wide) {
+      if (sm > 48 * 1024) cudaFuncSetAttribute(qkv_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      qkv_fast_kernel<true><<<grid, 256, sm, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld, out_ld, out_scale, d_max, tpb);
+    } else {
+      if (sm > 48 * 1024) cudaFuncSetAttribute(qkv_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      qkv_fast_kernel<false><<<grid, 256, sm, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld, out_ld, out_scale, d_max, tpb);
+    }
+    return check_launch("qkv_fast_kernel");
+  }
   if (sm > 48 * 1024) cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   qkv_kernel<<<dim3((unsigned)ceil_div(Nq, 32), n), 256, sm, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld,
                                                                    out_ld, out_scale, d_max);

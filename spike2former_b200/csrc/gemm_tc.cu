@@ -22,7 +22,6 @@ namespace s2f {
 constexpr int TC_BM = 128;        // rows (pixels / tokens) per tile == UMMA M
 constexpr int TC_BN = 64;         // output channels per tile
 constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 256;
 
 __host__ __device__ inline int tc_bk(int cin) { return cin >= 128 ? 128 : (cin >= 64 ? 64 : 32); }
 __host__ __device__ inline int tc_cin_pad(int cin) { const int bk = tc_bk(cin); return (cin + bk - 1) / bk * bk; }
@@ -41,6 +40,8 @@ struct TcParams {
   int bk;               // bytes of K per stage (32 / 64 / 128)
   int pieces, stages;
   int out_transposed;
+  int tiles_n, total_tiles;
+  int big_k;            // accumulators may exceed 2^22: convert with I2F instead of the magic-number trick
   int w_img_rows;       // packed weight rows per image (0: one weight matrix for all images)
   int ss_img_stride;    // scale/shift elements per image (0: shared)
   float d_max;
@@ -54,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -108,6 +112,43 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int bk) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+// Persistent: one CTA per SM walks the tile list (n-tile fastest, so CTAs running side by side share the A tile in L2).
+// Two accumulator buffers in TMEM (2 x 256 columns) let the epilogue of tile i overlap the main loop of tile i+1.
+constexpr int TC_ACC_COLS = 256;
+
+struct TileOrigin { int img, ho0, wo0, tile_m, tile_n; };
+
+__device__ __forceinline__ TileOrigin tile_origin(const TcParams& p, int tile) {
+  TileOrigin o;
+  o.tile_n = tile % p.tiles_n;
+  o.tile_m = tile / p.tiles_n;
+  o.img = 0; o.ho0 = 0; o.wo0 = 0;
+  if (p.mode_conv) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    o.img = o.tile_m / per_img;
+    const int t = o.tile_m % per_img;
+    o.ho0 = (t / p.tiles_w) * p.TH;
+    o.wo0 = (t % p.tiles_w) * p.TW;
+  } else if (p.w_img_rows) {
+    o.img = (o.tile_m * TC_BM) / p.M_img;      // M_img % 128 == 0 is required for per-image weights
+  }
+  return o;
+}
+
+// int32 accumulator -> float without I2F (valid for |d| < 2^22): 0x4B400000 is 1.5 * 2^23
+__device__ __forceinline__ float acc_to_float(uint32_t d, bool big) {
+  return big ? (float)(int)d : __uint_as_float(d + 0x4B400000u) - 12582912.f;
+}
+// NI-LIF level of y as the low byte of the returned word: round-half-even by the 2^23 trick (== rintf on [0, d_max])
+__device__ __forceinline__ uint32_t level_bits(float y, float d_max) {
+  return __float_as_uint(fminf(fmaxf(y, 0.f), d_max) + 8388608.f);
+}
+__device__ __forceinline__ uint32_t pack_levels(float a, float b, float c, float d, float d_max) {
+  const uint32_t lo = __byte_perm(level_bits(a, d_max), level_bits(b, d_max), 0x0040);
+  const uint32_t hi = __byte_perm(level_bits(c, d_max), level_bits(d, d_max), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -117,22 +158,22 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int stage_bytes = a_bytes + b_bytes;          // multiples of 1024
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + p.stages;             // [2]
+  uint64_t* tmem_empty = tmem_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int num_chunks = p.taps * p.cin_chunks;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * TC_ACC_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -140,37 +181,28 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile origin
-  int img = 0, ho0 = 0, wo0 = 0;
-  if (p.mode_conv) {
-    const int per_img = p.tiles_w * p.tiles_h;
-    img = tile_m / per_img;
-    const int t = tile_m % per_img;
-    ho0 = (t / p.tiles_w) * p.TH;
-    wo0 = (t % p.tiles_w) * p.TW;
-  } else if (p.w_img_rows) {
-    img = (tile_m * TC_BM) / p.M_img;        // M_img % 128 == 0 is required for per-image weights
-  }
-  const int w_row0 = p.w_img_rows ? img * p.w_img_rows : 0;
-
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer
       int stage = 0, phase = 0;
-      for (int c = 0; c < num_chunks; ++c) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-        const int tap = c / p.cin_chunks, cc = c % p.cin_chunks;
-        if (p.mode_conv) {
-          const int kh = tap / p.taps_w, kw = tap % p.taps_w;
-          tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, wo0 * p.stride - p.pad + kw, ho0 * p.stride - p.pad + kh, img);
-        } else {
-          tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, tile_m * TC_BM);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileOrigin o = tile_origin(p, tile);
+        const int w_row0 = (p.w_img_rows ? o.img * p.w_img_rows : 0) + o.tile_n * nB;
+        for (int c = 0; c < num_chunks; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          const int tap = c / p.cin_chunks, cc = c % p.cin_chunks;
+          if (p.mode_conv) {
+            const int kh = tap / p.taps_w, kw = tap % p.taps_w;
+            tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, o.wo0 * p.stride - p.pad + kw, o.ho0 * p.stride - p.pad + kh, o.img);
+          } else {
+            tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, o.tile_m * TC_BM);
+          }
+          tma_load_2d(sb, &map_b, &full[stage], c * p.bk, w_row0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tma_load_2d(sb, &map_b, &full[stage], c * p.bk, w_row0 + tile_n * nB);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -178,111 +210,136 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // ===== MMA issuer
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major, N>>3 @17, M>>4 @24
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nB >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0, phase = 0;
-      for (int c = 0; c < num_chunks; ++c) {
-        mbar_wait(&full[stage], phase);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint64_t da = smem_desc(sa, p.bk), db = smem_desc(sa + a_bytes, p.bk);
-        const int nk = p.bk / 32;
-        for (int k = 0; k < nk; ++k)
-          umma_i8(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);   // +32 B per K step
-        umma_commit(&empty[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
+        for (int c = 0; c < num_chunks; ++c) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t da = smem_desc(sa, p.bk), db = smem_desc(sa + a_bytes, p.bk);
+          const int nk = p.bk / 32;
+          for (int k = 0; k < nk; ++k)
+            umma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);   // +32 B per K step
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
       }
-      umma_commit(tmem_full);
     }
   } else {
     // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32); thread = one output row
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    int64_t m;            // flat output row (n*Ho*Wo index), -1 if outside
-    if (p.mode_conv) {
-      const int ho = ho0 + r / p.TW, wo = wo0 + r % p.TW;
-      m = (ho < p.Ho && wo < p.Wo) ? ((int64_t)img * p.Ho + ho) * p.Wo + wo : -1;
-    } else {
-      m = (int64_t)tile_m * TC_BM + r;
-      if (m >= p.M_total) m = -1;
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int co_base = tile_n * TC_BN;
-    const float* sc_ptr = p.scale + (int64_t)img * p.ss_img_stride;
-    const float* sh_ptr = p.shift + (int64_t)img * p.ss_img_stride;
+    const bool big = p.big_k != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileOrigin o = tile_origin(p, tile);
+      const int acc = it & 1;
+      int64_t m;            // flat output row (n*Ho*Wo index), -1 if outside
+      if (p.mode_conv) {
+        const int ho = o.ho0 + r / p.TW, wo = o.wo0 + r % p.TW;
+        m = (ho < p.Ho && wo < p.Wo) ? ((int64_t)o.img * p.Ho + ho) * p.Wo + wo : -1;
+      } else {
+        m = (int64_t)o.tile_m * TC_BM + r;
+        if (m >= p.M_total) m = -1;
+      }
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
+      const int co_base = o.tile_n * TC_BN;
+      const float* sc_ptr = p.scale + (int64_t)o.img * p.ss_img_stride;
+      const float* sh_ptr = p.shift + (int64_t)o.img * p.ss_img_stride;
 #pragma unroll 1
-    for (int j0 = 0; j0 < TC_BN; j0 += 16) {
-      if (co_base + j0 >= p.Cout) break;               // warp-uniform
-      uint32_t d0[16], d1[16], d2[16];
-      tmem_ld16(trow + j0, d0);
-      if (p.pieces > 1) tmem_ld16(trow + TC_BN + j0, d1);
-      if (p.pieces > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
-      tmem_ld_wait();
-      if (m < 0) continue;
-      float y[16];
+      for (int j0 = 0; j0 < TC_BN; j0 += 16) {
+        if (co_base + j0 >= p.Cout) break;               // warp-uniform
+        uint32_t d0[16], d1[16], d2[16];
+        tmem_ld16(trow + j0, d0);
+        if (p.pieces > 1) tmem_ld16(trow + TC_BN + j0, d1);
+        if (p.pieces > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
+        tmem_ld_wait();
+        if (m < 0) continue;
+        float y[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v = (float)(int)d0[j];
-        if (p.pieces > 1) v = fmaf(v, 128.f, (float)(int)d1[j]);
-        if (p.pieces > 2) v = fmaf(v, 128.f, (float)(int)d2[j]);
-        y[j] = v;
-      }
-      const int co0 = co_base + j0;
-      const int nvalid = min(16, p.Cout - co0);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < nvalid) y[j] = __fadd_rn(__fmul_rn(y[j], __ldg(sc_ptr + co0 + j)), __ldg(sh_ptr + co0 + j));
-      }
-      const int64_t row_off = m * p.Cout + co0;
-      if (p.residual) {
-        if (nvalid == 16 && (p.Cout & 3) == 0) {
+        for (int j = 0; j < 16; ++j) {
+          float v = acc_to_float(d0[j], big);
+          if (p.pieces > 1) v = fmaf(v, 128.f, acc_to_float(d1[j], big));
+          if (p.pieces > 2) v = fmaf(v, 128.f, acc_to_float(d2[j], big));
+          y[j] = v;
+        }
+        const int co0 = co_base + j0;
+        const int nvalid = min(16, p.Cout - co0);
+        const bool full16 = nvalid == 16 && (p.Cout & 3) == 0;
+        if (full16) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 rv = *reinterpret_cast<const float4*>(p.residual + row_off + 4 * q);
-            y[4 * q] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(sc_ptr + co0) + q);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(sh_ptr + co0) + q);
+            y[4 * q] = __fadd_rn(__fmul_rn(y[4 * q], sc.x), sh.x);
+            y[4 * q + 1] = __fadd_rn(__fmul_rn(y[4 * q + 1], sc.y), sh.y);
+            y[4 * q + 2] = __fadd_rn(__fmul_rn(y[4 * q + 2], sc.z), sh.z);
+            y[4 * q + 3] = __fadd_rn(__fmul_rn(y[4 * q + 3], sc.w), sh.w);
           }
         } else {
-          for (int j = 0; j < nvalid; ++j) y[j] += p.residual[row_off + j];
-        }
-      }
-      if (!p.out_transposed) {
-        if (p.out_f32) {
-          if (nvalid == 16 && (p.Cout & 3) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(p.out_f32 + row_off + 4 * q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) y[j] = __fadd_rn(__fmul_rn(y[j], __ldg(sc_ptr + co0 + j)), __ldg(sh_ptr + co0 + j));
+        }
+        const int64_t row_off = m * p.Cout + co0;
+        if (p.residual) {
+          if (full16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 rv = *reinterpret_cast<const float4*>(p.residual + row_off + 4 * q);
+              y[4 * q] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
+            }
           } else {
-            for (int j = 0; j < nvalid; ++j) p.out_f32[row_off + j] = y[j];
+            for (int j = 0; j < nvalid; ++j) y[j] += p.residual[row_off + j];
           }
         }
-        if (p.out_spike) {
-          if (nvalid == 16 && (p.Cout & 15) == 0) {
-            uint32_t w[4];
+        if (!p.out_transposed) {
+          if (p.out_f32) {
+            if (full16) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              w[q] = (uint32_t)(int)spike_level(y[4 * q], p.d_max) | ((uint32_t)(int)spike_level(y[4 * q + 1], p.d_max) << 8) |
-                     ((uint32_t)(int)spike_level(y[4 * q + 2], p.d_max) << 16) | ((uint32_t)(int)spike_level(y[4 * q + 3], p.d_max) << 24);
-            *reinterpret_cast<uint4*>(p.out_spike + row_off) = make_uint4(w[0], w[1], w[2], w[3]);
-          } else {
-            for (int j = 0; j < nvalid; ++j) p.out_spike[row_off + j] = (int8_t)(int)spike_level(y[j], p.d_max);
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(p.out_f32 + row_off + 4 * q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+            } else {
+              for (int j = 0; j < nvalid; ++j) p.out_f32[row_off + j] = y[j];
+            }
+          }
+          if (p.out_spike) {
+            if (nvalid == 16 && (p.Cout & 15) == 0) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) w[q] = pack_levels(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3], p.d_max);
+              *reinterpret_cast<uint4*>(p.out_spike + row_off) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              for (int j = 0; j < nvalid; ++j) p.out_spike[row_off + j] = (int8_t)(level_bits(y[j], p.d_max) & 0xffu);
+            }
+          }
+        } else {
+          const int64_t im = m / p.M_img, pm = m % p.M_img;
+          const int64_t tbase = im * (int64_t)p.M_img * p.Cout + pm;
+          for (int j = 0; j < nvalid; ++j) {
+            const int64_t oo = tbase + (int64_t)(co0 + j) * p.M_img;
+            if (p.out_f32) p.out_f32[oo] = y[j];
+            if (p.out_spike) p.out_spike[oo] = (int8_t)(level_bits(y[j], p.d_max) & 0xffu);
           }
         }
-      } else {
-        const int64_t im = m / p.M_img, pm = m % p.M_img;
-        const int64_t tbase = im * (int64_t)p.M_img * p.Cout + pm;
-        for (int j = 0; j < nvalid; ++j) {
-          const int64_t o = tbase + (int64_t)(co0 + j) * p.M_img;
-          if (p.out_f32) p.out_f32[o] = y[j];
-          if (p.out_spike) p.out_spike[o] = (int8_t)(int)spike_level(y[j], p.d_max);
-        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_ACC_COLS));
   }
 }
 
@@ -334,8 +391,8 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
   const int nB = TC_BN * p.pieces;
   const int stage_bytes = (TC_BM + nB) * p.bk;
-  p.stages = 100 * 1024 / stage_bytes;
-  if (p.stages > 8) p.stages = 8;
+  p.stages = 196 * 1024 / stage_bytes;               // one persistent CTA per SM owns the whole shared memory
+  if (p.stages > 10) p.stages = 10;
   if (p.stages < 2) p.stages = 2;
   const int tiles_n = (a->Cout + TC_BN - 1) / TC_BN;
   if (per_img_w) {
@@ -382,14 +439,24 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(B) failed (%s) code %lld", "", (long long)r);
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  p.tiles_n = tiles_n;
+  p.total_tiles = tiles_m * tiles_n;
+  p.big_k = ((int64_t)kpad * 8 * 64 >= (1ll << 22)) ? 1 : 0;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;          // never two CTAs on one SM: each allocates all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "gemm_i8_tc: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
   gemm_i8_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("gemm_i8_tc_kernel");
 }

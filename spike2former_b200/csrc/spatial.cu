@@ -6,64 +6,107 @@ namespace s2f {
 
 // ------------------------------------------------------------------------------------------------
 // Depthwise k x k, stride 1, 'same' padding (or no padding when no_pad, output shrinks by k-1).
-// One thread = one output pixel x 4 channels.  Weights are given tap-major [k*k, C] so a warp reads
-// consecutive channels of one tap.  fp32 accumulate in the reference's tap order (kh, kw).
-template <typename AT, int KS>
+// One thread = a strip of TW consecutive output pixels of one row x 4 channels.  Per kernel row it loads the
+// TW + k - 1 input pixels once (one 32-bit word = 4 int8 channels, unpacked with PRMT + FADD instead of I2F) and the
+// k weight vectors once, so the inner loop is ~65 % FFMA.  Threads run over channels fastest: every warp access is a
+// contiguous row segment.  Weights are tap-major [k*k, C].  fp32 accumulation in the reference's tap order (kh, kw).
+// One input pixel x 4 channels as raw bits (int8: one 32-bit word; fp32: a float4), loaded unconditionally from a clamped
+// address so that the compiler can issue all loads of a row back to back.
+struct Raw8 { uint32_t w; };
+struct Raw32 { float4 v; };
+__device__ __forceinline__ Raw8 load_raw(const int8_t* p) { return Raw8{__ldg(reinterpret_cast<const uint32_t*>(p))}; }
+__device__ __forceinline__ Raw32 load_raw(const float* p) { return Raw32{__ldg(reinterpret_cast<const float4*>(p))}; }
+__device__ __forceinline__ void unpack4(Raw8 r, bool ok, float& x0, float& x1, float& x2, float& x3) {
+  const uint32_t raw = ok ? r.w : 0u;
+  // levels are 0..127: 0x4B0000xx is the float 8388608 + xx
+  x0 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7650)) - 8388608.f;
+  x1 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7651)) - 8388608.f;
+  x2 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7652)) - 8388608.f;
+  x3 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7653)) - 8388608.f;
+}
+__device__ __forceinline__ void unpack4(Raw32 r, bool ok, float& x0, float& x1, float& x2, float& x3) {
+  x0 = ok ? r.v.x : 0.f; x1 = ok ? r.v.y : 0.f; x2 = ok ? r.v.z : 0.f; x3 = ok ? r.v.w : 0.f;
+}
+template <typename AT> struct RawOf;
+template <> struct RawOf<int8_t> { using type = Raw8; };
+template <> struct RawOf<float> { using type = Raw32; };
+
+template <typename AT, int KS, int TW>
 __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, float a_scale,
                                                      const float* __restrict__ w_tap, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, float* __restrict__ out_f32,
                                                      int8_t* __restrict__ out_spike, int n, int H, int W, int C, int Ho,
                                                      int Wo, int pad, float d_max) {
-  const int c4n = C >> 2;
-  const int64_t total = (int64_t)n * Ho * Wo * c4n;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(idx % c4n);
-    int64_t r = idx / c4n;
-    const int wo = (int)(r % Wo); r /= Wo;
-    const int ho = (int)(r % Ho);
-    const int img = (int)(r / Ho);
-    const int c = c4 * 4;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  using RT = typename RawOf<AT>::type;
+  const uint32_t c4n = (uint32_t)C >> 2;
+  const uint32_t strips = (uint32_t)(Wo + TW - 1) / TW;
+  const uint32_t total = (uint32_t)n * Ho * strips * c4n;          // host guarantees < 2^31
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    uint32_t r = idx / c4n;
+    const int wo0 = (int)(r % strips) * TW; r /= strips;
+    const int ho = (int)(r % (uint32_t)Ho);
+    const int img = (int)(r / (uint32_t)Ho);
+    float acc[TW][4];
+#pragma unroll
+    for (int t = 0; t < TW; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
     const AT* base = a + (int64_t)img * H * W * C + c;
+    const int wi0 = wo0 - pad;
+    int off[TW + KS - 1];                             // clamped column offsets, shared by all kernel rows
+    uint32_t valid = 0;
+#pragma unroll
+    for (int i = 0; i < TW + KS - 1; ++i) {
+      const int wi = wi0 + i;
+      off[i] = min(max(wi, 0), W - 1) * C;
+      valid |= (wi >= 0 && wi < W) ? (1u << i) : 0u;
+    }
 #pragma unroll
     for (int kh = 0; kh < KS; ++kh) {
       const int hi = ho - pad + kh;
       if (hi < 0 || hi >= H) continue;
+      const AT* row = base + (int64_t)hi * W * C;
+      RT raw[TW + KS - 1];
 #pragma unroll
-      for (int kw = 0; kw < KS; ++kw) {
-        const int wi = wo - pad + kw;
-        if (wi < 0 || wi >= W) continue;
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(w_tap + (int64_t)(kh * KS + kw) * C + c));
+      for (int i = 0; i < TW + KS - 1; ++i) raw[i] = load_raw(row + off[i]);
+      float4 wv[KS];
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) wv[kw] = __ldg(reinterpret_cast<const float4*>(w_tap + (kh * KS + kw) * C + c));
+#pragma unroll
+      for (int i = 0; i < TW + KS - 1; ++i) {
         float x0, x1, x2, x3;
-        if (sizeof(AT) == 1) {
-          const int raw = __ldg(reinterpret_cast<const int*>(reinterpret_cast<const int8_t*>(base) +
-                                                             ((int64_t)hi * W + wi) * C));
-          x0 = (float)(int8_t)(raw & 0xff); x1 = (float)(int8_t)((raw >> 8) & 0xff);
-          x2 = (float)(int8_t)((raw >> 16) & 0xff); x3 = (float)(int8_t)((raw >> 24) & 0xff);
-        } else {
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) +
-                                                                  ((int64_t)hi * W + wi) * C));
-          x0 = xv.x; x1 = xv.y; x2 = xv.z; x3 = xv.w;
+        unpack4(raw[i], (valid >> i) & 1u, x0, x1, x2, x3);
+#pragma unroll
+        for (int kw = 0; kw < KS; ++kw) {
+          const int t = i - kw;                       // compile-time after unrolling
+          if (t >= 0 && t < TW) {
+            acc[t][0] = fmaf(x0, wv[kw].x, acc[t][0]); acc[t][1] = fmaf(x1, wv[kw].y, acc[t][1]);
+            acc[t][2] = fmaf(x2, wv[kw].z, acc[t][2]); acc[t][3] = fmaf(x3, wv[kw].w, acc[t][3]);
+          }
         }
-        acc0 = fmaf(x0, wv.x, acc0); acc1 = fmaf(x1, wv.y, acc1);
-        acc2 = fmaf(x2, wv.z, acc2); acc3 = fmaf(x3, wv.w, acc3);
       }
     }
-    float y[4] = {acc0 * a_scale, acc1 * a_scale, acc2 * a_scale, acc3 * a_scale};
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (scale) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
-      y[0] = __fadd_rn(__fmul_rn(y[0], sc.x), sh.x); y[1] = __fadd_rn(__fmul_rn(y[1], sc.y), sh.y);
-      y[2] = __fadd_rn(__fmul_rn(y[2], sc.z), sh.z); y[3] = __fadd_rn(__fmul_rn(y[3], sc.w), sh.w);
+      sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      sh = __ldg(reinterpret_cast<const float4*>(shift + c));
     }
-    const int64_t o = (((int64_t)img * Ho + ho) * Wo + wo) * C + c;
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
-    if (out_spike) {
-      const uint32_t pk = (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
-                          ((uint32_t)(int)spike_level(y[2], d_max) << 16) |
-                          ((uint32_t)(int)spike_level(y[3], d_max) << 24);
-      *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
+    const int64_t o0 = (((int64_t)img * Ho + ho) * Wo + wo0) * C + c;
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+      if (wo0 + t >= Wo) break;
+      float y[4] = {acc[t][0] * a_scale, acc[t][1] * a_scale, acc[t][2] * a_scale, acc[t][3] * a_scale};
+      if (scale) {
+        y[0] = __fadd_rn(__fmul_rn(y[0], sc.x), sh.x); y[1] = __fadd_rn(__fmul_rn(y[1], sc.y), sh.y);
+        y[2] = __fadd_rn(__fmul_rn(y[2], sc.z), sh.z); y[3] = __fadd_rn(__fmul_rn(y[3], sc.w), sh.w);
+      }
+      const int64_t o = o0 + (int64_t)t * C;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+      if (out_spike) {
+        const uint32_t pk = (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
+                            ((uint32_t)(int)spike_level(y[2], d_max) << 16) |
+                            ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+        *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
+      }
     }
   }
 }
@@ -97,6 +140,7 @@ __global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x,
     const float ref_x = __fdiv_rn((float)wo + half + 0.5f, Win);
     const float ref_y = __fdiv_rn((float)ho + half + 0.5f, Hin);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 3
     for (int pt = 0; pt < P; ++pt) {
       const float m = (float)mk[pt] * mask_scale;
       // point order of _generate_dilation_grids: x index is the slow one (dcnv3_func.py:125-137)
@@ -111,14 +155,23 @@ __global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x,
       const int x0 = (int)fx - pad, y0 = (int)fy - pad;   // back to unpadded coordinates
       const float tx = ix - fx, ty = iy - fy;
       const float wnw = (1.f - tx) * (1.f - ty), wne = tx * (1.f - ty), wsw = (1.f - tx) * ty, wse = tx * ty;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      auto tap = [&](int yy, int xx, float wgt) {
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)yy * W + xx) * C));
-          s0 = fmaf(v.x, wgt, s0); s1 = fmaf(v.y, wgt, s1); s2 = fmaf(v.z, wgt, s2); s3 = fmaf(v.w, wgt, s3);
-        }
+      // four corners, loaded unconditionally from clamped addresses (weight 0 outside the map) so the 36 loads of a
+      // thread are independent of each other
+      auto corner = [&](int yy, int xx, float wgt, float4& v, float& wq) {
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
+        v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)yc * W + xc) * C));
+        wq = in ? wgt : 0.f;
       };
-      tap(y0, x0, wnw); tap(y0, x0 + 1, wne); tap(y0 + 1, x0, wsw); tap(y0 + 1, x0 + 1, wse);
+      float4 v00, v01, v10, v11;
+      float q00, q01, q10, q11;
+      corner(y0, x0, wnw, v00, q00); corner(y0, x0 + 1, wne, v01, q01);
+      corner(y0 + 1, x0, wsw, v10, q10); corner(y0 + 1, x0 + 1, wse, v11, q11);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      s0 = fmaf(v00.x, q00, s0); s1 = fmaf(v00.y, q00, s1); s2 = fmaf(v00.z, q00, s2); s3 = fmaf(v00.w, q00, s3);
+      s0 = fmaf(v01.x, q01, s0); s1 = fmaf(v01.y, q01, s1); s2 = fmaf(v01.z, q01, s2); s3 = fmaf(v01.w, q01, s3);
+      s0 = fmaf(v10.x, q10, s0); s1 = fmaf(v10.y, q10, s1); s2 = fmaf(v10.z, q10, s2); s3 = fmaf(v10.w, q10, s3);
+      s0 = fmaf(v11.x, q11, s0); s1 = fmaf(v11.y, q11, s1); s2 = fmaf(v11.z, q11, s2); s3 = fmaf(v11.w, q11, s3);
       a0 = fmaf(s0, m, a0); a1 = fmaf(s1, m, a1); a2 = fmaf(s2, m, a2); a3 = fmaf(s3, m, a3);
     }
     *reinterpret_cast<float4*>(out + pix * C + g * Cg + cq * 4) = make_float4(a0, a1, a2, a3);
@@ -215,13 +268,15 @@ extern "C" int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const fl
   const int pad = no_pad ? 0 : (k - 1) / 2;
   const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
   S2F_REQUIRE(Ho > 0 && Wo > 0, "dwconv: empty output");
-  const int64_t total = (int64_t)n * Ho * Wo * (C / 4);
+  constexpr int TW = 8;
+  const int64_t total = (int64_t)n * Ho * ((Wo + TW - 1) / TW) * (C / 4);
+  S2F_REQUIRE(total < (1ll << 31) && (int64_t)W * C < (1ll << 31), "dwconv: problem too large for 32-bit task indices");
   const int g = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   const float asc = a_is_spike ? a_scale : 1.f;
-#define S2F_DW(AT, KS)                                                                                                  \
-  dwconv_kernel<AT, KS><<<g, 256, 0, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, out_f32, out_spike, n, \
-                                           H, W, C, Ho, Wo, pad, d_max)
+#define S2F_DW(AT, KS)                                                                                                      \
+  dwconv_kernel<AT, KS, TW><<<g, 256, 0, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, out_f32, out_spike, n, \
+                                               H, W, C, Ho, Wo, pad, d_max)
   if (a_is_spike) {
     if (k == 3) S2F_DW(int8_t, 3); else if (k == 5) S2F_DW(int8_t, 5); else S2F_DW(int8_t, 7);
   } else {

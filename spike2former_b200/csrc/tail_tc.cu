@@ -8,7 +8,7 @@
 // The B operand (class probabilities, bf16 hi/lo, already in the UMMA K-major SWIZZLE_128B image) is produced once
 // per image by tail_prep_kernel and copied to shared memory once per CTA.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -30,7 +30,7 @@ __device__ __forceinline__ uint64_t tl_desc(uint32_t saddr) {      // SWIZZLE_12
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__device__ __forceinline__ void tl_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void tl_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -71,11 +71,11 @@ __global__ void __launch_bounds__(256) tail_prep_kernel(const float* __restrict_
   for (int e = threadIdx.x; e < Np * TL_KQ; e += blockDim.x) {
     const int c = e / TL_KQ, q = e % TL_KQ;
     const float v = (c < K && q < Q) ? prob[q * K + c] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16(v);
-    const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
     const int off = tl_off(Np, c, q);
-    *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(dst + plane + off) = lo;
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + plane + off) = lo;
   }
 }
 
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
   const float sh = (float)p.h / (float)p.H, sw = (float)p.w / (float)p.W;
   const float* mp = p.mask_pred + (int64_t)img * p.h * p.w * p.Q;
   const int64_t HW = (int64_t)p.H * p.W;
-  // instruction descriptor: D=F32 (1<<4), A=B=BF16 (1<<7, 1<<10), K-major, N>>3 @17, M>>4 @24
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(TL_BM >> 4) << 24);
+  // instruction descriptor: D=F32 (1<<4), A=B=F16 (format 0), K-major, N>>3 @17, M>>4 @24
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(TL_BM >> 4) << 24);
   uint32_t parity = 0;
 
   const int t_begin = blockIdx.x * p.tiles_per_cta;
@@ -152,11 +152,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
           const float up = w00 * __ldg(mp + o00 + q) + w01 * __ldg(mp + o01 + q) + w10 * __ldg(mp + o10 + q) + w11 * __ldg(mp + o11 + q);
           s = __fdividef(1.f, 1.f + __expf(-up));
         }
-        const __nv_bfloat16 hi = __float2bfloat16(s);
-        const __nv_bfloat16 lo = __float2bfloat16(s - __bfloat162float(hi));
+        const __half hi = __float2half_rn(s);
+        const __half lo = __float2half_rn(s - __half2float(hi));
         const int off = tl_off(TL_BM, r, q);
-        *reinterpret_cast<__nv_bfloat16*>(sA + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(sA + a_plane + off) = lo;
+        *reinterpret_cast<__half*>(sA + off) = hi;
+        *reinterpret_cast<__half*>(sA + a_plane + off) = lo;
       }
     }
     // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = tl_desc(abase + atom * TL_BM * 128) + (uint64_t)(k * 2);
             const uint64_t db = tl_desc(bbase + atom * p.Np * 128) + (uint64_t)(k * 2);
-            tl_mma_bf16(tmem_base, da, db, idesc, acc);
+            tl_mma_f16(tmem_base, da, db, idesc, acc);
             acc = 1;
           }
         }
@@ -247,6 +247,256 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exact x2 upsampling (H == 2h, W == 2w; every Spike2Former config): warp-specialised, pipelined version.
+//
+//   warps 0..7   producers: build the A operand (sigmoid of the bilinear x2 upsample, fp16 hi + lo) of a 4 x 32 pixel
+//                tile.  One task = one low-resolution cell (its 4 corners are shared by a 2 x 2 block of output pixels)
+//                x 8 queries: 8 x LDG.128, 32 sigmoids, 8 x STS.128 straight into the SWIZZLE_128B K-major image.
+//   warp  8      one thread issues tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo) into one of two TMEM accumulators.
+//   warps 9..12  epilogue: tcgen05.ld the other accumulator, store the NCHW logits (128 B per class per warp) and/or the
+//                fused argmax label.
+// Two A stages in shared memory and two accumulators in TMEM keep the three roles running on different tiles.
+// Tile geometry: output rows Y = 4*ty - 1 + {0..3} (cell rows kc = 2*ty - 1, 2*ty; rows are offset by one so that the two
+// rows of a cell never straddle tiles), columns X = 32*tx + {0..31} (cells jc = 16*tx - 1 .. 16*tx + 15; the first and
+// last cell contribute one column each).  Clamped corner indices reproduce upsample_bilinear2d's border rule.
+constexpr int T2_PROD_WARPS = 8;
+constexpr int T2_THREADS = (T2_PROD_WARPS + 1 + 4) * 32;    // 416
+constexpr int T2_CELLS_X = 17;
+constexpr int T2_ACC_COLS = 256;                            // TMEM columns per accumulator buffer
+
+struct Tail2P {
+  const float* mask_pred; const uint8_t* bpack; float* logits; uint8_t* labels;
+  int Q, K, Np, h, w, H, W, tiles_x, tiles_y, ctas_per_img;
+};
+
+__device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "T2_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra T2_DONE;\n\t"
+      "bra T2_WAIT;\n\t"
+      "T2_DONE:\n\t"
+      "}" ::"r"(tl_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void t2_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void t2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float t2_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ uint32_t t2_pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// 8 sigmoid values -> one 16-byte hi chunk and one 16-byte lo chunk of row r, query group g
+__device__ __forceinline__ void t2_store8(uint8_t* sA, int a_plane, int r, int g, const float* s) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(s[2 * j], s[2 * j + 1]);
+    const float2 back = __half22float2(hh);
+    hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    lo[j] = t2_pack_half2(s[2 * j] - back.x, s[2 * j + 1] - back.y);
+  }
+  const int off = (g >> 3) * (TL_BM * 128) + r * 128 + ((((g & 7) ^ (r & 7))) << 4);
+  *reinterpret_cast<uint4*>(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(sA + a_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) {
+  extern __shared__ __align__(1024) uint8_t t2_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(t2_raw) + 1023) & ~uintptr_t(1023));
+  const int b_plane = 2 * p.Np * 128;             // one of B_hi / B_lo (two 64-query atoms)
+  const int a_plane = 2 * TL_BM * 128;            // one of A_hi / A_lo: 32 KB
+  const int a_stage = 2 * a_plane;                // 64 KB
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + 2 * b_plane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * a_stage);
+  uint64_t* a_full = bars, *a_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.y;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&a_full[s])), "r"(T2_PROD_WARPS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&a_empty[s])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&t_full[s])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&t_empty[s])), "r"(4));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == T2_PROD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tl_smem_u32(tmem_slot)), "n"(2 * T2_ACC_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {  // B operand (pre-swizzled image of this picture's class probabilities) + zero the A stages (padding queries stay 0)
+    const uint4* src = reinterpret_cast<const uint4*>(p.bpack + (int64_t)img * 2 * b_plane);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = threadIdx.x; i < 2 * b_plane / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    uint4* za = reinterpret_cast<uint4*>(sA);
+    for (int i = threadIdx.x; i < 2 * a_stage / 16; i += blockDim.x) za[i] = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int64_t HW = (int64_t)p.H * p.W;
+
+  if (warp < T2_PROD_WARPS) {
+    // ================================================================== producers
+    const int ptid = threadIdx.x;                                  // 0..255
+    const int ngroups = (p.Q + 7) >> 3;
+    const int ntasks = 2 * T2_CELLS_X * ngroups;
+    const float* mp = p.mask_pred + (int64_t)img * p.h * p.w * p.Q;
+    const bool vec = (p.Q & 3) == 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
+      const int s = it & 1;
+      t2_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
+      uint8_t* dstA = sA + s * a_stage;
+      const int ty = tile / p.tiles_x, tx = tile % p.tiles_x;
+      for (int t = ptid; t < ntasks; t += T2_PROD_WARPS * 32) {
+        const int g = t % ngroups, cell = t / ngroups;
+        const int cx = cell % T2_CELLS_X, kr = cell / T2_CELLS_X;
+        const int jc = 16 * tx - 1 + cx, kc = 2 * ty - 1 + kr;
+        const int x0 = min(max(jc, 0), p.w - 1), x1 = min(max(jc + 1, 0), p.w - 1);
+        const int y0 = min(max(kc, 0), p.h - 1), y1 = min(max(kc + 1, 0), p.h - 1);
+        const int q0 = g * 8;
+        float c[4][8];
+        const float* src[4] = {mp + ((int64_t)y0 * p.w + x0) * p.Q + q0, mp + ((int64_t)y0 * p.w + x1) * p.Q + q0,
+                               mp + ((int64_t)y1 * p.w + x0) * p.Q + q0, mp + ((int64_t)y1 * p.w + x1) * p.Q + q0};
+        if (vec) {
+          const bool second = q0 + 4 < p.Q;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src[k]));
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (second) b = __ldg(reinterpret_cast<const float4*>(src[k]) + 1);
+            c[k][0] = a.x; c[k][1] = a.y; c[k][2] = a.z; c[k][3] = a.w;
+            c[k][4] = b.x; c[k][5] = b.y; c[k][6] = b.z; c[k][7] = b.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[k][j] = (q0 + j < p.Q) ? __ldg(src[k] + j) : 0.f;
+        }
+        // horizontal interpolation of both corner rows for the two output columns of the cell
+        float top[2][8], bot[2][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          top[0][j] = 0.75f * c[0][j] + 0.25f * c[1][j];
+          top[1][j] = 0.25f * c[0][j] + 0.75f * c[1][j];
+          bot[0][j] = 0.75f * c[2][j] + 0.25f * c[3][j];
+          bot[1][j] = 0.25f * c[2][j] + 0.75f * c[3][j];
+        }
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int ox = 2 * cx - 1 + dx;
+          if (ox < 0 || ox >= 32) continue;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const float wt = dy ? 0.25f : 0.75f, wb = dy ? 0.75f : 0.25f;
+            float sv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[j] = (q0 + j < p.Q) ? t2_sigmoid(wt * top[dx][j] + wb * bot[dx][j]) : 0.f;
+            t2_store8(dstA, a_plane, (2 * kr + dy) * 32 + ox, g, sv);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) t2_arrive(&a_full[s]);
+    }
+  } else if (warp == T2_PROD_WARPS) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(TL_BM >> 4) << 24);   // F32 += F16 x F16
+      const int ksteps = (p.Q + 15) >> 4;
+      const uint32_t b_hi = tl_smem_u32(sB), b_lo = b_hi + b_plane;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        t2_wait(&a_full[s], ph);
+        t2_wait(&t_empty[s], ph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = tl_smem_u32(sA + s * a_stage), a_lo = a_hi + a_plane;
+        const uint32_t d = tmem_base + (uint32_t)(s * T2_ACC_COLS);
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int combo = 0; combo < 3; ++combo) {
+          const uint32_t abase = combo == 1 ? a_lo : a_hi, bbase = combo == 2 ? b_lo : b_hi;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const int atom = ks >> 2, k = ks & 3;
+            const uint64_t da = tl_desc(abase + atom * TL_BM * 128) + (uint64_t)(k * 2);
+            const uint64_t db = tl_desc(bbase + atom * p.Np * 128) + (uint64_t)(k * 2);
+            tl_mma_f16(d, da, db, idesc, acc);
+            acc = 1;
+          }
+        }
+        t2_commit(&a_empty[s]);        // A stage reusable once these MMAs have read it
+        t2_commit(&t_full[s]);         // accumulator complete
+      }
+    }
+  } else {
+    // ================================================================== epilogue
+    const int quad = warp & 3;                                     // TMEM lane quadrant == output row of the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
+      const int s = it & 1;
+      t2_wait(&t_full[s], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int ty = tile / p.tiles_x, tx = tile % p.tiles_x;
+      const int Y = 4 * ty - 1 + quad, X = 32 * tx + lane;
+      const bool ok = Y >= 0 && Y < p.H && X < p.W;
+      const int64_t pix = (int64_t)Y * p.W + X;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * T2_ACC_COLS);
+      float best = -INFINITY;
+      int best_c = 0;
+      float* lg = p.logits ? p.logits + (int64_t)img * p.K * HW + pix : nullptr;
+      for (int c0 = 0; c0 < p.Np; c0 += 32) {
+        uint32_t v[32];
+        tl_ld16(trow + c0, v);
+        const bool two = c0 + 16 < p.Np;                            // warp-uniform
+        if (two) tl_ld16(trow + c0 + 16, v + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            if (c < p.K && (j < 16 || two)) {
+              const float y = __uint_as_float(v[j]);
+              if (lg) lg[(int64_t)c * HW] = y;
+              if (y > best) { best = y; best_c = c; }
+            }
+          }
+        }
+      }
+      if (p.labels && ok) p.labels[(int64_t)img * HW + pix] = (uint8_t)best_c;      // first maximum wins, as torch.argmax
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) t2_arrive(&t_empty[s]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == T2_PROD_WARPS) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * T2_ACC_COLS));
+  }
+}
+
 }  // namespace s2f
 
 using namespace s2f;
@@ -274,6 +524,25 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
   tail_prep_kernel<<<n, 256, prep_sm, st>>>(cls, reinterpret_cast<uint8_t*>(ws), Q, K, Np);
   int rc = check_launch("tail_prep_kernel");
   if (rc) return rc;
+  const size_t smem2 = (size_t)2 * 2 * Np * 128 + 2 * 2 * 2 * TL_BM * 128 + 128 + 1024;
+  if (H == 2 * h && W == 2 * w && smem2 <= 227 * 1024) {          // K <= 192 classes: both A stages + B fit
+    Tail2P q;
+    q.mask_pred = mask_pred; q.bpack = reinterpret_cast<const uint8_t*>(ws); q.logits = logits; q.labels = labels;
+    q.Q = Q; q.K = K; q.Np = Np; q.h = h; q.w = w; q.H = H; q.W = W;
+    q.tiles_x = (W + 31) / 32; q.tiles_y = (h + 1 + 1) / 2;          // cell rows -1 .. h-1, two per tile
+    const int tiles_img = q.tiles_x * q.tiles_y;
+    int per_img = n >= 148 ? 1 : 148 / n;
+    if (per_img > tiles_img) per_img = tiles_img;
+    q.ctas_per_img = per_img;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(tail_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "semantic_tail_tc: smem attribute: %s", cudaGetErrorString(e));
+      attr2 = true;
+    }
+    tail_x2_kernel<<<dim3(per_img, n), T2_THREADS, smem2, st>>>(q);
+    return check_launch("tail_x2_kernel");
+  }
   TailP p;
   p.mask_pred = mask_pred; p.bpack = reinterpret_cast<const uint8_t*>(ws); p.logits = logits; p.labels = labels;
   p.Q = Q; p.K = K; p.Np = Np; p.h = h; p.w = w; p.H = H; p.W = W;

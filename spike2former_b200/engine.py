@@ -446,11 +446,14 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True):
         if pr.active:
             pr.real(pd + f"output_convs_spike.{i}", yf)
         ys = pr.spike(pd + f"output_convs_spike.{i}", ys)
-        y, ysp = L[f"output.{i}"](ys, n, h, w, f32=True, spike=(i == 0))
-        y = pr.real(pd + f"y{model.num_inputs - 1 - i}", y)
+        # the finest level only feeds mask_feature_spike: its fp32 map (1 GB at batch 16) is not materialised
+        y, ysp = L[f"output.{i}"](ys, n, h, w, f32=(i > 0 or pr.active), spike=(i == 0))
+        if y is not None:
+            y = pr.real(pd + f"y{model.num_inputs - 1 - i}", y)
         outs.append(y)
         hp, wp = h, w
-    y = pr.real(pd + "mask_feature_spike", y)
+    if pr.active:
+        pr.real(pd + "mask_feature_spike", y)
     ysp = pr.spike(pd + "mask_feature_spike", ysp)
     mf = None
     if want_mask_feature or pr.active:
@@ -611,6 +614,32 @@ def head_predict(model, x, img_shape, probe=NOPROBE):
     return _predict_from(model, feats, img_shape, probe)
 
 
+class GraphedForward:
+    """One captured CUDA graph of segmentor_logits for a fixed input shape (see EncoderDecoder._run)."""
+
+    def __init__(self, seg, example, labels):
+        self.static_in = torch.empty_like(example)
+        self.static_in.copy_(example)
+        side = torch.cuda.Stream(device=example.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                     # builds the plans, sets kernel attributes, fills the PE caches
+                segmentor_logits(seg, self.static_in, labels=labels)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(example.device)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = segmentor_logits(seg, self.static_in, labels=labels)
+        self.launches = ops.launch_count() - l0    # kernels of this library inside one replay
+
+    def __call__(self, x):
+        if x.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 HBM_CLASSES = ("nilif", "dwconv", "dcn_gather", "upsample_add_lif", "elementwise", "linear_attn")
 
 
@@ -621,12 +650,16 @@ def profile_dominant(seg, img, steps=2):
     with torch.no_grad():
         segmentor_logits(seg, img)                      # warm
         torch.cuda.synchronize()
-        ops.set_profiler(prof)
-        try:
-            for _ in range(steps):
+        for _ in range(steps):
+            # park the GPU behind a ~0.3 s spin kernel while the host enqueues the whole forward: the events then
+            # bracket device time only, not the host's per-launch overhead (the production path replays a CUDA graph)
+            torch.cuda._sleep(int(6e8))
+            ops.set_profiler(prof)
+            try:
                 segmentor_logits(seg, img)
-        finally:
-            ops.set_profiler(None)
+            finally:
+                ops.set_profiler(None)
+            torch.cuda.synchronize()
     agg = prof.summary()
     total = sum(a["ms"] for a in agg.values())
     name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])

@@ -174,13 +174,40 @@ class EncoderDecoder(_Engined):
         self.align_corners = self.decode_head.align_corners
         self.num_classes = self.decode_head.num_classes
         self.out_channels = self.decode_head.out_channels
-        self._runner = None
+        self._graphs = {}
+        self.use_cuda_graph = True       # replay one captured CUDA graph per (input shape, output kind)
 
     def invalidate(self):
         super().invalidate()
-        self._runner = None
+        self._graphs = {}
         for m in (self.backbone, self.decode_head, self.decode_head.pixel_decoder):
             m.invalidate()
+
+    def _load_from_state_dict(self, *a, **k):
+        self._graphs = {}
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._graphs = {}
+        return super()._apply(fn, *a, **k)
+
+    def _run(self, inputs, labels):
+        """The whole forward is ~300 kernel launches of 5-50 us each: it is captured once per input shape into a
+        CUDA graph (all launches go to torch's current stream through the C ABI, workspaces come from the graph's
+        private pool) and replayed.  The returned tensor is the graph's output buffer: it is overwritten by the next
+        call with the same shape, exactly like a CUDA-graphed module in any serving stack."""
+        from . import engine
+
+        if not self.use_cuda_graph:
+            return engine.segmentor_logits(self, inputs, labels=labels)
+        if torch.cuda.is_current_stream_capturing():
+            return engine.segmentor_logits(self, inputs, labels=labels)
+        key = (tuple(inputs.shape), inputs.device.index, bool(labels))
+        g = self._graphs.get(key)
+        if g is None:
+            g = engine.GraphedForward(self, inputs, labels)
+            self._graphs[key] = g
+        return g(inputs)
 
     def extract_feat(self, inputs):
         return self.backbone(inputs)
@@ -188,9 +215,7 @@ class EncoderDecoder(_Engined):
     def encode_decode(self, inputs, batch_img_metas=None):
         """fp32 [B,3,H,W] -> seg logits [B,K,H,W] (encoder_decoder.py:125-133), whole-image mode."""
         _require_cuda(inputs, type(self).__name__)
-        from . import engine
-
-        return engine.segmentor_logits(self, inputs)
+        return self._run(inputs, labels=False)
 
     def forward(self, inputs, data_samples=None, mode="tensor"):
         return self.encode_decode(inputs)
@@ -199,9 +224,7 @@ class EncoderDecoder(_Engined):
     def predict_labels(self, inputs):
         """argmax over classes, as BaseSegmentor.postprocess_result (segmentors/base.py:177-188)."""
         _require_cuda(inputs, type(self).__name__)
-        from . import engine
-
-        return engine.segmentor_logits(self, inputs, labels=True)      # argmax fused into the tail kernel (uint8)
+        return self._run(inputs, labels=True)                          # argmax fused into the tail kernel (uint8)
 
 
 def build_segmentor(cfg) -> EncoderDecoder:

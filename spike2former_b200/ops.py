@@ -102,7 +102,8 @@ def nilif(x, scale=None, shift=None, residual=None, residual_period=0, v_in=None
                                    _ptr(v_in, torch.float32, "v_in"), _ptr(v_out), _ptr(levels, torch.int8, "levels"),
                                    _ptr(y), int(T), int(N), C_, float(d_max), float(norm), int(tr), int(tc),
                                    _ptr(ties), _stream()), "s2f_nilif_fwd")
-    _p1(e0, "nilif", 0, _nb(x, levels, v_in, v_out, y) + (x.numel() * 4 if residual is not None else 0))
+    _p1(e0, "nilif", 0, _nb(x, levels, v_in, v_out, y) + (x.numel() * 4 if residual is not None else 0),
+        f"{tuple(x.shape)} aff={int(scale is not None)} res={int(residual is not None)} tr={int(bool(transpose))}")
     return levels, v_out, y
 
 
@@ -249,7 +250,8 @@ def dwconv(a, w_tap, *, n, H, W, C_, k, scale=None, shift=None, a_scale=1.0 / NO
                                 _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"), None,
                                 _ptr(out_f), _ptr(out_s), n, H, W, C_, k, int(no_pad), float(d_max), _stream()),
           "s2f_dwconv")
-    _p1(e0, "dwconv", 2.0 * n * Ho * Wo * C_ * k * k, _nb(a, out_f, out_s))
+    _p1(e0, "dwconv", 2.0 * n * Ho * Wo * C_ * k * k, _nb(a, out_f, out_s),
+        f"{n}x{H}x{W}x{C_} k{k} f32={int(want_f32)} sp={int(want_spike)}")
     return out_f, out_s
 
 
@@ -269,7 +271,8 @@ def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=Non
     check(_lib.lib().s2f_linear_attn(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
                                      _ptr(ws), _ptr(out_s), _ptr(out_f), n, Nq, Nk, heads, d, int(q_ld or Cc),
                                      int(kv_ld or Cc), out_ld, float(out_scale), float(d_max), _stream()), "s2f_linear_attn")
-    _p1(e0, "linear_attn", 2.0 * n * heads * d * d * (Nq + Nk), n * (Nq + 2 * Nk) * Cc + _nb(out_s, out_f))
+    _p1(e0, "linear_attn", 2.0 * n * heads * d * d * (Nq + Nk), n * (Nq + 2 * Nk) * Cc + _nb(out_s, out_f),
+        f"{n} x Nq{Nq} Nk{Nk} h{heads} d{d}")
     return out_s, out_f
 
 
@@ -291,7 +294,7 @@ def upsample_add_lif(cur, prev, *, n, H, W, Hp, Wp, C_, want_f32=False, d_max=D_
     check(_lib.lib().s2f_upsample_add_lif(_ptr(cur, torch.float32, "cur"), _ptr(prev, torch.float32, "prev"),
                                           _ptr(out_s), _ptr(out_f), n, H, W, Hp, Wp, C_, float(d_max), _stream()),
           "s2f_upsample_add_lif")
-    _p1(e0, "upsample_add_lif", 0, _nb(cur, prev, out_s, out_f))
+    _p1(e0, "upsample_add_lif", 0, _nb(cur, prev, out_s, out_f), f"{n}x{H}x{W}x{C_}")
     return out_s, out_f
 
 

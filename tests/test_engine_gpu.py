@@ -87,3 +87,29 @@ def test_free_running_report():
     print("free-running logits rel err", float((logits - ref).abs().max() / ref.abs().max()))
     assert torch.isfinite(logits).all()
     assert sum(e["flips"] for e in sp[:4]) <= 4          # the first units still see identical inputs
+
+
+def test_cuda_graph_replay_matches_eager_launches():
+    """EncoderDecoder.encode_decode / predict_labels replay a captured CUDA graph: same bits as launch-by-launch."""
+    from spike2former_b200 import engine, synth
+
+    cfg = s2f.configs.tiny()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint("tiny", cfg), strict=True)
+    seg = seg.cuda()
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = (torch.randn(2, 3, 64, 64, generator=g).cuda() for _ in range(2))
+    with torch.no_grad():
+        e1 = engine.segmentor_logits(seg, x1).clone()
+        e2 = engine.segmentor_logits(seg, x2).clone()
+        g1 = seg.encode_decode(x1).clone()
+        g2 = seg.encode_decode(x2).clone()
+        g1b = seg.encode_decode(x1).clone()
+        lab = seg.predict_labels(x2).clone()
+    assert len(seg._graphs) == 2 and all(gr.launches > 50 for gr in seg._graphs.values())
+    assert torch.equal(g1, e1) and torch.equal(g2, e2) and torch.equal(g1b, e1)
+    assert not torch.equal(e1, e2)
+    assert torch.equal(lab.long(), e2.argmax(1))
+    seg.use_cuda_graph = False
+    with torch.no_grad():
+        assert torch.equal(seg.encode_decode(x1), e1)

@@ -185,6 +185,35 @@ def test_linear_attn_exact(n, Nq, Nk, heads, d):
     assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
 
 
+def test_linear_attn_strided_operands_and_padded_output():
+    """q|k|v as column slices of one fused [n, N, 3C] projection (engine._ms_block) and a 16-byte padded output row."""
+    g = gen(12)
+    n, N, heads, d = 2, 200, 8, 32
+    C = heads * d
+    qkv = _levels((n, N, 3 * C), g).cuda()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    scale = d ** -0.5 / 512
+    hs = lambda t: t.cpu().double().view(n, N, heads, d).permute(0, 2, 1, 3)
+    ref = (hs(q) @ (hs(k).transpose(-2, -1) @ hs(v))).permute(0, 2, 1, 3).reshape(n, N, C) * scale
+    os_, of = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, q_ld=3 * C, kv_ld=3 * C, out_ld=C + 16,
+                              out_scale=scale, want_f32=True)
+    assert (of.cpu()[..., :C].double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert torch.equal(os_.cpu()[..., :C], torch.round(torch.clamp(of.cpu()[..., :C], 0, 8)).to(torch.int8))
+    assert int(os_.cpu()[..., C:].abs().sum()) == 0 and float(of.cpu()[..., C:].abs().sum()) == 0.0
+
+
+def test_linear_attn_long_keys_need_wide_accumulation():
+    """Nk large enough that 8 * 64 * Nk * d exceeds int32: the 64-bit accumulation path (Cityscapes level 2)."""
+    g = gen(13)
+    n, Nq, Nk, heads, d = 1, 40, 140000, 2, 32
+    C = heads * d
+    q, k, v = _levels((n, Nq, C), g), _levels((n, Nk, C), g), _levels((n, Nk, C), g)
+    hs = lambda t, N: t.double().view(n, N, heads, d).permute(0, 2, 1, 3)
+    ref = (hs(q, Nq) @ (hs(k, Nk).transpose(-2, -1) @ hs(v, Nk))).permute(0, 2, 1, 3).reshape(n, Nq, C) * 1e-9
+    _, of = ops.linear_attn(q.cuda(), k.cuda(), v.cuda(), n=n, Nq=Nq, Nk=Nk, heads=heads, d=d, out_scale=1e-9, want_f32=True)
+    assert (of.cpu().double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("n,H,W,G,Cg", [(2, 8, 8, 4, 16), (1, 32, 32, 32, 8), (2, 5, 9, 8, 8)])
 def test_dcnv3_gather_vs_reference_core(n, H, W, G, Cg):
     """Pattern of ops_dcnv3/test.py:33-60 (seed 3, inputs*0.01, offsets*10, K=3, pad 1), fp32 tolerance of that
@@ -227,6 +256,34 @@ def test_semantic_tail_vs_torch():
     assert (got_tc.cpu() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
     assert torch.equal(lab.cpu().long(), got_tc.cpu().argmax(1))
     assert (lab.cpu().long() == ref.argmax(1)).float().mean().item() > 0.999
+
+
+@pytest.mark.parametrize("n,Q,K,h,w", [(2, 100, 150, 64, 64), (1, 100, 19, 20, 24), (3, 37, 150, 9, 50), (1, 128, 256, 16, 16)])
+def test_semantic_tail_pipelined_x2(n, Q, K, h, w):
+    """The warp-specialised x2 tail (tail_x2_kernel): ADE20K / Cityscapes class counts, ragged tiles, odd Q."""
+    g = gen(14)
+    mp = torch.randn(n, Q, h, w, generator=g) * 3
+    cls = torch.randn(n, Q, K + 1, generator=g) * 4
+    up = F.interpolate(mp, size=(2 * h, 2 * w), mode="bilinear", align_corners=False)
+    ref = torch.einsum("bqc,bqhw->bchw", F.softmax(cls, -1)[..., :-1], up.sigmoid())
+    mpp = mp.permute(0, 2, 3, 1).contiguous().cuda()
+    got, lab = ops.semantic_tail(mpp, cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=2 * h, W=2 * w, want_labels=True)
+    assert (got.cpu() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(lab.cpu().long(), got.cpu().argmax(1))
+    assert (lab.cpu().long() == ref.argmax(1)).float().mean().item() > 0.999
+    _, lab2 = ops.semantic_tail(mpp, cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=2 * h, W=2 * w, want_logits=False, want_labels=True)
+    assert torch.equal(lab2.cpu(), lab.cpu())
+
+
+def test_semantic_tail_general_scale_falls_back_to_serial_kernel():
+    g = gen(15)
+    n, Q, K, h, w, H, W = 1, 20, 11, 12, 16, 30, 50
+    mp = torch.randn(n, Q, h, w, generator=g) * 3
+    cls = torch.randn(n, Q, K + 1, generator=g) * 4
+    up = F.interpolate(mp, size=(H, W), mode="bilinear", align_corners=False)
+    ref = torch.einsum("bqc,bqhw->bchw", F.softmax(cls, -1)[..., :-1], up.sigmoid())
+    got, _ = ops.semantic_tail(mp.permute(0, 2, 3, 1).contiguous().cuda(), cls.cuda(), n=n, Q=Q, K=K, h=h, w=w, H=H, W=W)
+    assert (got.cpu() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
 
 
 def test_cpu_tensors_are_rejected():

@@ -1,0 +1,89 @@
+"""Summarise ncu captures into the tracked profiles/ directory (run in the build container, no GPU needed).
+
+    python tools/ncu_summary.py launches gpurun_out/X_launches.csv profiles/X_launches.md [last_n]
+        per-kernel table (launch count, total / mean device time, share) from a
+        `ncu --metrics gpu__time_duration.sum --csv` launch list; `last_n` keeps only the last n launches
+        (one forward) so that warm-up passes do not count.
+    python tools/ncu_summary.py full gpurun_out/X.ncu-rep profiles/X_full.md
+        the roofline-relevant metrics of every launch in a `ncu --set full` report.
+"""
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    name = re.sub(r"^void ", "", name)
+    name = name.replace("s2f::", "")
+    return name[:70]
+
+
+def launches(src, dst, last_n=None):
+    rows = []
+    with open(src, newline="") as f:
+        lines = [ln for ln in f if not ln.startswith("==")]
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+        rows.append((short(r["Kernel Name"]), us, r["Grid Size"], r["Block Size"]))
+    if last_n:
+        rows = rows[-int(last_n):]
+    agg = {}
+    for name, us, grid, block in rows:
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    tot = sum(a[1] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list summary ({src})\n\n")
+        f.write(f"{len(rows)} launches, {tot / 1e3:.3f} ms of device time (ncu: cold-cache, serialised -- compare shares, not absolutes)\n\n")
+        f.write("| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
+        for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{name}` | {cnt} | {us:.1f} | {us / cnt:.1f} | {100 * us / tot:.1f}% |\n")
+    print(open(dst).read())
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units, body = rd[0], rd[1], rd[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary ({src})\n\n")
+        for row in body:
+            f.write(f"## `{short(row[idx['Kernel Name']])}`  grid {row[idx['Grid Size']]} block {row[idx['Block Size']]}\n\n")
+            for k in KEYS:
+                if k in idx:
+                    f.write(f"- {k} = {row[idx[k]]} {units[idx[k]]}\n")
+            try:
+                rd_b = float(row[idx["dram__bytes_read.sum"]].replace(",", ""))
+                wr_b = float(row[idx["dram__bytes_write.sum"]].replace(",", ""))
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tb = rd_b * mult.get(units[idx["dram__bytes_read.sum"]], 1) + wr_b * mult.get(units[idx["dram__bytes_write.sum"]], 1)
+                t = float(row[idx["gpu__time_duration.sum"]].replace(",", ""))
+                tu = {"nsecond": 1e-9, "ns": 1e-9, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3, "ms": 1e-3}.get(units[idx["gpu__time_duration.sum"]], 1e-9)
+                f.write(f"- **traffic** (dram read+write) = {tb / 1e6:.2f} MB in {t * tu * 1e6:.1f} us -> {tb / (t * tu) / 1e9:.0f} GB/s\n")
+            except Exception as e:  # noqa: BLE001
+                f.write(f"- traffic: n/a ({e})\n")
+            f.write("\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1]
+    if mode == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+    else:
+        full(sys.argv[2], sys.argv[3])
