@@ -8,11 +8,12 @@
 //   D  int32 accumulators in TMEM, read back with tcgen05.ld by four epilogue warps that recombine the digit
 //      planes, apply the folded BatchNorm affine (+ residual) and emit fp32 and/or NI-LIF int8 levels.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Two CTAs fit on one SM, so one CTA's epilogue
-// overlaps the other's main loop.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, column half = (warp_id - 2) / 4).  The kernel is
+// persistent (one CTA per SM) with two accumulators in TMEM, so the epilogue of a tile overlaps the next main loop.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -21,7 +22,7 @@ namespace s2f {
 
 constexpr int TC_BM = 128;        // rows (pixels / tokens) per tile == UMMA M
 constexpr int TC_BN = 64;         // output channels per tile
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 __host__ __device__ inline int tc_bk(int cin) { return cin >= 128 ? 128 : (cin >= 64 ? 64 : 32); }
 __host__ __device__ inline int tc_cin_pad(int cin) { const int bk = tc_bk(cin); return (cin + bk - 1) / bk * bk; }
@@ -40,7 +41,9 @@ struct TcParams {
   int bk;               // bytes of K per stage (32 / 64 / 128)
   int pieces, stages;
   int out_transposed;
-  int tiles_n, total_tiles;
+  int tiles_n, tiles_m, ctas_per_n;
+  int debug;            // S2F_GEMM_DEBUG bits (experiments only): 1 = epilogue skips math and stores, 2 = no MMA issue
+  int b_resident;       // all K chunks of the weight tile stay in shared memory for the CTA's lifetime
   int big_k;            // accumulators may exceed 2^22: convert with I2F instead of the magic-number trick
   int w_img_rows;       // packed weight rows per image (0: one weight matrix for all images)
   int ss_img_stride;    // scale/shift elements per image (0: shared)
@@ -81,6 +84,20 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// One lane of a fully converged warp; used *inside* warp-uniform control flow so that the compiler keeps descriptors,
+// addresses and barriers in uniform registers (a divergent `if (lane == 0)` region makes it wrap every tcgen05 / TMA
+// instruction in an ELECT + R2UR.BROADCAST loop, ~25 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -112,33 +129,34 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int bk) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-// Persistent: one CTA per SM walks the tile list (n-tile fastest, so CTAs running side by side share the A tile in L2).
-// Two accumulator buffers in TMEM (2 x 256 columns) let the epilogue of tile i overlap the main loop of tile i+1.
+// Persistent, weight-stationary schedule.  CTA c owns output-channel tile n = c % tiles_n and walks the row tiles
+// m = c / tiles_n, + ctas_per_n, ...  so that
+//   * the tile's folded-BN scale / shift (and the digit-plane recombination factors) are staged in shared memory once;
+//   * when all K chunks of the weight tile fit (b_resident), the weights are fetched once per CTA and only the spike
+//     tile streams through the TMA pipeline -- 128*K bytes per tile instead of (128 + 192)*K;
+//   * CTAs that run side by side work on the same row tile for different channel tiles, so the A tile is an L2 hit.
+// Two accumulator buffers in TMEM (2 x 256 columns) let the epilogue of a tile overlap the main loop of the next.
 constexpr int TC_ACC_COLS = 256;
 
-struct TileOrigin { int img, ho0, wo0, tile_m, tile_n; };
+struct TileOrigin { int img, ho0, wo0; };
 
-__device__ __forceinline__ TileOrigin tile_origin(const TcParams& p, int tile) {
+__device__ __forceinline__ TileOrigin tile_origin(const TcParams& p, int tile_m) {
   TileOrigin o;
-  o.tile_n = tile % p.tiles_n;
-  o.tile_m = tile / p.tiles_n;
   o.img = 0; o.ho0 = 0; o.wo0 = 0;
   if (p.mode_conv) {
     const int per_img = p.tiles_w * p.tiles_h;
-    o.img = o.tile_m / per_img;
-    const int t = o.tile_m % per_img;
+    o.img = tile_m / per_img;
+    const int t = tile_m % per_img;
     o.ho0 = (t / p.tiles_w) * p.TH;
     o.wo0 = (t % p.tiles_w) * p.TW;
   } else if (p.w_img_rows) {
-    o.img = (o.tile_m * TC_BM) / p.M_img;      // M_img % 128 == 0 is required for per-image weights
+    o.img = (tile_m * TC_BM) / p.M_img;        // M_img % 128 == 0 is required for per-image weights
   }
   return o;
 }
 
 // int32 accumulator -> float without I2F (valid for |d| < 2^22): 0x4B400000 is 1.5 * 2^23
-__device__ __forceinline__ float acc_to_float(uint32_t d, bool big) {
-  return big ? (float)(int)d : __uint_as_float(d + 0x4B400000u) - 12582912.f;
-}
+__device__ __forceinline__ float acc_to_float(uint32_t d) { return __uint_as_float(d + 0x4B400000u) - 12582912.f; }
 // NI-LIF level of y as the low byte of the returned word: round-half-even by the 2^23 trick (== rintf on [0, d_max])
 __device__ __forceinline__ uint32_t level_bits(float y, float d_max) {
   return __float_as_uint(fminf(fmaxf(y, 0.f), d_max) + 8388608.f);
@@ -149,27 +167,52 @@ __device__ __forceinline__ uint32_t pack_levels(float a, float b, float c, float
   return __byte_perm(lo, hi, 0x5410);
 }
 
+// Stage the per-channel epilogue constants of one channel tile: ss[0..2][64] = scale * 128^(pieces-1-plane), ss[3][64] = shift.
+__device__ __forceinline__ void stage_affine(const TcParams& p, float* ss, int co_base, int img, int et) {
+  if (et < 4 * TC_BN) {
+    const int which = et >> 6, ch = co_base + (et & (TC_BN - 1));
+    float v = 0.f;
+    if (ch < p.Cout) {
+      if (which == 3) {
+        v = __ldg(p.shift + (int64_t)img * p.ss_img_stride + ch);
+      } else if (which < p.pieces) {
+        const float sc = __ldg(p.scale + (int64_t)img * p.ss_img_stride + ch);
+        const int e = p.pieces - 1 - which;
+        v = sc * (e == 2 ? 16384.f : (e == 1 ? 128.f : 1.f));          // exact: power-of-two factor
+      }
+    }
+    ss[et] = v;
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nB = TC_BN * p.pieces;                    // MMA N
   const int a_bytes = TC_BM * p.bk, b_bytes = nB * p.bk;
-  const int stage_bytes = a_bytes + b_bytes;          // multiples of 1024
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const int num_chunks = p.taps * p.cin_chunks;
+  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;      // multiples of 1024
+  uint8_t* b_res = smem;                                                   // [num_chunks][nB][bk] when resident
+  uint8_t* ring = smem + (p.b_resident ? (size_t)num_chunks * b_bytes : 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 2;                  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* ss_stage = reinterpret_cast<float*>(tmem_slot + 2);      // [2][4][64] floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_chunks = p.taps * p.cin_chunks;
+  const int tile_n = blockIdx.x % p.tiles_n;
+  const int slot = blockIdx.x / p.tiles_n;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -182,79 +225,109 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer
-      int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileOrigin o = tile_origin(p, tile);
-        const int w_row0 = (p.w_img_rows ? o.img * p.w_img_rows : 0) + o.tile_n * nB;
-        for (int c = 0; c < num_chunks; ++c) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          const int tap = c / p.cin_chunks, cc = c % p.cin_chunks;
-          if (p.mode_conv) {
-            const int kh = tap / p.taps_w, kw = tap % p.taps_w;
-            tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, o.wo0 * p.stride - p.pad + kw, o.ho0 * p.stride - p.pad + kh, o.img);
+    // ===== TMA producer (whole warp runs the loop; one elected lane issues)
+    if (p.b_resident) {
+      if (elect_one()) {
+        mbar_expect_tx(b_full, (uint32_t)(num_chunks * b_bytes));
+        for (int c = 0; c < num_chunks; ++c) tma_load_2d(b_res + (size_t)c * b_bytes, &map_b, b_full, c * p.bk, tile_n * nB);
+      }
+      __syncwarp();
+    }
+    int stage = 0, phase = 0;
+    for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n) {
+      const TileOrigin o = tile_origin(p, tile_m);
+      const int w_row0 = (p.w_img_rows ? o.img * p.w_img_rows : 0) + tile_n * nB;
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = ring + (size_t)stage * stage_bytes;
+        const int tap = c / p.cin_chunks, cc = c % p.cin_chunks;
+        if (elect_one()) {
+          if (p.debug & 4) {
+            mbar_arrive(&full[stage]);
           } else {
-            tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, o.tile_m * TC_BM);
+            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            if (p.mode_conv) {
+              const int kh = tap / p.taps_w, kw = tap % p.taps_w;
+              tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, o.wo0 * p.stride - p.pad + kw, o.ho0 * p.stride - p.pad + kh, o.img);
+            } else {
+              tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, tile_m * TC_BM);
+            }
+            if (!p.b_resident) tma_load_2d(sa + a_bytes, &map_b, &full[stage], c * p.bk, w_row0);
           }
-          tma_load_2d(sb, &map_b, &full[stage], c * p.bk, w_row0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nB >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+    // ===== MMA issuer (whole warp runs the loop; one elected lane issues)
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nB >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (p.b_resident) { mbar_wait(b_full, 0); tc_fence_after(); }
+    const int nk = p.bk / 32;
+    int stage = 0, phase = 0, it = 0;
+    for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
-        for (int c = 0; c < num_chunks; ++c) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t da = smem_desc(sa, p.bk), db = smem_desc(sa + a_bytes, p.bk);
-          const int nk = p.bk / 32;
-          for (int k = 0; k < nk; ++k)
-            umma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);   // +32 B per K step
+        const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
+        const uint32_t sb = p.b_resident ? smem_u32(b_res + (size_t)c * b_bytes) : sa + a_bytes;
+        const uint64_t da = smem_desc(sa, p.bk), db = smem_desc(sb, p.bk);
+        if (elect_one()) {
+          if (!(p.debug & 2)) {
+            for (int k = 0; k < nk; ++k)
+              umma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);   // +32 B per K step
+          }
           umma_commit(&empty[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (c == num_chunks - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32); thread = one output row
+    // ===== epilogue (8 warps): warp w reads TMEM lanes [32*(w%4), +32) -- thread = one output row -- and one half
+    // (32 channels) of the tile's columns.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
-    const bool big = p.big_k != 0;
+    const int et = threadIdx.x - 64;                    // 0..255 within the epilogue group
+    const int co_base = tile_n * TC_BN;
+    const bool per_tile_affine = p.ss_img_stride != 0;
+    if (!per_tile_affine) {
+      stage_affine(p, ss_stage, co_base, 0, et);
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
+    }
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const TileOrigin o = tile_origin(p, tile);
+    for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
+      const TileOrigin o = tile_origin(p, tile_m);
       const int acc = it & 1;
+      const float* ss = ss_stage;
+      if (per_tile_affine) {                             // per-image weights: constants change with the image
+        float* dst = ss_stage + acc * (4 * TC_BN);
+        stage_affine(p, dst, co_base, o.img, et);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        ss = dst;
+      }
       int64_t m;            // flat output row (n*Ho*Wo index), -1 if outside
       if (p.mode_conv) {
         const int ho = o.ho0 + r / p.TW, wo = o.wo0 + r % p.TW;
         m = (ho < p.Ho && wo < p.Wo) ? ((int64_t)o.img * p.Ho + ho) * p.Wo + wo : -1;
       } else {
-        m = (int64_t)o.tile_m * TC_BM + r;
+        m = (int64_t)tile_m * TC_BM + r;
         if (m >= p.M_total) m = -1;
       }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (p.debug & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
-      const int co_base = o.tile_n * TC_BN;
-      const float* sc_ptr = p.scale + (int64_t)o.img * p.ss_img_stride;
-      const float* sh_ptr = p.shift + (int64_t)o.img * p.ss_img_stride;
 #pragma unroll 1
-      for (int j0 = 0; j0 < TC_BN; j0 += 16) {
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j0 = half * 32 + jj * 16;
         if (co_base + j0 >= p.Cout) break;               // warp-uniform
         uint32_t d0[16], d1[16], d2[16];
         tmem_ld16(trow + j0, d0);
@@ -264,30 +337,34 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (m < 0) continue;
         float y[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = acc_to_float(d0[j], big);
-          if (p.pieces > 1) v = fmaf(v, 128.f, acc_to_float(d1[j], big));
-          if (p.pieces > 2) v = fmaf(v, 128.f, acc_to_float(d2[j], big));
-          y[j] = v;
+        for (int q = 0; q < 4; ++q) {
+          const float4 sh = *reinterpret_cast<const float4*>(ss + 3 * TC_BN + j0 + 4 * q);
+          y[4 * q] = sh.x; y[4 * q + 1] = sh.y; y[4 * q + 2] = sh.z; y[4 * q + 3] = sh.w;
         }
+        // y = shift + sum_planes float(d_plane) * (scale * 128^e), least significant plane first
+        auto plane = [&](const uint32_t (&d)[16], int which) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 m4 = *reinterpret_cast<const float4*>(ss + which * TC_BN + j0 + 4 * q);
+            if (p.big_k) {
+              y[4 * q] = fmaf((float)(int)d[4 * q], m4.x, y[4 * q]);
+              y[4 * q + 1] = fmaf((float)(int)d[4 * q + 1], m4.y, y[4 * q + 1]);
+              y[4 * q + 2] = fmaf((float)(int)d[4 * q + 2], m4.z, y[4 * q + 2]);
+              y[4 * q + 3] = fmaf((float)(int)d[4 * q + 3], m4.w, y[4 * q + 3]);
+            } else {
+              y[4 * q] = fmaf(acc_to_float(d[4 * q]), m4.x, y[4 * q]);
+              y[4 * q + 1] = fmaf(acc_to_float(d[4 * q + 1]), m4.y, y[4 * q + 1]);
+              y[4 * q + 2] = fmaf(acc_to_float(d[4 * q + 2]), m4.z, y[4 * q + 2]);
+              y[4 * q + 3] = fmaf(acc_to_float(d[4 * q + 3]), m4.w, y[4 * q + 3]);
+            }
+          }
+        };
+        if (p.pieces > 2) plane(d2, 2);
+        if (p.pieces > 1) plane(d1, 1);
+        plane(d0, 0);
         const int co0 = co_base + j0;
         const int nvalid = min(16, p.Cout - co0);
         const bool full16 = nvalid == 16 && (p.Cout & 3) == 0;
-        if (full16) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(sc_ptr + co0) + q);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(sh_ptr + co0) + q);
-            y[4 * q] = __fadd_rn(__fmul_rn(y[4 * q], sc.x), sh.x);
-            y[4 * q + 1] = __fadd_rn(__fmul_rn(y[4 * q + 1], sc.y), sh.y);
-            y[4 * q + 2] = __fadd_rn(__fmul_rn(y[4 * q + 2], sc.z), sh.z);
-            y[4 * q + 3] = __fadd_rn(__fmul_rn(y[4 * q + 3], sc.w), sh.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) y[j] = __fadd_rn(__fmul_rn(y[j], __ldg(sc_ptr + co0 + j)), __ldg(sh_ptr + co0 + j));
-        }
         const int64_t row_off = m * p.Cout + co0;
         if (p.residual) {
           if (full16) {
@@ -297,7 +374,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               y[4 * q] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
             }
           } else {
-            for (int j = 0; j < nvalid; ++j) y[j] += p.residual[row_off + j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nvalid) y[j] += p.residual[row_off + j];
           }
         }
         if (!p.out_transposed) {
@@ -307,7 +386,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(p.out_f32 + row_off + 4 * q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
             } else {
-              for (int j = 0; j < nvalid; ++j) p.out_f32[row_off + j] = y[j];
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nvalid) p.out_f32[row_off + j] = y[j];
             }
           }
           if (p.out_spike) {
@@ -317,16 +398,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int q = 0; q < 4; ++q) w[q] = pack_levels(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3], p.d_max);
               *reinterpret_cast<uint4*>(p.out_spike + row_off) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
-              for (int j = 0; j < nvalid; ++j) p.out_spike[row_off + j] = (int8_t)(level_bits(y[j], p.d_max) & 0xffu);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nvalid) p.out_spike[row_off + j] = (int8_t)(level_bits(y[j], p.d_max) & 0xffu);
             }
           }
         } else {
           const int64_t im = m / p.M_img, pm = m % p.M_img;
           const int64_t tbase = im * (int64_t)p.M_img * p.Cout + pm;
-          for (int j = 0; j < nvalid; ++j) {
-            const int64_t oo = tbase + (int64_t)(co0 + j) * p.M_img;
-            if (p.out_f32) p.out_f32[oo] = y[j];
-            if (p.out_spike) p.out_spike[oo] = (int8_t)(level_bits(y[j], p.d_max) & 0xffu);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < nvalid) {
+              const int64_t oo = tbase + (int64_t)(co0 + j) * p.M_img;
+              if (p.out_f32) p.out_f32[oo] = y[j];
+              if (p.out_spike) p.out_spike[oo] = (int8_t)(level_bits(y[j], p.d_max) & 0xffu);
+            }
           }
         }
       }
@@ -390,10 +476,6 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   const int per_img_w = a->per_image_weights ? 1 : 0;
   p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
   const int nB = TC_BN * p.pieces;
-  const int stage_bytes = (TC_BM + nB) * p.bk;
-  p.stages = 196 * 1024 / stage_bytes;               // one persistent CTA per SM owns the whole shared memory
-  if (p.stages > 10) p.stages = 10;
-  if (p.stages < 2) p.stages = 2;
   const int tiles_n = (a->Cout + TC_BN - 1) / TC_BN;
   if (per_img_w) {
     S2F_REQUIRE(!p.mode_conv && p.M_img % TC_BM == 0, "gemm_i8_tc: per-image weights need a 1x1 layer with Ho*Wo % 128 == 0");
@@ -440,9 +522,20 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
     if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(B) failed (%s) code %lld", "", (long long)r);
   }
   p.tiles_n = tiles_n;
-  p.total_tiles = tiles_m * tiles_n;
+  p.tiles_m = tiles_m;
+  { const char* dbg = getenv("S2F_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.big_k = ((int64_t)kpad * 8 * 64 >= (1ll << 22)) ? 1 : 0;
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  const int num_chunks = p.taps * p.cin_chunks;
+  const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 4 * TC_BN * sizeof(float);
+  const size_t budget = 226 * 1024 - fixed;
+  const size_t b_all = (size_t)num_chunks * nB * p.bk;
+  // weight-stationary when the whole K extent of the weight tile fits and still leaves >= 4 A stages
+  p.b_resident = (!per_img_w && b_all + 4 * (size_t)TC_BM * p.bk <= budget) ? 1 : 0;
+  const int stage_bytes = p.b_resident ? TC_BM * p.bk : (TC_BM + nB) * p.bk;
+  p.stages = (int)((budget - (p.b_resident ? b_all : 0)) / stage_bytes);
+  if (p.stages > 12) p.stages = 12;
+  if (p.stages < 2) p.stages = 2;
+  size_t smem = (p.b_resident ? b_all : 0) + (size_t)p.stages * stage_bytes + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;          // never two CTAs on one SM: each allocates all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
@@ -456,7 +549,12 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
-  const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+  // CTAs per channel tile: fill the SMs, never more than there are row tiles
+  int per_n = num_sms / tiles_n;
+  if (per_n < 1) per_n = 1;
+  if (per_n > tiles_m) per_n = tiles_m;
+  p.ctas_per_n = per_n;
+  const unsigned grid = (unsigned)(per_n * tiles_n);
   gemm_i8_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("gemm_i8_tc_kernel");
 }

@@ -287,6 +287,17 @@ __device__ __forceinline__ void t2_arrive(uint64_t* bar) {
 __device__ __forceinline__ void t2_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tl_smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool t2_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float t2_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t t2_pack_half2(float a, float b) {
@@ -420,19 +431,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
     }
   } else if (warp == T2_PROD_WARPS) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(TL_BM >> 4) << 24);   // F32 += F16 x F16
-      const int ksteps = (p.Q + 15) >> 4;
-      const uint32_t b_hi = tl_smem_u32(sB), b_lo = b_hi + b_plane;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        t2_wait(&a_full[s], ph);
-        t2_wait(&t_empty[s], ph ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = tl_smem_u32(sA + s * a_stage), a_lo = a_hi + a_plane;
-        const uint32_t d = tmem_base + (uint32_t)(s * T2_ACC_COLS);
+    // the whole warp runs the loop and one elected lane issues: operands stay in uniform registers
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(TL_BM >> 4) << 24);   // F32 += F16 x F16
+    const int ksteps = (p.Q + 15) >> 4;
+    const uint32_t b_hi = tl_smem_u32(sB), b_lo = b_hi + b_plane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      t2_wait(&a_full[s], ph);
+      t2_wait(&t_empty[s], ph ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = tl_smem_u32(sA + s * a_stage), a_lo = a_hi + a_plane;
+      const uint32_t d = tmem_base + (uint32_t)(s * T2_ACC_COLS);
+      if (t2_elect_one()) {
         uint32_t acc = 0;
 #pragma unroll 1
         for (int combo = 0; combo < 3; ++combo) {
@@ -448,6 +460,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
         t2_commit(&a_empty[s]);        // A stage reusable once these MMAs have read it
         t2_commit(&t_full[s]);         // accumulator complete
       }
+      __syncwarp();
     }
   } else {
     // ================================================================== epilogue

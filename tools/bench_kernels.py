@@ -25,8 +25,8 @@ FLUSH = None
 def flush_l2():
     global FLUSH
     if FLUSH is None:
-        FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    FLUSH.zero_()
+        FLUSH = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
+    FLUSH.view(torch.int64).sum()        # read 256 MB: evicts the working set and leaves only clean lines in L2
 
 
 def timed(fn, iters=ITERS, flush=True):
@@ -38,6 +38,7 @@ def timed(fn, iters=ITERS, flush=True):
         if flush:
             flush_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400000)        # ~0.2 ms spin: the launch below is already queued when the GPU reaches e0
         e0.record()
         fn()
         e1.record()
@@ -71,7 +72,8 @@ def bench_gemm(out):
     for name, n, H, W, cin, cout, k, stride, f32, spike, res in GEMM_CASES:
         a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8).cuda()
         w = torch.randn(cout, k * k * cin, generator=g) / (cin * k * k) ** 0.5
-        packed, rowscale = ops.pack_weights_i8(w, k * k, cin, 3)
+        PIECES = int(os.environ.get("PIECES", "3"))
+        packed, rowscale = ops.pack_weights_i8(w, k * k, cin, PIECES)
         packed = packed.cuda()
         sc, sh = (rowscale / 8).cuda(), torch.zeros(cout).cuda()
         pad = (k - 1) // 2
@@ -80,7 +82,7 @@ def bench_gemm(out):
 
         def run():
             ops.gemm_tc(a, packed, n=n, H=H, W=W, Cin=cin, Cout=cout, scale=sc, shift=sh, k=k, stride=stride, pad=pad,
-                        pieces=3, residual=r, want_f32=f32, want_spike=spike)
+                        pieces=PIECES, residual=r, want_f32=f32, want_spike=spike)
 
         t = timed(run)
         flops = 2.0 * n * Ho * Wo * cout * k * k * cin
