@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs2f.so")
+LIB_PATH = os.environ.get("S2F_LIB") or os.path.join(_HERE, "libs2f.so")      # S2F_LIB: experiment builds only
 
 ABI_VERSION = 2
 

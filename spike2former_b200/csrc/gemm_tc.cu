@@ -22,7 +22,11 @@ namespace s2f {
 
 constexpr int TC_BM = 128;        // rows (pixels / tokens) per tile == UMMA M
 constexpr int TC_BN = 64;         // output channels per tile
-constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+#ifndef S2F_EPI_WARPS
+#define S2F_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = S2F_EPI_WARPS;                 // 8 or 16: column split of the epilogue (32 or 16 channels per warp)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0 TMA, warp 1 MMA, the rest epilogue
 
 __host__ __device__ inline int tc_bk(int cin) { return cin >= 128 ? 128 : (cin >= 64 ? 64 : 32); }
 __host__ __device__ inline int tc_cin_pad(int cin) { const int bk = tc_bk(cin); return (cin + bk - 1) / bk * bk; }
@@ -42,9 +46,8 @@ struct TcParams {
   int pieces, stages;
   int out_transposed;
   int tiles_n, tiles_m, ctas_per_n;
-  int debug;            // S2F_GEMM_DEBUG bits (experiments only): 1 = epilogue skips math and stores, 2 = no MMA issue
+  int group;            // K chunks per pipeline stage (3 = one kernel row of a 3x3 layer with narrow Cin)
   int b_resident;       // all K chunks of the weight tile stay in shared memory for the CTA's lifetime
-  int big_k;            // accumulators may exceed 2^22: convert with I2F instead of the magic-number trick
   int w_img_rows;       // packed weight rows per image (0: one weight matrix for all images)
   int ss_img_stride;    // scale/shift elements per image (0: shared)
   float d_max;
@@ -155,8 +158,11 @@ __device__ __forceinline__ TileOrigin tile_origin(const TcParams& p, int tile_m)
   return o;
 }
 
-// int32 accumulator -> float without I2F (valid for |d| < 2^22): 0x4B400000 is 1.5 * 2^23
-__device__ __forceinline__ float acc_to_float(uint32_t d) { return __uint_as_float(d + 0x4B400000u) - 12582912.f; }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 // NI-LIF level of y as the low byte of the returned word: round-half-even by the 2^23 trick (== rintf on [0, d_max])
 __device__ __forceinline__ uint32_t level_bits(float y, float d_max) {
   return __float_as_uint(fminf(fmaxf(y, 0.f), d_max) + 8388608.f);
@@ -169,7 +175,7 @@ __device__ __forceinline__ uint32_t pack_levels(float a, float b, float c, float
 
 // Stage the per-channel epilogue constants of one channel tile: ss[0..2][64] = scale * 128^(pieces-1-plane), ss[3][64] = shift.
 __device__ __forceinline__ void stage_affine(const TcParams& p, float* ss, int co_base, int img, int et) {
-  if (et < 4 * TC_BN) {
+  for (; et < 4 * TC_BN; et += 32 * TC_EPI_WARPS) {
     const int which = et >> 6, ch = co_base + (et & (TC_BN - 1));
     float v = 0.f;
     if (ch < p.Cout) {
@@ -185,14 +191,60 @@ __device__ __forceinline__ void stage_affine(const TcParams& p, float* ss, int c
   }
 }
 
+
+template <int PIECES, int NK>
+__device__ __forceinline__ void mma_role(const TcParams& p, uint32_t ring_addr, uint32_t bres_addr, int stage_bytes,
+                                         uint64_t* full, uint64_t* empty, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                         uint32_t tmem_base, int slot) {
+  constexpr int nB = TC_BN * PIECES;
+  constexpr int BKB = 32 * NK;                                   // bytes of K per chunk
+  constexpr uint32_t A_STEP = (TC_BM * BKB) >> 4, B_STEP = (nB * BKB) >> 4;      // descriptor units (16 B)
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major, N>>3 @17, M>>4 @24
+  constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nB >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  const uint64_t da_ring = smem_desc(ring_addr, BKB);
+  const uint64_t db_res = smem_desc(bres_addr, BKB);
+  const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+  const int G = p.group, num_groups = (p.taps * p.cin_chunks) / G, stages = p.stages;
+  const bool resident = p.b_resident != 0;
+  int stage = 0, phase = 0, it = 0;
+  for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
+    const int acc = it & 1;
+    mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
+    uint32_t c_units = 0;                                    // resident-B offset of the current chunk, descriptor units
+    for (int g = 0; g < num_groups; ++g) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da0 = da_ring + (uint64_t)((uint32_t)stage * stage_step);
+        const uint64_t db0 = resident ? db_res + (uint64_t)c_units : da0 + (uint64_t)((uint32_t)G * A_STEP);
+        for (int gi = 0; gi < G; ++gi) {
+          const uint64_t da = da0 + (uint64_t)((uint32_t)gi * A_STEP), db = db0 + (uint64_t)((uint32_t)gi * B_STEP);
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+            umma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (g | gi | k) ? 1u : 0u);   // +32 B per K step
+        }
+        umma_commit(&empty[stage]);
+        if (g == num_groups - 1) umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+      c_units += (uint32_t)G * B_STEP;
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
+template <int PIECES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nB = TC_BN * p.pieces;                    // MMA N
+  constexpr int nB = TC_BN * PIECES;                    // MMA N
   const int a_bytes = TC_BM * p.bk, b_bytes = nB * p.bk;
   const int num_chunks = p.taps * p.cin_chunks;
-  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;      // multiples of 1024
+  const int stage_bytes = p.group * (p.b_resident ? a_bytes : a_bytes + b_bytes);      // multiples of 1024
+  const int num_groups = num_chunks / p.group;
   uint8_t* b_res = smem;                                                   // [num_chunks][nB][bk] when resident
   uint8_t* ring = smem + (p.b_resident ? (size_t)num_chunks * b_bytes : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
@@ -211,7 +263,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -237,22 +289,20 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n) {
       const TileOrigin o = tile_origin(p, tile_m);
       const int w_row0 = (p.w_img_rows ? o.img * p.w_img_rows : 0) + tile_n * nB;
-      for (int c = 0; c < num_chunks; ++c) {
+      const int x0 = o.wo0 * p.stride - p.pad, y0 = o.ho0 * p.stride - p.pad, row0 = tile_m * TC_BM;
+      int c = 0, cc = 0, kh = 0, kw = 0;                   // running chunk index / channel chunk / tap coordinates
+      for (int g = 0; g < num_groups; ++g) {
         mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = ring + (size_t)stage * stage_bytes;
-        const int tap = c / p.cin_chunks, cc = c % p.cin_chunks;
+        uint8_t* st = ring + (size_t)stage * stage_bytes;
         if (elect_one()) {
-          if (p.debug & 4) {
-            mbar_arrive(&full[stage]);
-          } else {
-            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            if (p.mode_conv) {
-              const int kh = tap / p.taps_w, kw = tap % p.taps_w;
-              tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, o.wo0 * p.stride - p.pad + kw, o.ho0 * p.stride - p.pad + kh, o.img);
-            } else {
-              tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, tile_m * TC_BM);
-            }
-            if (!p.b_resident) tma_load_2d(sa + a_bytes, &map_b, &full[stage], c * p.bk, w_row0);
+          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          for (int gi = 0; gi < p.group; ++gi) {
+            uint8_t* sa = st + gi * a_bytes;
+            if (p.mode_conv) tma_load_4d(sa, &map_a, &full[stage], cc * p.bk, x0 + kw, y0 + kh, o.img);
+            else tma_load_2d(sa, &map_a, &full[stage], cc * p.bk, row0);
+            if (!p.b_resident) tma_load_2d(st + p.group * a_bytes + gi * b_bytes, &map_b, &full[stage], c * p.bk, w_row0);
+            ++c;
+            if (++cc == p.cin_chunks) { cc = 0; if (++kw == p.taps_w) { kw = 0; ++kh; } }
           }
         }
         __syncwarp();
@@ -260,58 +310,36 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (whole warp runs the loop; one elected lane issues)
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nB >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // ===== MMA issuer (whole warp runs the loop; one elected lane issues).  Everything per chunk is a handful of
+    // uniform-datapath instructions: descriptors advance by constant strides (address >> 4 fits the 14-bit field).
     if (p.b_resident) { mbar_wait(b_full, 0); tc_fence_after(); }
-    const int nk = p.bk / 32;
-    int stage = 0, phase = 0, it = 0;
-    for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
-      const int acc = it & 1;
-      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
-      for (int c = 0; c < num_chunks; ++c) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
-        const uint32_t sb = p.b_resident ? smem_u32(b_res + (size_t)c * b_bytes) : sa + a_bytes;
-        const uint64_t da = smem_desc(sa, p.bk), db = smem_desc(sb, p.bk);
-        if (elect_one()) {
-          if (!(p.debug & 2)) {
-            for (int k = 0; k < nk; ++k)
-              umma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);   // +32 B per K step
-          }
-          umma_commit(&empty[stage]);
-          if (c == num_chunks - 1) umma_commit(&tmem_full[acc]);
-        }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-    }
+    if (p.bk == 128) mma_role<PIECES, 4>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
+    else if (p.bk == 64) mma_role<PIECES, 2>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
+    else mma_role<PIECES, 1>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
   } else {
     // ===== epilogue (8 warps): warp w reads TMEM lanes [32*(w%4), +32) -- thread = one output row -- and one half
     // (32 channels) of the tile's columns.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                   // column slice: 64 / (TC_EPI_WARPS / 4) channels each
+    constexpr int COLS_PER_WARP = TC_BN / (TC_EPI_WARPS / 4);
     const int r = quad * 32 + lane;
     const int et = threadIdx.x - 64;                    // 0..255 within the epilogue group
     const int co_base = tile_n * TC_BN;
     const bool per_tile_affine = p.ss_img_stride != 0;
     if (!per_tile_affine) {
       stage_affine(p, ss_stage, co_base, 0, et);
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");     // epilogue warps only
     }
     int it = 0;
     for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
       const TileOrigin o = tile_origin(p, tile_m);
       const int acc = it & 1;
-      const float* ss = ss_stage;
+      uint32_t ss_addr = smem_u32(ss_stage);
       if (per_tile_affine) {                             // per-image weights: constants change with the image
         float* dst = ss_stage + acc * (4 * TC_BN);
         stage_affine(p, dst, co_base, o.img, et);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        ss = dst;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        ss_addr = smem_u32(dst);
       }
       int64_t m;            // flat output row (n*Ho*Wo index), -1 if outside
       if (p.mode_conv) {
@@ -323,45 +351,41 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      if (p.debug & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
 #pragma unroll 1
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j0 = half * 32 + jj * 16;
+      for (int jj = 0; jj < COLS_PER_WARP / 16; ++jj) {
+        const int j0 = half * COLS_PER_WARP + jj * 16;
         if (co_base + j0 >= p.Cout) break;               // warp-uniform
         uint32_t d0[16], d1[16], d2[16];
         tmem_ld16(trow + j0, d0);
-        if (p.pieces > 1) tmem_ld16(trow + TC_BN + j0, d1);
-        if (p.pieces > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
+        if (PIECES > 1) tmem_ld16(trow + TC_BN + j0, d1);
+        if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
         tmem_ld_wait();
         if (m < 0) continue;
+        // y = shift + float(d0) * (scale * 128^(pieces-1)) + float(low planes combined in int32) * scale.
+        // The two low digit planes are merged exactly in integer arithmetic (|d1 * 128 + d2| < 2^31 for K < 32768), so
+        // the recombination costs one IMAD, two I2FP and two FFMA per output; each conversion rounds once (fp32).
         float y[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 sh = *reinterpret_cast<const float4*>(ss + 3 * TC_BN + j0 + 4 * q);
-          y[4 * q] = sh.x; y[4 * q + 1] = sh.y; y[4 * q + 2] = sh.z; y[4 * q + 3] = sh.w;
-        }
-        // y = shift + sum_planes float(d_plane) * (scale * 128^e), least significant plane first
-        auto plane = [&](const uint32_t (&d)[16], int which) {
+          const float4 sh = lds128(ss_addr + (uint32_t)(3 * TC_BN + j0 + 4 * q) * 4u);
+          const float4 s_lo = lds128(ss_addr + (uint32_t)((PIECES - 1) * TC_BN + j0 + 4 * q) * 4u);   // scale * 1
+          const float4 s_hi = lds128(ss_addr + (uint32_t)(j0 + 4 * q) * 4u);                               // scale * 128^(pieces-1)
+          float lo[4], hi[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 m4 = *reinterpret_cast<const float4*>(ss + which * TC_BN + j0 + 4 * q);
-            if (p.big_k) {
-              y[4 * q] = fmaf((float)(int)d[4 * q], m4.x, y[4 * q]);
-              y[4 * q + 1] = fmaf((float)(int)d[4 * q + 1], m4.y, y[4 * q + 1]);
-              y[4 * q + 2] = fmaf((float)(int)d[4 * q + 2], m4.z, y[4 * q + 2]);
-              y[4 * q + 3] = fmaf((float)(int)d[4 * q + 3], m4.w, y[4 * q + 3]);
-            } else {
-              y[4 * q] = fmaf(acc_to_float(d[4 * q]), m4.x, y[4 * q]);
-              y[4 * q + 1] = fmaf(acc_to_float(d[4 * q + 1]), m4.y, y[4 * q + 1]);
-              y[4 * q + 2] = fmaf(acc_to_float(d[4 * q + 2]), m4.z, y[4 * q + 2]);
-              y[4 * q + 3] = fmaf(acc_to_float(d[4 * q + 3]), m4.w, y[4 * q + 3]);
-            }
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            if (PIECES == 3) { lo[e] = (float)((int)d1[j] * 128 + (int)d2[j]); hi[e] = (float)(int)d0[j]; }
+            else if (PIECES == 2) { lo[e] = (float)((int)d0[j] * 128 + (int)d1[j]); hi[e] = 0.f; }
+            else { lo[e] = (float)(int)d0[j]; hi[e] = 0.f; }
           }
-        };
-        if (p.pieces > 2) plane(d2, 2);
-        if (p.pieces > 1) plane(d1, 1);
-        plane(d0, 0);
+          y[4 * q] = fmaf(lo[0], s_lo.x, sh.x); y[4 * q + 1] = fmaf(lo[1], s_lo.y, sh.y);
+          y[4 * q + 2] = fmaf(lo[2], s_lo.z, sh.z); y[4 * q + 3] = fmaf(lo[3], s_lo.w, sh.w);
+          if (PIECES == 3) {
+            y[4 * q] = fmaf(hi[0], s_hi.x, y[4 * q]); y[4 * q + 1] = fmaf(hi[1], s_hi.y, y[4 * q + 1]);
+            y[4 * q + 2] = fmaf(hi[2], s_hi.z, y[4 * q + 2]); y[4 * q + 3] = fmaf(hi[3], s_hi.w, y[4 * q + 3]);
+          }
+        }
         const int co0 = co_base + j0;
         const int nvalid = min(16, p.Cout - co0);
         const bool full16 = nvalid == 16 && (p.Cout & 3) == 0;
@@ -523,15 +547,17 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   }
   p.tiles_n = tiles_n;
   p.tiles_m = tiles_m;
-  { const char* dbg = getenv("S2F_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-  p.big_k = ((int64_t)kpad * 8 * 64 >= (1ll << 22)) ? 1 : 0;
+
+  S2F_REQUIRE((int64_t)kpad * 8 * 64 * 129 < (1ll << 31), "gemm_i8_tc: K too large for the int32 plane merge");
   const int num_chunks = p.taps * p.cin_chunks;
   const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 4 * TC_BN * sizeof(float);
   const size_t budget = 226 * 1024 - fixed;
   const size_t b_all = (size_t)num_chunks * nB * p.bk;
   // weight-stationary when the whole K extent of the weight tile fits and still leaves >= 4 A stages
-  p.b_resident = (!per_img_w && b_all + 4 * (size_t)TC_BM * p.bk <= budget) ? 1 : 0;
-  const int stage_bytes = p.b_resident ? TC_BM * p.bk : (TC_BM + nB) * p.bk;
+  p.b_resident = (!per_img_w && b_all + 6 * (size_t)TC_BM * p.bk <= budget) ? 1 : 0;
+  p.group = (p.mode_conv && p.taps == 9 && p.cin_chunks == 1 && p.bk <= 64) ? 3 : 1;
+  if (p.group == 1 && p.b_resident && num_chunks % 2 == 0) p.group = 2;      // 32 KB spike stages: half the barrier rounds
+  const int stage_bytes = p.group * (p.b_resident ? TC_BM * p.bk : (TC_BM + nB) * p.bk);
   p.stages = (int)((budget - (p.b_resident ? b_all : 0)) / stage_bytes);
   if (p.stages > 12) p.stages = 12;
   if (p.stages < 2) p.stages = 2;
@@ -539,7 +565,9 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (smem < 120 * 1024) smem = 120 * 1024;          // never two CTAs on one SM: each allocates all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "gemm_i8_tc: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -555,7 +583,9 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (per_n > tiles_m) per_n = tiles_m;
   p.ctas_per_n = per_n;
   const unsigned grid = (unsigned)(per_n * tiles_n);
-  gemm_i8_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  if (p.pieces == 3) gemm_i8_tc_kernel<3><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  else if (p.pieces == 2) gemm_i8_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  else gemm_i8_tc_kernel<1><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("gemm_i8_tc_kernel");
 }
 

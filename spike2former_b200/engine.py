@@ -98,10 +98,39 @@ def _conv_gemm(sd, conv_key, bn_key, device, k=1, stride=1, pad=0, extra_scale=N
     return Gemm(w2d, s, t, cin, k, stride, pad, device)
 
 
-def _rep_gemm(sd, keys, device, cin_pad=None, cout_pad=None):
-    """One dense 3x3 for one or several RepConv(+BN) branches sharing their input (outputs concatenated)."""
+def head_pad(d):
+    """Per-head channel count kept in HBM: a multiple of 4 so that every head slice is 32-bit aligned for the
+    attention kernels (stage 4: 360 channels = 8 heads x 45 -> 8 x 48)."""
+    return (d + 3) // 4 * 4
+
+
+def _head_index(heads, d, dp):
+    """positions of the reference's channels h*d + j inside the head-padded layout h*dp + j"""
+    return (torch.arange(heads)[:, None] * dp + torch.arange(d)[None, :]).reshape(-1)
+
+
+def _rep_gemm(sd, keys, device, cin_pad=None, cout_pad=None, out_heads=None, in_heads=None):
+    """One dense 3x3 for one or several RepConv(+BN) branches sharing their input (outputs concatenated).
+    out_heads = (heads, d, dp): every branch's output channels are scattered into the head-padded layout;
+    in_heads: the same for the input channels (zero weights / zero outputs at the padding positions)."""
     ws, bs = zip(*(fold.repconv_dense3x3(sd, k) for k in keys))
+    if out_heads is not None:
+        heads, d, dp = out_heads
+        idx = _head_index(heads, d, dp)
+        ws2, bs2 = [], []
+        for w, b in zip(ws, bs):
+            w2 = torch.zeros(heads * dp, w.shape[1], dtype=w.dtype); w2[idx] = w
+            b2 = torch.zeros(heads * dp, dtype=b.dtype); b2[idx] = b
+            ws2.append(w2); bs2.append(b2)
+        ws, bs = ws2, bs2
     w, b = torch.cat(ws, 0), torch.cat(bs, 0)
+    if in_heads is not None:
+        heads, d, dp = in_heads
+        idx = _head_index(heads, d, dp)
+        w3 = w.reshape(w.shape[0], 9, heads * d)
+        w4 = torch.zeros(w.shape[0], 9, heads * dp, dtype=w.dtype)
+        w4[:, :, idx] = w3
+        w = w4.reshape(w.shape[0], -1)
     w, s, b, cin = _pad_channels(w, torch.ones_like(b), b, 9, cin_pad, cout_pad)
     return Gemm(w, s, b, cin, 3, 1, 1, device)
 
@@ -132,11 +161,16 @@ class BackbonePlan:
         for name, st in (("downsample1_2", 2), ("downsample2", 2), ("downsample3", 2), ("downsample4", 1)):
             L[name] = _conv_gemm(sd, name + ".encode_conv", name + ".encode_bn", dev, 3, st, 1,
                                  cout_pad=pad16(e[3]) if name == "downsample4" else None)
+        nh = model.num_heads
         for name in [f"block3.{j}" for j in range(6)] + [f"block4.{j}" for j in range(2)]:
-            cp = pad16(self.width[name.split(".")[0]])
+            c = self.width[name.split(".")[0]]
+            cp = pad16(c)
+            d = c // nh
+            hp = (nh, d, head_pad(d)) if head_pad(d) != d else None      # q|k|v and the attention output are head-padded
             L[name + ".qkv"] = _rep_gemm(sd, [name + ".attn.q_conv", name + ".attn.k_conv", name + ".attn.v_conv"], dev,
-                                         cin_pad=cp)
-            L[name + ".proj"] = _rep_gemm(sd, [name + ".attn.proj_conv"], dev, cin_pad=cp, cout_pad=cp)
+                                         cin_pad=cp, out_heads=hp)
+            L[name + ".proj"] = _rep_gemm(sd, [name + ".attn.proj_conv"], dev, cin_pad=None if hp else cp, cout_pad=cp,
+                                          in_heads=hp)
             L[name + ".fc1"] = _conv_gemm(sd, name + ".mlp.fc1_conv", name + ".mlp.fc1_bn", dev, cin_pad=cp)
             L[name + ".fc2"] = _conv_gemm(sd, name + ".mlp.fc2_conv", name + ".mlp.fc2_bn", dev, cout_pad=cp)
 
@@ -281,19 +315,35 @@ def _ms_block(L, name, s, sp, n, H, W, heads, pr, C):
     C is the reference width; the stream / spike buffers carry pad16(C) channels (zeros beyond C)."""
     CP = s.shape[-1]
     d = C // heads
+    dp = head_pad(d)
+    CA = heads * dp                                                        # width of q, k, v and of the attention output
     N = H * W
     sp = pr.spike(f"{name}.attn.head_spike", sp)
-    _, qkv = L[name + ".qkv"](sp, n, H, W, spike=True)                      # [n,H,W,3C] levels of q|k|v
+    _, qkv = L[name + ".qkv"](sp, n, H, W, spike=True)                      # [n,H,W,3*CA] levels of q|k|v
     if pr.active:
-        q, k, v = (pr.spike(f"{name}.attn.{nm}_spike", qkv[..., i * C:(i + 1) * C].contiguous())
+        def ref_layout(t):                                                  # head-padded [.., heads*dp] -> reference [.., C]
+            return t.reshape(n, H, W, heads, dp)[..., :d].reshape(n, H, W, C).contiguous()
+
+        def padded(t):
+            out = torch.zeros(n, H, W, heads, dp, dtype=t.dtype, device=t.device)
+            out[..., :d] = t.reshape(n, H, W, heads, d)
+            return out.reshape(n, H, W, CA)
+
+        q, k, v = (padded(pr.spike(f"{name}.attn.{nm}_spike", ref_layout(qkv[..., i * CA:(i + 1) * CA])))
                    for i, nm in enumerate("qkv"))
-        ld = C
+        ld = CA
     else:
-        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-        ld = 3 * C
-    att, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, q_ld=ld, kv_ld=ld, out_ld=CP,
+        q, k, v = qkv[..., :CA], qkv[..., CA:2 * CA], qkv[..., 2 * CA:]
+        ld = 3 * CA
+    out_w = CA if dp != d else CP
+    att, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=dp, q_ld=ld, kv_ld=ld, out_ld=out_w,
                              out_scale=(d ** -0.5) * INV ** 3)
-    att = pr.spike(f"{name}.attn.attn_spike", att.view(n, H, W, CP))
+    att = att.view(n, H, W, out_w)
+    if pr.active:
+        if dp != d:
+            att = padded(pr.spike(f"{name}.attn.attn_spike", ref_layout(att)))
+        else:
+            att = pr.spike(f"{name}.attn.attn_spike", att)
     s2, sp2 = L[name + ".proj"](att, n, H, W, residual=s, f32=True, spike=True)
     s2 = pr.real(f"{name}.mlp.fc1_spike", s2)
     sp2 = pr.spike(f"{name}.mlp.fc1_spike", sp2)

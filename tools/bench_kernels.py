@@ -72,7 +72,7 @@ def bench_gemm(out):
     for name, n, H, W, cin, cout, k, stride, f32, spike, res in GEMM_CASES:
         a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8).cuda()
         w = torch.randn(cout, k * k * cin, generator=g) / (cin * k * k) ** 0.5
-        PIECES = int(os.environ.get("PIECES", "3"))
+        PIECES = int(os.environ.get("PIECES", "3"))          # experiments: fewer digit planes
         packed, rowscale = ops.pack_weights_i8(w, k * k, cin, PIECES)
         packed = packed.cuda()
         sc, sh = (rowscale / 8).cuda(), torch.zeros(cout).cuda()
