@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 2 */
+S2F_API int s2f_abi_version(void);   /* currently 3 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -106,6 +106,11 @@ typedef struct {
   int n, H, W, Cin, Cout, KH, KW, stride, pad, pieces;
   float d_max;
   int per_image_weights;   /* 1: w_packed / scale / shift hold one matrix per image (1x1, Ho*Wo % 128 == 0) */
+  /* Top-down FPN merge fused into the epilogue (pixel_decoder.py:455-462): when up_prev != NULL,
+   *   y += bilinear_upsample(up_prev [n, up_H, up_W, Cout] fp32 -> [Ho, Wo], align_corners=False)[row, co]
+   * is added after the affine (same arithmetic as s2f_upsample_add_lif), so lateral conv + upsample + add + NI-LIF
+   * is one launch and the fp32 lateral map never reaches HBM.  Not combinable with out_transposed. */
+  const float* up_prev; int up_H, up_W;
 } s2f_gemm_tc_args;
 
 S2F_API int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream);

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S2F_LIB") or os.path.join(_HERE, "libs2f.so")      # S2F_LIB: experiment builds only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ConvArgs(C.Structure):
@@ -32,6 +32,7 @@ class GemmTcArgs(C.Structure):
         ("n", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
         ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("pieces", C.c_int),
         ("d_max", C.c_float), ("per_image_weights", C.c_int),
+        ("up_prev", C.c_void_p), ("up_H", C.c_int), ("up_W", C.c_int),
     ]
 
 

@@ -256,8 +256,7 @@ __global__ void __launch_bounds__(256) qkv_fast_kernel(const int8_t* __restrict_
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
     if (out_spike)
       *reinterpret_cast<uint32_t*>(out_spike + o) =
-          (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
-          ((uint32_t)(int)spike_level(y[2], d_max) << 16) | ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+          pack_levels4(y[0], y[1], y[2], y[3], d_max);
   }
 }
 

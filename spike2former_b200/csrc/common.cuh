@@ -37,6 +37,18 @@ __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + 
 // round-half-to-even of clamp(v, 0, d): torch.round(torch.clamp(v, 0, d)) -- surrogate.py:529
 __device__ __forceinline__ float spike_level(float v, float d_max) { return rintf(fminf(fmaxf(v, 0.f), d_max)); }
 
+// The same level as the low byte of a word, without the XU-pipe FRND / F2I instructions: for 0 <= v <= d_max < 2^22,
+// v + 2^23 rounds (to nearest, ties to even -- the default fp32 add) to an integer whose value sits in the low mantissa
+// bits of 0x4B000000 | level.  pack_levels4 assembles four of them into one 32-bit word with three PRMT.
+__device__ __forceinline__ uint32_t level_bits(float v, float d_max) {
+  return __float_as_uint(fminf(fmaxf(v, 0.f), d_max) + 8388608.f);
+}
+__device__ __forceinline__ uint32_t pack_levels4(float a, float b, float c, float d, float d_max) {
+  const uint32_t lo = __byte_perm(level_bits(a, d_max), level_bits(b, d_max), 0x0040);
+  const uint32_t hi = __byte_perm(level_bits(c, d_max), level_bits(d, d_max), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+
 __device__ __forceinline__ bool is_tie(float v, float d_max) {
   return (v > 0.f) && (v < d_max) && ((v - floorf(v)) == 0.5f);
 }

@@ -8,19 +8,11 @@
 //   out[img, m, co] = epi( sum_{kh,kw,ci} A[img, ho*s-p+kh, wo*s-p+kw, ci] * W[co, kh, kw, ci] )
 //   epi(acc) = acc*scale[co] + shift[co] (+ residual) -> fp32 and/or NI-LIF int8 level.
 #include "common.cuh"
+#include "conv_direct.cuh"
 
 namespace s2f {
 
 constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4, NTHREADS = 256;
-
-struct ConvP {
-  const void* a; const float* w; const float* scale; const float* shift; const float* residual;
-  float* out_f32; int8_t* out_spike;
-  int n, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, K, ldw;
-  int64_t a_img_stride, a_stride_m, a_stride_k, w_img_stride;
-  float a_scale, d_max;
-  int out_transposed, generic;
-};
 
 template <typename AT>
 __device__ __forceinline__ float a_val(const AT* p, int64_t i);
@@ -173,6 +165,7 @@ extern "C" int s2f_conv_simt(const s2f_conv_args* a, void* stream) {
   p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
   p.out_transposed = a->out_transposed;
   S2F_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv_simt: empty output");
+  if (launch_conv_direct(p, a->a_is_spike != 0, (cudaStream_t)stream)) return check_launch("conv_direct_kernel");
   const int M = p.Ho * p.Wo;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p.Cout, BN), (unsigned)p.n);
   S2F_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_simt: grid too large");

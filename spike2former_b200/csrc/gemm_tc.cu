@@ -33,6 +33,7 @@ __host__ __device__ inline int tc_cin_pad(int cin) { const int bk = tc_bk(cin); 
 
 struct TcParams {
   const float* scale; const float* shift; const float* residual;
+  const float* up_prev; int up_H, up_W;     // fused FPN merge: y += bilinear_up(up_prev [n, up_H, up_W, Cout])
   float* out_f32; int8_t* out_spike;
   int M_total;          // n * Ho * Wo
   int M_img;            // Ho * Wo
@@ -163,16 +164,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-// NI-LIF level of y as the low byte of the returned word: round-half-even by the 2^23 trick (== rintf on [0, d_max])
-__device__ __forceinline__ uint32_t level_bits(float y, float d_max) {
-  return __float_as_uint(fminf(fmaxf(y, 0.f), d_max) + 8388608.f);
-}
-__device__ __forceinline__ uint32_t pack_levels(float a, float b, float c, float d, float d_max) {
-  const uint32_t lo = __byte_perm(level_bits(a, d_max), level_bits(b, d_max), 0x0040);
-  const uint32_t hi = __byte_perm(level_bits(c, d_max), level_bits(d, d_max), 0x0040);
-  return __byte_perm(lo, hi, 0x5410);
-}
-
 // Stage the per-channel epilogue constants of one channel tile: ss[0..2][64] = scale * 128^(pieces-1-plane), ss[3][64] = shift.
 __device__ __forceinline__ void stage_affine(const TcParams& p, float* ss, int co_base, int img, int et) {
   for (; et < 4 * TC_BN; et += 32 * TC_EPI_WARPS) {
@@ -349,6 +340,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         m = (int64_t)tile_m * TC_BM + r;
         if (m >= p.M_total) m = -1;
       }
+      // fused FPN merge: source coordinates of this row in the coarser map (upsample_bilinear2d, align_corners=False)
+      const float* up00 = nullptr; const float* up01 = nullptr; const float* up10 = nullptr; const float* up11 = nullptr;
+      float up_hx = 0.f, up_lx = 0.f, up_hy = 0.f, up_ly = 0.f;
+      if (p.up_prev && m >= 0) {
+        const int im = (int)(m / p.M_img), rr = (int)(m % p.M_img);
+        const int yo = rr / p.Wo, xo = rr % p.Wo;
+        float sy = ((float)p.up_H / (float)p.Ho) * ((float)yo + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+        float sx = ((float)p.up_W / (float)p.Wo) * ((float)xo + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < p.up_H - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_W - 1 ? 1 : 0);
+        up_ly = sy - (float)y0; up_lx = sx - (float)x0; up_hy = 1.f - up_ly; up_hx = 1.f - up_lx;
+        const float* pb = p.up_prev + (int64_t)im * p.up_H * p.up_W * p.Cout;
+        up00 = pb + ((int64_t)y0 * p.up_W + x0) * p.Cout; up01 = pb + ((int64_t)y0 * p.up_W + x1) * p.Cout;
+        up10 = pb + ((int64_t)y1 * p.up_W + x0) * p.Cout; up11 = pb + ((int64_t)y1 * p.up_W + x1) * p.Cout;
+      }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
@@ -403,6 +409,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if (j < nvalid) y[j] += p.residual[row_off + j];
           }
         }
+        if (p.up_prev) {                                   // host guarantees Cout % 16 == 0 here
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 p00 = __ldg(reinterpret_cast<const float4*>(up00 + co0) + q), p01 = __ldg(reinterpret_cast<const float4*>(up01 + co0) + q);
+            const float4 p10 = __ldg(reinterpret_cast<const float4*>(up10 + co0) + q), p11 = __ldg(reinterpret_cast<const float4*>(up11 + co0) + q);
+            // ATen: hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11), then cur + up
+            y[4 * q] = y[4 * q] + (up_hy * (up_hx * p00.x + up_lx * p01.x) + up_ly * (up_hx * p10.x + up_lx * p11.x));
+            y[4 * q + 1] = y[4 * q + 1] + (up_hy * (up_hx * p00.y + up_lx * p01.y) + up_ly * (up_hx * p10.y + up_lx * p11.y));
+            y[4 * q + 2] = y[4 * q + 2] + (up_hy * (up_hx * p00.z + up_lx * p01.z) + up_ly * (up_hx * p10.z + up_lx * p11.z));
+            y[4 * q + 3] = y[4 * q + 3] + (up_hy * (up_hx * p00.w + up_lx * p01.w) + up_ly * (up_hx * p10.w + up_lx * p11.w));
+          }
+        }
         if (!p.out_transposed) {
           if (p.out_f32) {
             if (full16) {
@@ -419,7 +437,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (nvalid == 16 && (p.Cout & 15) == 0) {
               uint32_t w[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) w[q] = pack_levels(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3], p.d_max);
+              for (int q = 0; q < 4; ++q) w[q] = pack_levels4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3], p.d_max);
               *reinterpret_cast<uint4*>(p.out_spike + row_off) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
 #pragma unroll
@@ -493,6 +511,11 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   const int Ho = (a->H + 2 * a->pad - a->KH) / a->stride + 1, Wo = (a->W + 2 * a->pad - a->KW) / a->stride + 1;
   S2F_REQUIRE(Ho > 0 && Wo > 0, "gemm_i8_tc: empty output");
   p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out_f32 = a->out_f32; p.out_spike = a->out_spike;
+  p.up_prev = a->up_prev; p.up_H = a->up_H; p.up_W = a->up_W;
+  if (a->up_prev) {
+    S2F_REQUIRE(a->up_H > 0 && a->up_W > 0 && a->Cout % 16 == 0 && !a->out_transposed && (reinterpret_cast<uintptr_t>(a->up_prev) & 15) == 0,
+                "gemm_i8_tc: fused upsample needs Cout % 16 == 0, 16-byte aligned up_prev and a non-transposed output");
+  }
   p.Ho = Ho; p.Wo = Wo; p.Cout = a->Cout; p.M_img = Ho * Wo; p.M_total = a->n * Ho * Wo;
   p.taps_w = a->KW; p.taps = a->KH * a->KW; p.stride = a->stride; p.pad = a->pad;
   p.bk = tc_bk(a->Cin); p.cin_chunks = (a->Cin + p.bk - 1) / p.bk;

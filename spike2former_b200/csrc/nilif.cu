@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d) {
 // Vector kernel: N % 16 == 0, C % 4 == 0 (when affine), residual_period % 4 == 0.
 // Each thread owns 16 consecutive neurons: 4 x LDG.128 per step, 1 x STG.128 per step.
 template <bool AFFINE, bool RESID, bool STATE, bool YNORM, bool TIES>
-__global__ void __launch_bounds__(256) nilif_vec_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, 3) nilif_vec_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift,
                                                         const float* __restrict__ residual, int64_t res_period,
                                                         const float* __restrict__ v_in, float* __restrict__ v_out,
@@ -40,6 +40,11 @@ __global__ void __launch_bounds__(256) nilif_vec_kernel(const float* __restrict_
                                                         unsigned long long* __restrict__ ties) {
   const int64_t nchunks = N >> 4;
   unsigned int my_ties = 0;
+  // When the grid stride is a multiple of the channel count, a thread sees the same 16 channels in every iteration:
+  // the per-channel scale / shift are then loaded once (they would otherwise triple the kernel's L1 wavefronts).
+  const bool hoisted = AFFINE && (((int64_t)gridDim.x * blockDim.x * 16) % C == 0);
+  bool have_affine = false;
+  float sc[16], sh[16];
   for (int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; chunk < nchunks;
        chunk += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i0 = chunk << 4;
@@ -54,16 +59,18 @@ __global__ void __launch_bounds__(256) nilif_vec_kernel(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
     }
-    float sc[16], sh[16];
-    if (AFFINE) {
+    if (AFFINE && !(hoisted && have_affine)) {
+      const int c0 = (int)(i0 % C);                      // one 64-bit modulo per 16 neurons
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int c = (int)((i0 + 4 * j) % C);
+        int c = c0 + 4 * j;
+        if (C >= 16) { if (c >= C) c -= C; } else { c %= C; }
         float4 a = __ldg(reinterpret_cast<const float4*>(scale + c));
         float4 b = __ldg(reinterpret_cast<const float4*>(shift + c));
         sc[4 * j] = a.x; sc[4 * j + 1] = a.y; sc[4 * j + 2] = a.z; sc[4 * j + 3] = a.w;
         sh[4 * j] = b.x; sh[4 * j + 1] = b.y; sh[4 * j + 2] = b.z; sh[4 * j + 3] = b.w;
       }
+      have_affine = true;
     }
     for (int t = 0; t < T; ++t) {
       const int64_t base = (int64_t)t * N + i0;
@@ -87,18 +94,21 @@ __global__ void __launch_bounds__(256) nilif_vec_kernel(const float* __restrict_
         }
       }
       float s[16];
+      uint32_t lb[16];                                   // 0x4B000000 | level: rounding by the 2^23 trick (no FRND / F2I)
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         v[j] += u[j];
         if (TIES) my_ties += is_tie(v[j], d_max) ? 1u : 0u;
-        s[j] = spike_level(v[j], d_max);
+        const float t = fminf(fmaxf(v[j], 0.f), d_max) + 8388608.f;
+        lb[j] = __float_as_uint(t);
+        s[j] = t - 8388608.f;                            // == rintf(clamp(v, 0, d_max))
         v[j] -= s[j];
       }
       int4 o;
-      o.x = (int)pack4(s[0], s[1], s[2], s[3]);
-      o.y = (int)pack4(s[4], s[5], s[6], s[7]);
-      o.z = (int)pack4(s[8], s[9], s[10], s[11]);
-      o.w = (int)pack4(s[12], s[13], s[14], s[15]);
+      o.x = (int)__byte_perm(__byte_perm(lb[0], lb[1], 0x0040), __byte_perm(lb[2], lb[3], 0x0040), 0x5410);
+      o.y = (int)__byte_perm(__byte_perm(lb[4], lb[5], 0x0040), __byte_perm(lb[6], lb[7], 0x0040), 0x5410);
+      o.z = (int)__byte_perm(__byte_perm(lb[8], lb[9], 0x0040), __byte_perm(lb[10], lb[11], 0x0040), 0x5410);
+      o.w = (int)__byte_perm(__byte_perm(lb[12], lb[13], 0x0040), __byte_perm(lb[14], lb[15], 0x0040), 0x5410);
       stg_stream(reinterpret_cast<int4*>(levels + base), o);
       if (YNORM) {
 #pragma unroll

@@ -102,9 +102,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
       const int64_t o = o0 + (int64_t)t * C;
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
       if (out_spike) {
-        const uint32_t pk = (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
-                            ((uint32_t)(int)spike_level(y[2], d_max) << 16) |
-                            ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+        const uint32_t pk = pack_levels4(y[0], y[1], y[2], y[3], d_max);
         *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
       }
     }
@@ -216,9 +214,7 @@ __global__ void __launch_bounds__(256) upsample_add_lif_kernel(const float* __re
     y[3] = cv.w + (hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w));
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
     if (out_spike) {
-      const uint32_t pk = (uint32_t)(int)spike_level(y[0], d_max) | ((uint32_t)(int)spike_level(y[1], d_max) << 8) |
-                          ((uint32_t)(int)spike_level(y[2], d_max) << 16) |
-                          ((uint32_t)(int)spike_level(y[3], d_max) << 24);
+      const uint32_t pk = pack_levels4(y[0], y[1], y[2], y[3], d_max);
       *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
     }
   }
@@ -241,8 +237,7 @@ __global__ void __launch_bounds__(256) affine_add_lif_kernel(const float* __rest
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + i) = v;
     if (out_spike) {
-      const uint32_t pk = (uint32_t)(int)spike_level(v.x, d_max) | ((uint32_t)(int)spike_level(v.y, d_max) << 8) |
-                          ((uint32_t)(int)spike_level(v.z, d_max) << 16) | ((uint32_t)(int)spike_level(v.w, d_max) << 24);
+      const uint32_t pk = pack_levels4(v.x, v.y, v.z, v.w, d_max);
       *reinterpret_cast<uint32_t*>(out_spike + i) = pk;
     }
   }

@@ -9,6 +9,7 @@
 // per image by tail_prep_kernel and copied to shared memory once per CTA.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -250,24 +251,26 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Exact x2 upsampling (H == 2h, W == 2w; every Spike2Former config): warp-specialised, pipelined version.
 //
-//   warps 0..7   producers: build the A operand (sigmoid of the bilinear x2 upsample, fp16 hi + lo) of a 4 x 32 pixel
+//   warps 0..6   producers: build the A operand (sigmoid of the bilinear x2 upsample, fp16 hi + lo) of a 4 x 32 pixel
 //                tile.  One task = one low-resolution cell (its 4 corners are shared by a 2 x 2 block of output pixels)
 //                x 8 queries: 8 x LDG.128, 32 sigmoids, 8 x STS.128 straight into the SWIZZLE_128B K-major image.
-//   warp  8      one thread issues tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo) into one of two TMEM accumulators.
-//   warps 9..12  epilogue: tcgen05.ld the other accumulator, store the NCHW logits (128 B per class per warp) and/or the
+//   warp  7      one thread issues tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo) into one of two TMEM accumulators.
+//   warps 8..15  epilogue: tcgen05.ld the other accumulator, store the NCHW logits (128 B per class per warp) and/or the
 //                fused argmax label.
 // Two A stages in shared memory and two accumulators in TMEM keep the three roles running on different tiles.
 // Tile geometry: output rows Y = 4*ty - 1 + {0..3} (cell rows kc = 2*ty - 1, 2*ty; rows are offset by one so that the two
 // rows of a cell never straddle tiles), columns X = 32*tx + {0..31} (cells jc = 16*tx - 1 .. 16*tx + 15; the first and
 // last cell contribute one column each).  Clamped corner indices reproduce upsample_bilinear2d's border rule.
-constexpr int T2_PROD_WARPS = 8;
-constexpr int T2_THREADS = (T2_PROD_WARPS + 1 + 4) * 32;    // 416
+constexpr int T2_PROD_WARPS = 7;                            // 224 threads: 442 tasks per tile = two balanced rounds; 16 warps total -> 128 registers
+constexpr int T2_EPI_WARPS = 8;                             // two per TMEM lane quadrant, half of the classes each
+constexpr int T2_THREADS = (T2_PROD_WARPS + 1 + T2_EPI_WARPS) * 32;    // 544
 constexpr int T2_CELLS_X = 17;
 constexpr int T2_ACC_COLS = 256;                            // TMEM columns per accumulator buffer
 
 struct Tail2P {
   const float* mask_pred; const uint8_t* bpack; float* logits; uint8_t* labels;
   int Q, K, Np, h, w, H, W, tiles_x, tiles_y, ctas_per_img;
+  int debug;      // S2F_TAIL_DEBUG (experiments): 1 epilogue idle, 2 no MMA, 4 producers idle
 };
 
 __device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity) {
@@ -298,7 +301,15 @@ __device__ __forceinline__ bool t2_elect_one() {
       "}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ float t2_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) with the two SFU approximations and no range fix-ups: ex2 saturates to 0 / +inf
+// and rcp(+inf) = 0, which are the correct limits.  Branch-free on purpose: a per-element conditional around it makes
+// the compiler serialise 32 dependent MUFU chains per task.
+__device__ __forceinline__ float t2_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 
 __device__ __forceinline__ uint32_t t2_pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -331,6 +342,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * a_stage);
   uint64_t* a_full = bars, *a_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_best = reinterpret_cast<float*>(tmem_slot + 4);          // [2 stages][128] partial argmax of the upper class half
+  int* s_bidx = reinterpret_cast<int*>(s_best + 2 * TL_BM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.y;
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&a_full[s])), "r"(T2_PROD_WARPS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&a_empty[s])), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&t_full[s])), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&t_empty[s])), "r"(4));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&t_empty[s])), "r"(T2_EPI_WARPS));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -365,43 +378,55 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
 
   if (warp < T2_PROD_WARPS) {
     // ================================================================== producers
-    const int ptid = threadIdx.x;                                  // 0..255
+    const int ptid = threadIdx.x;                                  // 0 .. 32*T2_PROD_WARPS - 1
+    constexpr int NPROD = T2_PROD_WARPS * 32;
     const int ngroups = (p.Q + 7) >> 3;
     const int ntasks = 2 * T2_CELLS_X * ngroups;
     const float* mp = p.mask_pred + (int64_t)img * p.h * p.w * p.Q;
     const bool vec = (p.Q & 3) == 0;
+    float c[4][8];                                                 // the four corners of the current task, 8 queries each
+    // corner loads of task t of `tile` (issued early: they are in flight while the previous task is being finished)
+    auto load_task = [&](int tile, int t) {
+      const int ty = tile / p.tiles_x, tx = tile % p.tiles_x;
+      const int g = t % ngroups, cell = t / ngroups;
+      const int cx = cell % T2_CELLS_X, kr = cell / T2_CELLS_X;
+      const int jc = 16 * tx - 1 + cx, kc = 2 * ty - 1 + kr;
+      const int x0 = min(max(jc, 0), p.w - 1), x1 = min(max(jc + 1, 0), p.w - 1);
+      const int y0 = min(max(kc, 0), p.h - 1), y1 = min(max(kc + 1, 0), p.h - 1);
+      const int q0 = g * 8;
+      const float* src[4] = {mp + ((int64_t)y0 * p.w + x0) * p.Q + q0, mp + ((int64_t)y0 * p.w + x1) * p.Q + q0,
+                             mp + ((int64_t)y1 * p.w + x0) * p.Q + q0, mp + ((int64_t)y1 * p.w + x1) * p.Q + q0};
+      if (vec) {
+        const bool second = q0 + 4 < p.Q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src[k]));
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (second) b = __ldg(reinterpret_cast<const float4*>(src[k]) + 1);
+          c[k][0] = a.x; c[k][1] = a.y; c[k][2] = a.z; c[k][3] = a.w;
+          c[k][4] = b.x; c[k][5] = b.y; c[k][6] = b.z; c[k][7] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c[k][j] = (q0 + j < p.Q) ? __ldg(src[k] + j) : 0.f;
+      }
+    };
+    if (blockIdx.x < tiles_img && ptid < ntasks) load_task(blockIdx.x, ptid);
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
       const int s = it & 1;
       t2_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
       uint8_t* dstA = sA + s * a_stage;
-      const int ty = tile / p.tiles_x, tx = tile % p.tiles_x;
-      for (int t = ptid; t < ntasks; t += T2_PROD_WARPS * 32) {
+      if (!(p.debug & 4))
+      for (int t = ptid; t < ntasks; t += NPROD) {
         const int g = t % ngroups, cell = t / ngroups;
         const int cx = cell % T2_CELLS_X, kr = cell / T2_CELLS_X;
-        const int jc = 16 * tx - 1 + cx, kc = 2 * ty - 1 + kr;
-        const int x0 = min(max(jc, 0), p.w - 1), x1 = min(max(jc + 1, 0), p.w - 1);
-        const int y0 = min(max(kc, 0), p.h - 1), y1 = min(max(kc + 1, 0), p.h - 1);
         const int q0 = g * 8;
-        float c[4][8];
-        const float* src[4] = {mp + ((int64_t)y0 * p.w + x0) * p.Q + q0, mp + ((int64_t)y0 * p.w + x1) * p.Q + q0,
-                               mp + ((int64_t)y1 * p.w + x0) * p.Q + q0, mp + ((int64_t)y1 * p.w + x1) * p.Q + q0};
-        if (vec) {
-          const bool second = q0 + 4 < p.Q;
+        float qmask[8];                                        // 1 for real queries, 0 for the padding of the last group
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src[k]));
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (second) b = __ldg(reinterpret_cast<const float4*>(src[k]) + 1);
-            c[k][0] = a.x; c[k][1] = a.y; c[k][2] = a.z; c[k][3] = a.w;
-            c[k][4] = b.x; c[k][5] = b.y; c[k][6] = b.z; c[k][7] = b.w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[k][j] = (q0 + j < p.Q) ? __ldg(src[k] + j) : 0.f;
-        }
+        for (int j = 0; j < 8; ++j) qmask[j] = (q0 + j < p.Q) ? 1.f : 0.f;
         // horizontal interpolation of both corner rows for the two output columns of the cell
         float top[2][8], bot[2][8];
 #pragma unroll
@@ -411,6 +436,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
           bot[0][j] = 0.75f * c[2][j] + 0.25f * c[3][j];
           bot[1][j] = 0.25f * c[2][j] + 0.75f * c[3][j];
         }
+        // c is dead: start the loads of this thread's next task (same tile or the CTA's next tile)
+        if (t + NPROD < ntasks) load_task(tile, t + NPROD);
+        else if (tile + p.ctas_per_img < tiles_img && ptid < ntasks) load_task(tile + p.ctas_per_img, ptid);
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
           const int ox = 2 * cx - 1 + dx;
@@ -420,7 +448,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
             const float wt = dy ? 0.25f : 0.75f, wb = dy ? 0.75f : 0.25f;
             float sv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sv[j] = (q0 + j < p.Q) ? t2_sigmoid(wt * top[dx][j] + wb * bot[dx][j]) : 0.f;
+            for (int j = 0; j < 8; ++j) sv[j] = t2_sigmoid(wt * top[dx][j] + wb * bot[dx][j]) * qmask[j];
             t2_store8(dstA, a_plane, (2 * kr + dy) * 32 + ox, g, sv);
           }
         }
@@ -447,7 +475,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
       if (t2_elect_one()) {
         uint32_t acc = 0;
 #pragma unroll 1
-        for (int combo = 0; combo < 3; ++combo) {
+        for (int combo = (p.debug & 2) ? 3 : 0; combo < 3; ++combo) {
           const uint32_t abase = combo == 1 ? a_lo : a_hi, bbase = combo == 2 ? b_lo : b_hi;
           for (int ks = 0; ks < ksteps; ++ks) {
             const int atom = ks >> 2, k = ks & 3;
@@ -464,7 +492,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
     }
   } else {
     // ================================================================== epilogue
-    const int quad = warp & 3;                                     // TMEM lane quadrant == output row of the tile
+    // warp -> (TMEM lane quadrant = output row of the tile, class half).  A single warp can only issue an instruction
+    // every few cycles, so the 150 stores per pixel are spread over two warps per quadrant.
+    const int quad = warp & 3;
+    const int half = (warp - (T2_PROD_WARPS + 1)) >> 2;
+    const int ncol16 = p.Np / 16;
+    const int cb_begin = half ? (ncol16 + 1) / 2 : 0, cb_end = half ? ncol16 : (ncol16 + 1) / 2;
+    const uint32_t HW4 = (uint32_t)HW;
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
       const int s = it & 1;
@@ -477,26 +511,42 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * T2_ACC_COLS);
       float best = -INFINITY;
       int best_c = 0;
-      float* lg = p.logits ? p.logits + (int64_t)img * p.K * HW + pix : nullptr;
-      for (int c0 = 0; c0 < p.Np; c0 += 32) {
+      float* lg = (p.logits && ok) ? p.logits + (int64_t)img * p.K * HW + pix : nullptr;
+      for (int cb = (p.debug & 1) ? cb_end : cb_begin; cb < cb_end; cb += 2) {
         uint32_t v[32];
-        tl_ld16(trow + c0, v);
-        const bool two = c0 + 16 < p.Np;                            // warp-uniform
-        if (two) tl_ld16(trow + c0 + 16, v + 16);
+        tl_ld16(trow + cb * 16, v);
+        const bool two = cb + 1 < cb_end;                           // warp-uniform
+        if (two) tl_ld16(trow + cb * 16 + 16, v + 16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (ok) {
+        const int c0 = cb * 16;
+        const int nv = min(two ? 32 : 16, p.K - c0);               // valid classes among the loaded columns
+        if (lg) {
+          if (nv == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lg[(uint32_t)(c0 + j) * HW4] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) lg[(uint32_t)(c0 + j) * HW4] = __uint_as_float(v[j]);
+          }
+        }
+        if (p.labels) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c < p.K && (j < 16 || two)) {
-              const float y = __uint_as_float(v[j]);
-              if (lg) lg[(int64_t)c * HW] = y;
-              if (y > best) { best = y; best_c = c; }
-            }
+            const float y = __uint_as_float(v[j]);
+            if (j < nv && y > best) { best = y; best_c = c0 + j; }
           }
         }
       }
-      if (p.labels && ok) p.labels[(int64_t)img * HW + pix] = (uint8_t)best_c;      // first maximum wins, as torch.argmax
+      if (p.labels) {                                               // combine the two class halves: first maximum wins
+        const int r = quad * 32 + lane;
+        if (half) { s_best[s * TL_BM + r] = best; s_bidx[s * TL_BM + r] = best_c; }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        if (!half && ok) {
+          const float b1 = s_best[s * TL_BM + r];
+          p.labels[(int64_t)img * HW + pix] = (uint8_t)((b1 > best) ? s_bidx[s * TL_BM + r] : best_c);
+        }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) t2_arrive(&t_empty[s]);
@@ -537,7 +587,7 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
   tail_prep_kernel<<<n, 256, prep_sm, st>>>(cls, reinterpret_cast<uint8_t*>(ws), Q, K, Np);
   int rc = check_launch("tail_prep_kernel");
   if (rc) return rc;
-  const size_t smem2 = (size_t)2 * 2 * Np * 128 + 2 * 2 * 2 * TL_BM * 128 + 128 + 1024;
+  const size_t smem2 = (size_t)2 * 2 * Np * 128 + 2 * 2 * 2 * TL_BM * 128 + 128 + 4 * TL_BM * 4 + 1024;
   if (H == 2 * h && W == 2 * w && smem2 <= 227 * 1024) {          // K <= 192 classes: both A stages + B fit
     Tail2P q;
     q.mask_pred = mask_pred; q.bpack = reinterpret_cast<const uint8_t*>(ws); q.logits = logits; q.labels = labels;
@@ -547,6 +597,7 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
     int per_img = n >= 148 ? 1 : 148 / n;
     if (per_img > tiles_img) per_img = tiles_img;
     q.ctas_per_img = per_img;
+    { const char* dbg = getenv("S2F_TAIL_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
     static bool attr2 = false;
     if (!attr2) {
       cudaError_t e = cudaFuncSetAttribute(tail_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

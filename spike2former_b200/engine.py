@@ -40,12 +40,14 @@ class Gemm:
             packed, rowscale = ops.pack_weights_i8(w2d.to(torch.float32), k * k, self.cin, TC_PIECES)
             self.tc = (packed.to(device), fold.f32(scale.double().cpu() * rowscale.double(), device))
 
-    def __call__(self, a, n, H, W, residual=None, f32=False, spike=False, transposed=False, a_scale=INV, **kw):
+    def __call__(self, a, n, H, W, residual=None, f32=False, spike=False, transposed=False, a_scale=INV, up_prev=None, **kw):
         if self.tc is not None and a.dtype == torch.int8 and not kw and n * H * W >= TC_MIN_ROWS:
             sc = self.tc[1] if a_scale == 1.0 else self._scaled(a_scale)
             return ops.gemm_tc(a, self.tc[0], n=n, H=H, W=W, Cin=self.cin, Cout=self.cout, scale=sc, shift=self.shift,
                                k=self.k, stride=self.stride, pad=self.pad, pieces=TC_PIECES, residual=residual,
-                               want_f32=f32, want_spike=spike, transposed=transposed)
+                               want_f32=f32, want_spike=spike, transposed=transposed, up_prev=up_prev)
+        if up_prev is not None:
+            raise RuntimeError("fused FPN merge needs the tensor-core path")
         return self._simt(a, n, H, W, residual, f32, spike, transposed, a_scale, **kw)
 
     def _scaled(self, a_scale):
@@ -491,10 +493,16 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True):
         s_i, sp_i = feats[i]
         _, h, w, _ = s_i.shape
         sp_i = pr.spike(pd + f"lateral_convs_spike.{i}", sp_i)
-        cur, _ = L[f"lateral.{i}"](sp_i, n, h, w, f32=True)
-        ys, yf = ops.upsample_add_lif(cur, y, n=n, H=h, W=w, Hp=hp, Wp=wp, C_=C, want_f32=pr.active)
-        if pr.active:
-            pr.real(pd + f"output_convs_spike.{i}", yf)
+        lat = L[f"lateral.{i}"]
+        if not pr.active and lat.tc is not None and n * h * w >= TC_MIN_ROWS and C % 16 == 0:
+            # lateral 1x1 + BN, bilinear upsample of the coarser level, add and NI-LIF in one launch: the fp32 lateral
+            # map (1 GB at batch 16 for the 256^2 level) is never written
+            _, ys = lat(sp_i, n, h, w, spike=True, up_prev=y)
+        else:
+            cur, _ = lat(sp_i, n, h, w, f32=True)
+            ys, yf = ops.upsample_add_lif(cur, y, n=n, H=h, W=w, Hp=hp, Wp=wp, C_=C, want_f32=pr.active)
+            if pr.active:
+                pr.real(pd + f"output_convs_spike.{i}", yf)
         ys = pr.spike(pd + f"output_convs_spike.{i}", ys)
         # the finest level only feeds mask_feature_spike: its fp32 map (1 GB at batch 16) is not materialised
         y, ysp = L[f"output.{i}"](ys, n, h, w, f32=(i > 0 or pr.active), spike=(i == 0))

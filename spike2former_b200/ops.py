@@ -212,7 +212,7 @@ def pack_rows_i8_device(w, *, n_img, rows_per_img, K, pieces=3, post_scale=1.0, 
 
 
 def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad=0, pieces=3, residual=None,
-            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX, per_image=False):
+            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX, per_image=False, up_prev=None):
     """tcgen05 spike GEMM.  a: int8 levels channels-last; `scale` already contains rowscale * 1/8."""
     if a.dtype != torch.int8:
         raise S2FError("gemm_tc: a must be int8 levels")
@@ -230,6 +230,10 @@ def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad
     args.KH = args.KW = k
     args.stride, args.pad, args.pieces, args.d_max = stride, pad, pieces, float(d_max)
     args.per_image_weights = int(per_image)
+    if up_prev is not None:                      # fused top-down FPN merge: y += bilinear_up(up_prev)
+        if up_prev.dim() != 4 or up_prev.shape[0] != n or up_prev.shape[3] != Cout:
+            raise S2FError("gemm_tc: up_prev must be fp32 [n, Hp, Wp, Cout]")
+        args.up_prev, args.up_H, args.up_W = _ptr(up_prev, torch.float32, "up_prev"), int(up_prev.shape[1]), int(up_prev.shape[2])
     e0 = _p0()
     check(_lib.lib().s2f_gemm_i8_tc(C.byref(args), _stream()), "s2f_gemm_i8_tc")
     _p1(e0, "gemm_tc", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces,

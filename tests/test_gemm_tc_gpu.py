@@ -93,3 +93,27 @@ def test_gemm_tc_matches_cuda_core_kernel_bitwise_spikes():
     frac = (f_cc - f_cc.floor() - 0.5).abs()
     assert int((diff & (frac > 1e-4)).sum()) == 0
     assert int(diff.sum()) <= 1e-4 * diff.numel()
+
+
+@pytest.mark.parametrize("cin,H,W", [(32, 32, 32), (64, 16, 24), (128, 8, 8)])
+def test_gemm_tc_fused_fpn_merge_matches_separate_kernels(cin, H, W):
+    """lateral 1x1 + BN + bilinear_up(prev) + NI-LIF in one launch == gemm_tc -> s2f_upsample_add_lif up to the
+    compiler's FMA contraction of the interpolation (pixel_decoder.py:451-462)."""
+    g = torch.Generator().manual_seed(7)
+    n, cout = 2, 256
+    a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8).cuda()
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) + 1
+    prev = (torch.randn(n, H // 2, W // 2, cout, generator=g) * 2).cuda()
+    packed, rowscale = ops.pack_weights_i8(w, 1, cin, 3)
+    kw = dict(n=n, H=H, W=W, Cin=cin, Cout=cout, scale=(sc * rowscale / 8).cuda(), shift=sh.cuda())
+    cur, _ = ops.gemm_tc(a, packed.cuda(), want_f32=True, **kw)
+    want_s, want_f = ops.upsample_add_lif(cur, prev, n=n, H=H, W=W, Hp=H // 2, Wp=W // 2, C_=cout, want_f32=True)
+    got_f, got_s = ops.gemm_tc(a, packed.cuda(), want_f32=True, want_spike=True, up_prev=prev, **kw)
+    assert (got_f - want_f).abs().max().item() < 2e-6 * max(1.0, want_f.abs().max().item())
+    assert torch.equal(got_s, torch.round(torch.clamp(got_f, 0, 8)).to(torch.int8))      # spikes of the kernel's own fp32
+    flips = got_s != want_s
+    assert int(flips.sum()) <= 1e-4 * flips.numel()
+    assert int((flips & ((want_f - want_f.floor() - 0.5).abs() > 1e-4)).sum()) == 0      # only at rounding ties
+    up = F.interpolate(prev.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert (got_f - (cur + up)).abs().max().item() < 1e-5
