@@ -32,6 +32,7 @@ import torch  # noqa: E402
 H = W = 512
 WORKLOAD = "Spike2Former SDTv2 + DCN pixel decoder, ADE20K-shape 512x512 inference (150 classes, 100 queries)"
 ALG_GFLOP_PER_IMG = 131.0      # 142 GFLOP minus the six discarded mask einsums (inference uses [-1])
+CITY_H, CITY_W = 1024, 2048    # BASELINE.json config 4: Cityscapes shape (19 classes), reported as a secondary number
 
 
 def peaks():
@@ -108,14 +109,87 @@ def cpu_reference_run(steps, warmup):
                        f"{cores} threads, after {warmup} warm-up"), dt / steps * 1e3
 
 
+def kernel_microbench(dev):
+    """BASELINE.json config 2 on one GPU: fused NI-LIF (B=64, N=1024, C=512, T=1) and the MLP spike GEMM 512->2048."""
+    from spike2former_b200 import ops
+
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.view(torch.int64).sum()                  # evict the working set, leave clean lines in L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(400000)                      # the launch is queued before the GPU reaches e0
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts) * 1e-3
+
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(64, 1024, 512, generator=g) * 12 - 2).to(dev)
+    lv = torch.empty(x.shape, dtype=torch.int8, device=dev)
+    t = timed(lambda: ops.nilif(x, out=lv))
+    nilif = dict(workload="NI-LIF B=64 N=1024 C=512 T=1 D=8", us=t * 1e6, gbs=x.numel() * 5 / t / 1e9,
+                 algorithmic_bytes=x.numel() * 5)
+    n, Hh, Ww, cin, cout = 64, 32, 32, 512, 2048
+    a = torch.randint(0, 9, (n, Hh, Ww, cin), generator=g, dtype=torch.int8).to(dev)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    packed, rowscale = ops.pack_weights_i8(w, 1, cin, 3)
+    packed, sc, sh = packed.to(dev), (rowscale / 8).to(dev), torch.zeros(cout, device=dev)
+    t = timed(lambda: ops.gemm_tc(a, packed, n=n, H=Hh, W=Ww, Cin=cin, Cout=cout, scale=sc, shift=sh, pieces=3,
+                                  want_spike=True))
+    gemm = dict(workload="spike GEMM fc1 512->2048, 65536 tokens, int8 spikes x 3 int8 weight planes, NI-LIF epilogue",
+                us=t * 1e6, tflops_algorithmic=2.0 * n * Hh * Ww * cin * cout / t / 1e12)
+    return dict(nilif_cfg2=nilif, gemm_cfg2=gemm)
+
+
+def cityscapes_throughput(dev, world, dist, B, steps=4):
+    """Secondary number (BASELINE.json config 4): Cityscapes config at 1024x2048, batch-sharded, inputs resident."""
+    import spike2former_b200 as s2f
+    from spike2former_b200 import synth
+
+    cfg = s2f.configs.cityscapes()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint("cityscapes", cfg), strict=True)
+    seg = seg.to(dev)
+    g = torch.Generator().manual_seed(7)
+    xs = [torch.randn(B, 3, CITY_H, CITY_W, generator=g).to(dev) for _ in range(2)]
+    with torch.no_grad():
+        for i in range(3):
+            seg.predict_labels(xs[i & 1])
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            seg.predict_labels(xs[i & 1])
+        e1.record()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    del seg, xs
+    torch.cuda.empty_cache()
+    return dict(workload="Spike2Former SDTv2 + DCN pixel decoder, Cityscapes-shape 1024x2048 (19 classes), fused argmax",
+                batch_per_gpu=B, images_per_second=world * B / (ms / 1e3), ms_per_step=ms)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--city-batch", type=int, default=4, help="images per GPU for the 1024x2048 secondary number (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,7 +231,6 @@ def main():
     g = torch.Generator().manual_seed(1000 + rank)   # working set (GBs of activations) thrashes L2 anyway
     host = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(NBUF)]
     devin = [h.to(dev) for h in host]
-    host_out = torch.empty(B, H, W, dtype=torch.uint8).pin_memory()
 
     def barrier():
         if dist is not None:
@@ -168,13 +241,27 @@ def main():
         with torch.no_grad():
             return seg.encode_decode(devin[i % NBUF])
 
+    # end-to-end: pinned host batch -> H2D (copy stream, double buffered so the copy of step i+1 overlaps the forward of
+    # step i) -> forward with fused argmax -> D2H of the uint8 label map; all of it inside the timed region
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty(B, 3, H, W, device=dev) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    host_outs = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
     def step_e2e(i):
+        j = i & 1
+        main = torch.cuda.current_stream()
         with torch.no_grad():
-            x = host[i % NBUF].to(dev, non_blocking=True)
-            labels = seg.predict_labels(x)
-            host_out.copy_(labels, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return host_out
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[j])
+                stage[j].copy_(host[i % NBUF], non_blocking=True)
+                ev_ready[j].record(copy_stream)
+            main.wait_event(ev_ready[j])
+            labels = seg.predict_labels(stage[j])
+            ev_free[j].record(main)
+            host_outs[j].copy_(labels, non_blocking=True)
+        return host_outs[j]
 
     # ------------------------------------------------------------------ device-resident timing
     for i in range(args.warmup):
@@ -201,14 +288,14 @@ def main():
     value = world * B * args.steps / (ms_max / 1e3)
 
     # ------------------------------------------------------------------ end-to-end (host buffers) timing
-    for i in range(2):
+    for i in range(4):
         step_e2e(i)
     barrier()
     e0.record()
     for i in range(args.steps):
         step_e2e(i)
     e1.record()
-    barrier()
+    barrier()                                  # every H2D, forward and D2H of the timed steps has completed here
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -216,6 +303,9 @@ def main():
 
     # ------------------------------------------------------------------ roofline of the dominant kernel class
     roof = engine.profile_dominant(seg, devin[0], steps=min(args.steps, 3)) if rank == 0 else None
+
+    micro = kernel_microbench(dev) if rank == 0 else None
+    city = cityscapes_throughput(dev, world, dist, args.city_batch) if args.city_batch > 0 else None
 
     if rank != 0:
         if dist is not None:
@@ -243,6 +333,15 @@ def main():
                            "share_of_step": roof["share"], "launches_per_step": roof["launches"],
                            "peak_source": pk["src"] + (" bf16 sustained (inside a long step)" if roof["bound"] == "tensor" else " copy"),
                            "per_class_ms": roof["per_class_ms"]}
+    if city:
+        out["cityscapes_1024x2048"] = city
+    if micro:
+        micro["nilif_cfg2"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["gbs"] / pk["hbm"]
+        micro["nilif_cfg2"]["frac_of_8tbs_nominal"] = micro["nilif_cfg2"]["gbs"] / 8000.0
+        # int8 tensor peak is taken as 2x the measured bf16 peak; the kernel executes 3 int8 MACs (digit planes) per
+        # algorithmic MAC, so utilisation of the int8 pipe = 3 * algorithmic / (2 * bf16 peak)
+        micro["gemm_cfg2"]["int8_pipe_utilisation_est"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] / (2.0 * pk["bf16_sustained"])
+        out["kernels"] = micro
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference_run(6, 1)
         out["cpu_baseline"] = cb

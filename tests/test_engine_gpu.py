@@ -76,6 +76,22 @@ def test_ade20k_teacher_forced_512():
     assert rel < 1e-2 and agree >= 0.999 and ncls >= 20
 
 
+def test_cityscapes_config_teacher_forced_256x512():
+    """Cityscapes config (19 classes, encoder FFN 2048) at a non-square shape: ragged class tile in the tail,
+    different GEMM widths, rectangular maps everywhere."""
+    cfg = s2f.configs.cityscapes()
+    pr, logits, ref, taps = _run(cfg, 256, 512)
+    s = _report(pr)
+    assert s["unknown"] == [] and s["neurons"] == 270
+    assert s["unexplained"] == 0 and s["maxdev"] <= 1
+    assert s["flips"] <= 1e-5 * s["spike_elems"]
+    assert s["worst_rel"] < 1e-4, s["worst_real"]
+    rel = float((logits - ref).abs().max() / ref.abs().max())
+    agree = float((logits.argmax(1) == ref.argmax(1)).float().mean())
+    print(f"Cityscapes cfg 256x512: logits rel err {rel:.3e}, argmax agreement {agree:.6f}")
+    assert rel < 1e-2 and agree >= 0.999
+
+
 def test_free_running_report():
     """No forcing: reports how spike flips grow through the (chaotic, random-init) network."""
     cfg = s2f.configs.tiny()
