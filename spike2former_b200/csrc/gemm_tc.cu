@@ -321,17 +321,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       stage_affine(p, ss_stage, co_base, 0, et);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");     // epilogue warps only
     }
-    int it = 0;
+    int it = 0, staged_img = -1, staged_buf = 0;
     for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
       const TileOrigin o = tile_origin(p, tile_m);
       const int acc = it & 1;
-      uint32_t ss_addr = smem_u32(ss_stage);
-      if (per_tile_affine) {                             // per-image weights: constants change with the image
-        float* dst = ss_stage + acc * (4 * TC_BN);
-        stage_affine(p, dst, co_base, o.img, et);
+      if (per_tile_affine && o.img != staged_img) {      // per-image weights: constants change with the image only
+        staged_buf ^= 1;                                 // the other buffer may still be read by a slower warp
+        stage_affine(p, ss_stage + staged_buf * (4 * TC_BN), co_base, o.img, et);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-        ss_addr = smem_u32(dst);
+        staged_img = o.img;
       }
+      const uint32_t ss_addr = smem_u32(ss_stage + staged_buf * (4 * TC_BN));
       int64_t m;            // flat output row (n*Ho*Wo index), -1 if outside
       if (p.mode_conv) {
         const int ho = o.ho0 + r / p.TW, wo = o.wo0 + r % p.TW;
