@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def stop(self):
         self._halt.set()
@@ -326,10 +326,17 @@ def main():
         "gpu_launches": int(launches),
         "model_tflops": value * ALG_GFLOP_PER_IMG / 1e3,
     }
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if roof and roof["kernel"] == "gemm_tc" and os.path.exists(tj):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list (mean over the
+        # 179 GEMM launches of one forward), scaled from the profiled batch to this run's batch
+        t = json.load(open(tj))["gemm_i8_tc_kernel<3>"]
+        traffic = t["dram_bytes_per_launch"] * B / t["batch"]
     if roof:
         peak = pk["bf16_sustained"] if roof["bound"] == "tensor" else pk["hbm"]
         out["roofline"] = {"bound": roof["bound"], "achieved": roof["achieved"], "peak": peak, "unit": roof["unit"],
-                           "frac": roof["achieved"] / peak, "traffic": None, "kernel": roof["kernel"],
+                           "frac": roof["achieved"] / peak, "traffic": traffic, "kernel": roof["kernel"],
                            "share_of_step": roof["share"], "launches_per_step": roof["launches"],
                            "peak_source": pk["src"] + (" bf16 sustained (inside a long step)" if roof["bound"] == "tensor" else " copy"),
                            "per_class_ms": roof["per_class_ms"]}
