@@ -341,6 +341,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (m >= p.M_total) m = -1;
       }
       // fused FPN merge: source coordinates of this row in the coarser map (upsample_bilinear2d, align_corners=False)
+      if (p.residual && m >= 0) {                      // this warp's 128-byte residual slice -> L1 before the accumulator wait
+        const int cpre = co_base + half * COLS_PER_WARP;
+        if (cpre < p.Cout) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.residual + m * p.Cout + cpre));
+      }
       const float* up00 = nullptr; const float* up01 = nullptr; const float* up10 = nullptr; const float* up11 = nullptr;
       float up_hx = 0.f, up_lx = 0.f, up_hy = 0.f, up_ly = 0.f;
       if (p.up_prev && m >= 0) {
@@ -354,6 +358,15 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const float* pb = p.up_prev + (int64_t)im * p.up_H * p.up_W * p.Cout;
         up00 = pb + ((int64_t)y0 * p.up_W + x0) * p.Cout; up01 = pb + ((int64_t)y0 * p.up_W + x1) * p.Cout;
         up10 = pb + ((int64_t)y1 * p.up_W + x0) * p.Cout; up11 = pb + ((int64_t)y1 * p.up_W + x1) * p.Cout;
+        // pull this warp's 128-byte slice of the four corners into L1 now: the loads in the chunk loop below then hit
+        // L1 instead of exposing an L2 round trip per chunk on the (latency-bound) epilogue path
+        const int cpre = co_base + half * COLS_PER_WARP;
+        if (cpre < p.Cout) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(up00 + cpre));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(up01 + cpre));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(up10 + cpre));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(up11 + cpre));
+        }
       }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();

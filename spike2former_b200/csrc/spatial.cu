@@ -31,13 +31,14 @@ template <typename AT> struct RawOf;
 template <> struct RawOf<int8_t> { using type = Raw8; };
 template <> struct RawOf<float> { using type = Raw32; };
 
-template <typename AT, int KS, int TW>
+template <typename AT, int KS, int TW, int CT>      // CT: compile-time channel count (0 = use the runtime C)
 __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, float a_scale,
                                                      const float* __restrict__ w_tap, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, float* __restrict__ out_f32,
-                                                     int8_t* __restrict__ out_spike, int n, int H, int W, int C, int Ho,
+                                                     int8_t* __restrict__ out_spike, int n, int H, int W, int C_rt, int Ho,
                                                      int Wo, int pad, float d_max) {
   using RT = typename RawOf<AT>::type;
+  const int C = CT ? CT : C_rt;                      // a constant C turns the interior loads into [base + immediate]
   const uint32_t c4n = (uint32_t)C >> 2;
   const uint32_t strips = (uint32_t)(Wo + TW - 1) / TW;
   const uint32_t total = (uint32_t)n * Ho * strips * c4n;          // host guarantees < 2^31
@@ -54,11 +55,18 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
     const int wi0 = wo0 - pad;
     int off[TW + KS - 1];                             // clamped column offsets, shared by all kernel rows
     uint32_t valid = 0;
+    const bool interior = wi0 >= 0 && wi0 + TW + KS - 1 <= W;
+    if (interior) {
+      valid = (1u << (TW + KS - 1)) - 1u;
 #pragma unroll
-    for (int i = 0; i < TW + KS - 1; ++i) {
-      const int wi = wi0 + i;
-      off[i] = min(max(wi, 0), W - 1) * C;
-      valid |= (wi >= 0 && wi < W) ? (1u << i) : 0u;
+      for (int i = 0; i < TW + KS - 1; ++i) off[i] = (wi0 + i) * C;
+    } else {
+#pragma unroll
+      for (int i = 0; i < TW + KS - 1; ++i) {
+        const int wi = wi0 + i;
+        off[i] = min(max(wi, 0), W - 1) * C;
+        valid |= (wi >= 0 && wi < W) ? (1u << i) : 0u;
+      }
     }
 #pragma unroll
     for (int kh = 0; kh < KS; ++kh) {
@@ -66,8 +74,14 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
       if (hi < 0 || hi >= H) continue;
       const AT* row = base + (int64_t)hi * W * C;
       RT raw[TW + KS - 1];
+      if (CT && interior) {
+        const AT* row0 = row + wi0 * CT;
 #pragma unroll
-      for (int i = 0; i < TW + KS - 1; ++i) raw[i] = load_raw(row + off[i]);
+        for (int i = 0; i < TW + KS - 1; ++i) raw[i] = load_raw(row0 + i * CT);
+      } else {
+#pragma unroll
+        for (int i = 0; i < TW + KS - 1; ++i) raw[i] = load_raw(row + off[i]);
+      }
       float4 wv[KS];
 #pragma unroll
       for (int kw = 0; kw < KS; ++kw) wv[kw] = __ldg(reinterpret_cast<const float4*>(w_tap + (kh * KS + kw) * C + c));
@@ -85,20 +99,19 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
         }
       }
     }
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    // y = acc * (a_scale * scale) + shift: one FFMA per output (a_scale is a power of two, so the product is exact)
+    float4 sc = make_float4(a_scale, a_scale, a_scale, a_scale), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (scale) {
-      sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c));
+      sc = make_float4(s4.x * a_scale, s4.y * a_scale, s4.z * a_scale, s4.w * a_scale);
       sh = __ldg(reinterpret_cast<const float4*>(shift + c));
     }
     const int64_t o0 = (((int64_t)img * Ho + ho) * Wo + wo0) * C + c;
 #pragma unroll
     for (int t = 0; t < TW; ++t) {
       if (wo0 + t >= Wo) break;
-      float y[4] = {acc[t][0] * a_scale, acc[t][1] * a_scale, acc[t][2] * a_scale, acc[t][3] * a_scale};
-      if (scale) {
-        y[0] = __fadd_rn(__fmul_rn(y[0], sc.x), sh.x); y[1] = __fadd_rn(__fmul_rn(y[1], sc.y), sh.y);
-        y[2] = __fadd_rn(__fmul_rn(y[2], sc.z), sh.z); y[3] = __fadd_rn(__fmul_rn(y[3], sc.w), sh.w);
-      }
+      const float y[4] = {fmaf(acc[t][0], sc.x, sh.x), fmaf(acc[t][1], sc.y, sh.y), fmaf(acc[t][2], sc.z, sh.z),
+                          fmaf(acc[t][3], sc.w, sh.w)};
       const int64_t o = o0 + (int64_t)t * C;
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
       if (out_spike) {
@@ -114,18 +127,18 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
 // unnormalise) so sampling coordinates agree with the reference to the last bits:
 //   loc = ref + grid*os + off*os/size ; g = 2*loc - 1 ; ix = ((g + 1)*size - 1)/2   (padded image coords)
 // One thread = one (pixel, group, 4 channels).  x is read through the 1-pixel zero border analytically.
+template <int CQ>      // float4 channel quads per group handled by one thread (Cg = 4 * CQ)
 __global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                     const int8_t* __restrict__ mask, float mask_scale,
-                                                    float* __restrict__ out, int n, int H, int W, int G, int Cg, int K,
+                                                    float* __restrict__ out, int n, int H, int W, int G, int K,
                                                     float os) {
-  const int q4 = Cg >> 2;
+  constexpr int Cg = 4 * CQ;
   const int C = G * Cg, P = K * K, pad = (K - 1) / 2;
   const float Hin = (float)(H + 2 * pad), Win = (float)(W + 2 * pad);
-  const int64_t total = (int64_t)n * H * W * G * q4;
+  const int64_t total = (int64_t)n * H * W * G;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(idx % q4);
-    int64_t r = idx / q4;
+    int64_t r = idx;
     const int g = (int)(r % G); r /= G;
     const int wo = (int)(r % W); r /= W;
     const int ho = (int)(r % H);
@@ -133,46 +146,54 @@ __global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x,
     const int64_t pix = ((int64_t)img * H + ho) * W + wo;
     const float* off = offset + pix * (int64_t)(G * P * 2) + (int64_t)g * P * 2;
     const int8_t* mk = mask + pix * (int64_t)(G * P) + (int64_t)g * P;
-    const float* xb = x + (int64_t)img * H * W * C + g * Cg + cq * 4;
+    const float* xb = x + (int64_t)img * H * W * C + g * Cg;
     const float half = (float)pad;   // dilation 1: (K-1)/2
     const float ref_x = __fdiv_rn((float)wo + half + 0.5f, Win);
     const float ref_y = __fdiv_rn((float)ho + half + 0.5f, Hin);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float acc[CQ][4];
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
 #pragma unroll 3
     for (int pt = 0; pt < P; ++pt) {
+      const float2 o2 = __ldg(reinterpret_cast<const float2*>(off) + pt);     // (x, y) offset of this point: 8-byte aligned
       const float m = (float)mk[pt] * mask_scale;
       // point order of _generate_dilation_grids: x index is the slow one (dcnv3_func.py:125-137)
       const float gx = __fdiv_rn((float)(pt / K) - half, Win);
       const float gy = __fdiv_rn((float)(pt % K) - half, Hin);
-      const float lx = __fadd_rn(__fadd_rn(ref_x, __fmul_rn(gx, os)), __fdiv_rn(__fmul_rn(off[2 * pt], os), Win));
-      const float ly = __fadd_rn(__fadd_rn(ref_y, __fmul_rn(gy, os)), __fdiv_rn(__fmul_rn(off[2 * pt + 1], os), Hin));
+      const float lx = __fadd_rn(__fadd_rn(ref_x, __fmul_rn(gx, os)), __fdiv_rn(__fmul_rn(o2.x, os), Win));
+      const float ly = __fadd_rn(__fadd_rn(ref_y, __fmul_rn(gy, os)), __fdiv_rn(__fmul_rn(o2.y, os), Hin));
       const float sgx = __fadd_rn(__fmul_rn(2.f, lx), -1.f), sgy = __fadd_rn(__fmul_rn(2.f, ly), -1.f);
       const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgx, 1.f), Win), -1.f), 0.5f);
       const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgy, 1.f), Hin), -1.f), 0.5f);
       const float fx = floorf(ix), fy = floorf(iy);
       const int x0 = (int)fx - pad, y0 = (int)fy - pad;   // back to unpadded coordinates
       const float tx = ix - fx, ty = iy - fy;
-      const float wnw = (1.f - tx) * (1.f - ty), wne = tx * (1.f - ty), wsw = (1.f - tx) * ty, wse = tx * ty;
-      // four corners, loaded unconditionally from clamped addresses (weight 0 outside the map) so the 36 loads of a
-      // thread are independent of each other
-      auto corner = [&](int yy, int xx, float wgt, float4& v, float& wq) {
-        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
-        v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)yc * W + xc) * C));
-        wq = in ? wgt : 0.f;
-      };
-      float4 v00, v01, v10, v11;
-      float q00, q01, q10, q11;
-      corner(y0, x0, wnw, v00, q00); corner(y0, x0 + 1, wne, v01, q01);
-      corner(y0 + 1, x0, wsw, v10, q10); corner(y0 + 1, x0 + 1, wse, v11, q11);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      s0 = fmaf(v00.x, q00, s0); s1 = fmaf(v00.y, q00, s1); s2 = fmaf(v00.z, q00, s2); s3 = fmaf(v00.w, q00, s3);
-      s0 = fmaf(v01.x, q01, s0); s1 = fmaf(v01.y, q01, s1); s2 = fmaf(v01.z, q01, s2); s3 = fmaf(v01.w, q01, s3);
-      s0 = fmaf(v10.x, q10, s0); s1 = fmaf(v10.y, q10, s1); s2 = fmaf(v10.z, q10, s2); s3 = fmaf(v10.w, q10, s3);
-      s0 = fmaf(v11.x, q11, s0); s1 = fmaf(v11.y, q11, s1); s2 = fmaf(v11.z, q11, s2); s3 = fmaf(v11.w, q11, s3);
-      a0 = fmaf(s0, m, a0); a1 = fmaf(s1, m, a1); a2 = fmaf(s2, m, a2); a3 = fmaf(s3, m, a3);
+      // corner weights (0 outside the map) and clamped addresses: all loads are unconditional and independent
+      const bool inx0 = x0 >= 0 && x0 < W, inx1 = x0 + 1 >= 0 && x0 + 1 < W;
+      const bool iny0 = y0 >= 0 && y0 < H, iny1 = y0 + 1 >= 0 && y0 + 1 < H;
+      const float q00 = (inx0 && iny0) ? (1.f - tx) * (1.f - ty) : 0.f, q01 = (inx1 && iny0) ? tx * (1.f - ty) : 0.f;
+      const float q10 = (inx0 && iny1) ? (1.f - tx) * ty : 0.f, q11 = (inx1 && iny1) ? tx * ty : 0.f;
+      const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+      const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+      const float4* p00 = reinterpret_cast<const float4*>(xb + ((int64_t)yc0 * W + xc0) * C);
+      const float4* p01 = reinterpret_cast<const float4*>(xb + ((int64_t)yc0 * W + xc1) * C);
+      const float4* p10 = reinterpret_cast<const float4*>(xb + ((int64_t)yc1 * W + xc0) * C);
+      const float4* p11 = reinterpret_cast<const float4*>(xb + ((int64_t)yc1 * W + xc1) * C);
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) {
+        const float4 v00 = __ldg(p00 + c), v01 = __ldg(p01 + c), v10 = __ldg(p10 + c), v11 = __ldg(p11 + c);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        s0 = fmaf(v00.x, q00, s0); s1 = fmaf(v00.y, q00, s1); s2 = fmaf(v00.z, q00, s2); s3 = fmaf(v00.w, q00, s3);
+        s0 = fmaf(v01.x, q01, s0); s1 = fmaf(v01.y, q01, s1); s2 = fmaf(v01.z, q01, s2); s3 = fmaf(v01.w, q01, s3);
+        s0 = fmaf(v10.x, q10, s0); s1 = fmaf(v10.y, q10, s1); s2 = fmaf(v10.z, q10, s2); s3 = fmaf(v10.w, q10, s3);
+        s0 = fmaf(v11.x, q11, s0); s1 = fmaf(v11.y, q11, s1); s2 = fmaf(v11.z, q11, s2); s3 = fmaf(v11.w, q11, s3);
+        acc[c][0] = fmaf(s0, m, acc[c][0]); acc[c][1] = fmaf(s1, m, acc[c][1]);
+        acc[c][2] = fmaf(s2, m, acc[c][2]); acc[c][3] = fmaf(s3, m, acc[c][3]);
+      }
     }
-    *reinterpret_cast<float4*>(out + pix * C + g * Cg + cq * 4) = make_float4(a0, a1, a2, a3);
+#pragma unroll
+    for (int c = 0; c < CQ; ++c)
+      *reinterpret_cast<float4*>(out + pix * C + g * Cg + c * 4) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
   }
 }
 
@@ -269,14 +290,23 @@ extern "C" int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const fl
   const int g = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   const float asc = a_is_spike ? a_scale : 1.f;
-#define S2F_DW(AT, KS)                                                                                                      \
-  dwconv_kernel<AT, KS, TW><<<g, 256, 0, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, out_f32, out_spike, n, \
-                                               H, W, C, Ho, Wo, pad, d_max)
+#define S2F_DW_C(AT, KS, CT)                                                                                               \
+  dwconv_kernel<AT, KS, TW, CT><<<g, 256, 0, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, out_f32, out_spike, \
+                                                   n, H, W, C, Ho, Wo, pad, d_max)
+#define S2F_DW(AT, KS)                                                                            \
+  do {                                                                                            \
+    if (sizeof(AT) == 1 && C == 64) S2F_DW_C(AT, KS, 64);                                         \
+    else if (sizeof(AT) == 1 && C == 128) S2F_DW_C(AT, KS, 128);                                  \
+    else if (sizeof(AT) == 1 && C == 256) S2F_DW_C(AT, KS, 256);                                  \
+    else if (sizeof(AT) == 1 && C == 512) S2F_DW_C(AT, KS, 512);                                  \
+    else S2F_DW_C(AT, KS, 0);                                                                     \
+  } while (0)
   if (a_is_spike) {
     if (k == 3) S2F_DW(int8_t, 3); else if (k == 5) S2F_DW(int8_t, 5); else S2F_DW(int8_t, 7);
   } else {
     if (k == 3) S2F_DW(float, 3); else if (k == 5) S2F_DW(float, 5); else S2F_DW(float, 7);
   }
+#undef S2F_DW_C
 #undef S2F_DW
   return check_launch("dwconv_kernel");
 }
@@ -286,9 +316,16 @@ extern "C" int s2f_dcnv3_gather(const float* x, const float* offset, const int8_
   S2F_REQUIRE(x && offset && mask && out, "dcnv3_gather: null pointer");
   S2F_REQUIRE(Cg % 4 == 0, "dcnv3_gather: group channels must be a multiple of 4");
   S2F_REQUIRE(K % 2 == 1 && K >= 1, "dcnv3_gather: K must be odd");
-  const int64_t total = (int64_t)n * H * W * G * (Cg / 4);
-  dcnv3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, offset, mask, mask_scale, out, n, H, W, G, Cg,
-                                                                       K, offset_scale);
+  S2F_REQUIRE(Cg <= 16 && ((G * K * K * 2) % 2 == 0), "dcnv3_gather: at most 16 channels per group");
+  const int64_t total = (int64_t)n * H * W * G;
+  const int grid = grid_for(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (Cg / 4) {
+    case 1: dcnv3_kernel<1><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+    case 2: dcnv3_kernel<2><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+    case 3: dcnv3_kernel<3><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+    default: dcnv3_kernel<4><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+  }
   return check_launch("dcnv3_kernel");
 }
 

@@ -22,7 +22,8 @@ from .ops import NORM
 
 INV = 1.0 / NORM
 USE_TC = True            # spike-operand layers run on the tcgen05 kernel (the CUDA-core kernel covers the rest)
-TC_PIECES = 3            # int8 digit planes per weight: 21-bit fixed point per output channel, exact accumulation
+import os as _os
+TC_PIECES = int(_os.environ.get("S2F_TC_PIECES", "3"))   # int8 digit planes per weight: 3 = 21-bit fixed point (default), 2 = 14-bit fast mode
 TC_MIN_ROWS = 1024       # below this many output rows a 128-row tile grid cannot fill the GPU
 
 
