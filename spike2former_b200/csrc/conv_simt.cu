@@ -9,6 +9,7 @@
 //   epi(acc) = acc*scale[co] + shift[co] (+ residual) -> fp32 and/or NI-LIF int8 level.
 #include "common.cuh"
 #include "conv_direct.cuh"
+#include "conv_tf32.cuh"
 
 namespace s2f {
 
@@ -165,6 +166,7 @@ extern "C" int s2f_conv_simt(const s2f_conv_args* a, void* stream) {
   p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
   p.out_transposed = a->out_transposed;
   S2F_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv_simt: empty output");
+  if (launch_pw_tf32(p, a->a_is_spike != 0, (cudaStream_t)stream)) return check_launch("pw_tf32_kernel");
   if (launch_conv_direct(p, a->a_is_spike != 0, (cudaStream_t)stream)) return check_launch("conv_direct_kernel");
   const int M = p.Ho * p.Wo;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p.Cout, BN), (unsigned)p.n);

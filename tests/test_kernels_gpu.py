@@ -152,6 +152,24 @@ def test_conv_simt_vs_torch(cin, cout, k, stride, H, W):
     assert torch.equal(oft.cpu().view(n, cout, Ho * Wo).permute(0, 2, 1), of2.cpu().view(n, Ho * Wo, cout))
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 32, 24, 20), (128, 64, 16, 16), (256, 128, 9, 7), (64, 16, 8, 8)])
+def test_pointwise_fp32_3xtf32_vs_float64(cin, cout, H, W):
+    """SepConv.pwconv2 path (sdtv2.py:176-178): fp32 activations x fp32 weights on the tensor cores with 3xTF32
+    compensation must stay fp32-grade (the plain-TF32 error would be ~5e-4)."""
+    g = gen(21)
+    n = 3
+    a = torch.randn(n, H, W, cin, generator=g) * 2
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    res = torch.randn(n, H, W, cout, generator=g)
+    ref = (a.double().view(-1, cin) @ w.double().t()).view(n, H, W, cout) * sc.double() + sh.double() + res.double()
+    of, os_ = ops.conv_simt(a.cuda(), ops.pad_rows4(w.cuda()), n=n, H=H, W=W, Cin=cin, Cout=cout, scale=sc.cuda(),
+                            shift=sh.cuda(), residual=res.cuda(), want_f32=True, want_spike=True)
+    err = (of.cpu().double() - ref).abs().max().item()
+    assert err < 3e-6 * max(1.0, ref.abs().max().item()), err
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+
+
 @pytest.mark.parametrize("k", [3, 5, 7])
 @pytest.mark.parametrize("spike_in", [True, False])
 def test_dwconv_vs_torch(k, spike_in):
