@@ -24,7 +24,8 @@ INV = 1.0 / NORM
 USE_TC = True            # spike-operand layers run on the tcgen05 kernel (the CUDA-core kernel covers the rest)
 import os as _os
 TC_PIECES = int(_os.environ.get("S2F_TC_PIECES", "3"))   # int8 digit planes per weight: 3 = 21-bit fixed point (default), 2 = 14-bit fast mode
-TC_MIN_ROWS = 1024       # below this many output rows a 128-row tile grid cannot fill the GPU
+TC_MIN_ROWS = 1          # every eligible layer runs on the tensor-core kernel whatever the batch: its integer accumulation
+                         # is order-independent, so an image's result never depends on how many images share the launch
 
 
 # ------------------------------------------------------------------------------------------------ plan

@@ -129,3 +129,26 @@ def test_cuda_graph_replay_matches_eager_launches():
     seg.use_cuda_graph = False
     with torch.no_grad():
         assert torch.equal(seg.encode_decode(x1), e1)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 512, 512), (3, 384, 640), (2, 256, 128)])
+def test_public_api_shapes_and_batches(B, H, W):
+    """Public path (EncoderDecoder.encode_decode / predict_labels, CUDA-graph replay) at other batches and
+    rectangular shapes of the ADE20K model: finite logits, labels == argmax(logits), images independent of the batch."""
+    from spike2former_b200 import synth
+
+    cfg = s2f.configs.ade20k()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint("ade20k", cfg), strict=True)
+    seg = seg.cuda()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 3, H, W, generator=g).cuda()
+    with torch.no_grad():
+        logits = seg.encode_decode(x).clone()
+        labels = seg.predict_labels(x).clone()
+        single = seg.encode_decode(x[:1].contiguous()).clone()
+    assert logits.shape == (B, 150, H, W) and labels.shape == (B, H, W)
+    assert torch.isfinite(logits).all()
+    assert torch.equal(labels.long(), logits.argmax(1))
+    assert torch.equal(single[0], logits[0])                 # batch-sharding invariant: an image does not see its batch
+    assert logits.argmax(1).unique().numel() >= 2                 # not a constant map (small random-weight images show few classes)
