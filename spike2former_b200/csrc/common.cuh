@@ -43,7 +43,18 @@ __device__ __forceinline__ float spike_level(float v, float d_max) { return rint
 __device__ __forceinline__ uint32_t level_bits(float v, float d_max) {
   return __float_as_uint(fminf(fmaxf(v, 0.f), d_max) + 8388608.f);
 }
+// Same for d_max = 8 (every Spike2Former config): clamp by the saturating multiply (FMUL.SAT clamps to [0, 1]; the
+// power-of-two scalings are exact), then one FFMA puts the rounded level into the mantissa: 2 instructions, not 3.
+__device__ __forceinline__ uint32_t level_bits8(float v) {
+  return __float_as_uint(fmaf(__saturatef(v * 0.125f), 8.f, 8388608.f));
+}
+__device__ __forceinline__ uint32_t pack_levels4_d8(float a, float b, float c, float d) {
+  const uint32_t lo = __byte_perm(level_bits8(a), level_bits8(b), 0x0040);
+  const uint32_t hi = __byte_perm(level_bits8(c), level_bits8(d), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
 __device__ __forceinline__ uint32_t pack_levels4(float a, float b, float c, float d, float d_max) {
+  if (d_max == 8.f) return pack_levels4_d8(a, b, c, d);          // uniform branch
   const uint32_t lo = __byte_perm(level_bits(a, d_max), level_bits(b, d_max), 0x0040);
   const uint32_t hi = __byte_perm(level_bits(c, d_max), level_bits(d, d_max), 0x0040);
   return __byte_perm(lo, hi, 0x5410);

@@ -164,24 +164,16 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-// Stage the per-channel epilogue constants of one channel tile: ss[0..2][64] = scale * 128^(pieces-1-plane), ss[3][64] = shift.
+// Stage the per-channel epilogue constants of one channel tile: ss[0][64] = scale, ss[1][64] = shift.
+// (The digit planes are merged before the affine: y = (d0 * 128^(P-1) + merged low planes) * scale + shift.)
 __device__ __forceinline__ void stage_affine(const TcParams& p, float* ss, int co_base, int img, int et) {
-  for (; et < 4 * TC_BN; et += 32 * TC_EPI_WARPS) {
+  for (; et < 2 * TC_BN; et += 32 * TC_EPI_WARPS) {
     const int which = et >> 6, ch = co_base + (et & (TC_BN - 1));
     float v = 0.f;
-    if (ch < p.Cout) {
-      if (which == 3) {
-        v = __ldg(p.shift + (int64_t)img * p.ss_img_stride + ch);
-      } else if (which < p.pieces) {
-        const float sc = __ldg(p.scale + (int64_t)img * p.ss_img_stride + ch);
-        const int e = p.pieces - 1 - which;
-        v = sc * (e == 2 ? 16384.f : (e == 1 ? 128.f : 1.f));          // exact: power-of-two factor
-      }
-    }
+    if (ch < p.Cout) v = __ldg((which ? p.shift : p.scale) + (int64_t)img * p.ss_img_stride + ch);
     ss[et] = v;
   }
 }
-
 
 template <int PIECES, int NK>
 __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t ring_addr, uint32_t bres_addr, int stage_bytes,
@@ -381,29 +373,23 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
         tmem_ld_wait();
         if (m < 0) continue;
-        // y = shift + float(d0) * (scale * 128^(pieces-1)) + float(low planes combined in int32) * scale.
-        // The two low digit planes are merged exactly in integer arithmetic (|d1 * 128 + d2| < 2^31 for K < 32768), so
-        // the recombination costs one IMAD, two I2FP and two FFMA per output; each conversion rounds once (fp32).
+        // v = d0 * 128^(P-1) + (low planes merged exactly in int32: |d1 * 128 + d2| < 2^31 for K < 32768), one rounding;
+        // y = v * scale + shift.  Per output: one IMAD, two I2FP, two FFMA.
         float y[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 sh = lds128(ss_addr + (uint32_t)(3 * TC_BN + j0 + 4 * q) * 4u);
-          const float4 s_lo = lds128(ss_addr + (uint32_t)((PIECES - 1) * TC_BN + j0 + 4 * q) * 4u);   // scale * 1
-          const float4 s_hi = lds128(ss_addr + (uint32_t)(j0 + 4 * q) * 4u);                               // scale * 128^(pieces-1)
-          float lo[4], hi[4];
+          const float4 sc = lds128(ss_addr + (uint32_t)(j0 + 4 * q) * 4u);
+          const float4 sh = lds128(ss_addr + (uint32_t)(TC_BN + j0 + 4 * q) * 4u);
+          float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = 4 * q + e;
-            if (PIECES == 3) { lo[e] = (float)((int)d1[j] * 128 + (int)d2[j]); hi[e] = (float)(int)d0[j]; }
-            else if (PIECES == 2) { lo[e] = (float)((int)d0[j] * 128 + (int)d1[j]); hi[e] = 0.f; }
-            else { lo[e] = (float)(int)d0[j]; hi[e] = 0.f; }
+            if (PIECES == 3) v[e] = fmaf((float)(int)d0[j], 16384.f, (float)((int)d1[j] * 128 + (int)d2[j]));
+            else if (PIECES == 2) v[e] = (float)((int)d0[j] * 128 + (int)d1[j]);
+            else v[e] = (float)(int)d0[j];
           }
-          y[4 * q] = fmaf(lo[0], s_lo.x, sh.x); y[4 * q + 1] = fmaf(lo[1], s_lo.y, sh.y);
-          y[4 * q + 2] = fmaf(lo[2], s_lo.z, sh.z); y[4 * q + 3] = fmaf(lo[3], s_lo.w, sh.w);
-          if (PIECES == 3) {
-            y[4 * q] = fmaf(hi[0], s_hi.x, y[4 * q]); y[4 * q + 1] = fmaf(hi[1], s_hi.y, y[4 * q + 1]);
-            y[4 * q + 2] = fmaf(hi[2], s_hi.z, y[4 * q + 2]); y[4 * q + 3] = fmaf(hi[3], s_hi.w, y[4 * q + 3]);
-          }
+          y[4 * q] = fmaf(v[0], sc.x, sh.x); y[4 * q + 1] = fmaf(v[1], sc.y, sh.y);
+          y[4 * q + 2] = fmaf(v[2], sc.z, sh.z); y[4 * q + 3] = fmaf(v[3], sc.w, sh.w);
         }
         const int co0 = co_base + j0;
         const int nvalid = min(16, p.Cout - co0);
