@@ -12,6 +12,7 @@
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, column half = (warp_id - 2) / 4).  The kernel is
 // persistent (one CTA per SM) with two accumulators in TMEM, so the epilogue of a tile overlaps the next main loop.
 #include <cuda.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -52,6 +53,9 @@ struct TcParams {
   int w_img_rows;       // packed weight rows per image (0: one weight matrix for all images)
   int ss_img_stride;    // scale/shift elements per image (0: shared)
   float d_max;
+  int up_tma;           // the coarser FPN level arrives as TMA patches in shared memory (exact 2x upsample)
+  int up_PW, up_PH;     // patch extent in source pixels: TW/2 + 2, TH/2 + 2
+  int staged;           // epilogue through a per-warp shared-memory transpose: coalesced residual / up_prev / fp32 traffic
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -218,9 +222,291 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t ring_addr, 
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------------ epilogue variants
+// The kernel is compiled once per epilogue kind: run-time flags in the (latency-bound, 2 warps per scheduler)
+// epilogue cost branches, instruction-cache misses and dead registers -- 478 executed instructions per warp and tile
+// in the flag-driven version against ~300 here.
+constexpr int EPI_GENERIC = 0;     // every combination (transposed / ragged / per-image affine ...): flag driven
+constexpr int EPI_SPIKE = 1;       // int8 levels only, Cout % 16 == 0, d_max = 8: the bulk of the network's launches
+constexpr int EPI_STAGED = 2;      // fp32 / residual outputs through the shared-memory transpose
+constexpr int EPI_STAGED_UP = 3;   // the same + fused FPN merge from TMA patches
+
+// exact plane merge: d0 * 128^(P-1) + (low planes merged in int32), one rounding
 template <int PIECES>
+__device__ __forceinline__ float merge_planes(uint32_t d0, uint32_t d1, uint32_t d2) {
+  if (PIECES == 3) return fmaf((float)(int)d0, 16384.f, (float)((int)d1 * 128 + (int)d2));
+  if (PIECES == 2) return (float)((int)d0 * 128 + (int)d1);
+  return (float)(int)d0;
+}
+
+// Spike-only epilogue: lane = accumulator row, warp = 32 channels.  All six TMEM loads of the warp's slice are issued
+// back to back and the accumulator is handed back to the MMA warp as soon as they have landed in registers.
+// ss: [64] scale/8, [64] shift/8 (the power-of-two scaling is exact), so that the level is
+//   rne(8 * sat(v * scale/8 + shift/8)):  FFMA.SAT + FFMA (2^23 trick) per output, then PRMT packing.
+template <int PIECES>
+__device__ __forceinline__ void epilogue_spike(const TcParams& p, float* ss, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                               uint32_t tmem_base, int slot, int tile_n, int warp, int lane) {
+  const int quad = warp & 3, half = (warp - 2) >> 2;
+  const int r = quad * 32 + lane;
+  const int et = threadIdx.x - 64;
+  const int co_base = tile_n * TC_BN;
+  for (int e = et; e < 2 * TC_BN; e += 32 * TC_EPI_WARPS) {
+    const int ch = co_base + (e & (TC_BN - 1));
+    ss[e] = ch < p.Cout ? 0.125f * __ldg(((e >> 6) ? p.shift : p.scale) + ch) : 0.f;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+  const int cw0 = co_base + half * 32;                     // this warp's first channel
+  const int nchunks = cw0 >= p.Cout ? 0 : (cw0 + 16 >= p.Cout ? 1 : 2);      // Cout % 16 == 0 on this path
+  const uint32_t ss_addr = smem_u32(ss) + (uint32_t)(half * 32) * 4u;
+  int it = 0;
+  for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
+    const int acc = it & 1;
+    int64_t m;
+    if (p.mode_conv) {
+      const TileOrigin o = tile_origin(p, tile_m);
+      const int ho = o.ho0 + r / p.TW, wo = o.wo0 + r % p.TW;
+      m = (ho < p.Ho && wo < p.Wo) ? ((int64_t)o.img * p.Ho + ho) * p.Wo + wo : -1;
+    } else {
+      m = (int64_t)tile_m * TC_BM + r;
+      if (m >= p.M_total) m = -1;
+    }
+    int8_t* dst = p.out_spike + m * p.Cout + cw0;
+    mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS) + (uint32_t)(half * 32);
+    uint32_t d[2][3][16];
+    if (nchunks > 0) {
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        tmem_ld16(trow + jj * 16, d[jj][0]);
+        if (PIECES > 1) tmem_ld16(trow + TC_BN + jj * 16, d[jj][1]);
+        if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + jj * 16, d[jj][2]);
+      }
+      tmem_ld_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);            // accumulator drained: the next tile's MMAs may start
+    if (m < 0) continue;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      if (jj < nchunks) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 sc = lds128(ss_addr + (uint32_t)(jj * 16 + 4 * q) * 4u);
+          const float4 sh = lds128(ss_addr + (uint32_t)(TC_BN + jj * 16 + 4 * q) * 4u);
+          const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, h4[4] = {sh.x, sh.y, sh.z, sh.w};
+          uint32_t b[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            const float v = merge_planes<PIECES>(d[jj][0][j], d[jj][1][j], d[jj][2][j]);
+            b[e] = __float_as_uint(fmaf(__saturatef(fmaf(v, s4[e], h4[e])), 8.f, 8388608.f));
+          }
+          w[q] = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+        }
+        *reinterpret_cast<uint4*>(dst + jj * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ staged epilogue
+// tcgen05.ld hands every lane one accumulator ROW, so an epilogue that goes to global memory straight from those
+// registers touches 32 different rows per instruction (32 L1 wavefronts for 512 bytes).  Layers that read a residual /
+// the coarser FPN level or write fp32 are bound by exactly that, so they take this path instead: the warp parks its
+// 32 rows x 32 channels of merged accumulators in a private shared-memory tile (row stride 36 floats: conflict-free for
+// both the row-per-lane STS.128 and the 4-rows-x-128-byte LDS.128), releases the TMEM accumulator, and then walks the
+// tile with lane = (row % 4, channel quad): every global access is 4 rows x 128 contiguous bytes.
+constexpr int TC_STG_LD = 36;                               // floats per staged row (32 + 4 padding)
+constexpr int TC_STG_FLOATS = 32 * TC_STG_LD;               // per epilogue warp
+constexpr int TC_UP_SLOT = 60 * TC_BN * 4;                  // one patch: <= 60 source pixels x 64 channels fp32 (TW x TH = 16x8 or 8x16)
+constexpr int TC_AUX_OFF = 512 + 2 * 4 * TC_BN * 4 + TC_EPI_WARPS * TC_STG_FLOATS * 4;   // barriers | affine | staging -> patches
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int PIECES, bool UP_TMA>
+__device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                uint32_t tmem_base, int slot, int tile_n, int warp, int lane,
+                                                const uint8_t* up_patch, uint64_t* up_full, uint64_t* up_empty) {
+  static_assert(TC_EPI_WARPS == 8, "the staged epilogue assumes 32 channels per epilogue warp");
+  const int quad = warp & 3, half = (warp - 2) >> 2;
+  const int r = quad * 32 + lane;
+  const int cq = lane & 7, rsub = lane >> 3;
+  const int cw = tile_n * TC_BN + half * 32 + 4 * cq;         // this lane's four channels in phase 2
+  const bool cvalid = cw < p.Cout;                            // Cout % 4 == 0 on this path
+  const bool warp_has_cols = tile_n * TC_BN + half * 32 < p.Cout;
+  const uint32_t stg_addr = smem_u32(stg);
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+  int loaded_img = -1;
+  int it = 0;
+  for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
+    const TileOrigin o = tile_origin(p, tile_m);
+    const int acc = it & 1;
+    const int aff_img = p.ss_img_stride ? o.img : 0;
+    if (aff_img != loaded_img) {                              // warp-uniform; once per CTA unless the weights are per image
+      if (cvalid) {
+        sc = __ldg(reinterpret_cast<const float4*>(p.scale + (int64_t)aff_img * p.ss_img_stride + cw));
+        sh = __ldg(reinterpret_cast<const float4*>(p.shift + (int64_t)aff_img * p.ss_img_stride + cw));
+      }
+      loaded_img = aff_img;
+    }
+    int m;                // flat output row of this lane's TMEM row (n*Ho*Wo index < 2^31), -1 if outside
+    if (p.mode_conv) {
+      const int ho = o.ho0 + r / p.TW, wo = o.wo0 + r % p.TW;
+      m = (ho < p.Ho && wo < p.Wo) ? (o.img * p.Ho + ho) * p.Wo + wo : -1;
+    } else {
+      m = tile_m * TC_BM + r;
+      if (m >= p.M_total) m = -1;
+    }
+    // fused FPN merge: the four source pixels (indices into up_prev's [n*up_H*up_W] pixel axis) and the two fractions
+    int u00 = 0, u01 = 0, u10 = 0, u11 = 0;
+    float up_lx = 0.f, up_ly = 0.f;
+    if (p.up_prev && m >= 0) {
+      const int im = m / p.M_img, rr = m % p.M_img;
+      const int yo = rr / p.Wo, xo = rr % p.Wo;
+      float sy = ((float)p.up_H / (float)p.Ho) * ((float)yo + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+      float sx = ((float)p.up_W / (float)p.Wo) * ((float)xo + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = y0 + (y0 < p.up_H - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_W - 1 ? 1 : 0);
+      up_ly = sy - (float)y0; up_lx = sx - (float)x0;
+      if (UP_TMA) {          // pixel indices inside the tile's patch (origin: ho0/2 - 1, wo0/2 - 1), one byte each
+        const int py = o.ho0 / 2 - 1, px = o.wo0 / 2 - 1;
+        const int l0 = (y0 - py) * p.up_PW - px, l1 = (y1 - py) * p.up_PW - px;
+        u00 = (l0 + x0) | ((l0 + x1) << 8) | ((l1 + x0) << 16) | ((l1 + x1) << 24);
+      } else {
+        const int pb = im * p.up_H * p.up_W;
+        u00 = pb + y0 * p.up_W + x0; u01 = pb + y0 * p.up_W + x1; u10 = pb + y1 * p.up_W + x0; u11 = pb + y1 * p.up_W + x1;
+      }
+    }
+    // the residual rows of phase 2 do not depend on the accumulator: issue their (coalesced) loads now, so that the
+    // DRAM / L2 latency is covered by the wait for the MMAs and by phase 1
+    // element offsets of this lane's eight phase-2 rows relative to the tile's first row (32-bit; negative = no row):
+    // the 64-bit part of every address is a per-tile, warp-uniform base
+    const int64_t mt0 = p.mode_conv ? ((int64_t)o.img * p.Ho + o.ho0) * p.Wo + o.wo0 : (int64_t)tile_m * TC_BM;
+    const int rel_c = m >= 0 ? (m - (int)mt0) * p.Cout : INT_MIN / 2;
+    int orow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = __shfl_sync(0xffffffffu, rel_c, 4 * i + rsub);
+      orow[i] = cvalid ? t + cw : -1;                           // cvalid: this lane's channel quad exists
+    }
+    const float* res_t = p.residual ? p.residual + mt0 * p.Cout : nullptr;
+    float* of_t = p.out_f32 ? p.out_f32 + mt0 * p.Cout : nullptr;
+    int8_t* os_t = p.out_spike ? p.out_spike + mt0 * p.Cout : nullptr;
+    float4 res[8];
+    if (p.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (orow[i] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(res_t + orow[i]));
+      }
+    }
+    mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
+    // ---- phase 1: accumulators -> merged fp32 -> this lane's row of the staging tile (16 channels at a time: the
+    // residual rows already occupy 32 registers)
+    if (warp_has_cols) {
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j0 = half * 32 + jj * 16;
+        uint32_t d0[16], d1[16], d2[16];
+        tmem_ld16(trow + j0, d0);
+        if (PIECES > 1) tmem_ld16(trow + TC_BN + j0, d1);
+        if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
+        tmem_ld_wait();
+        const uint32_t wa = stg_addr + (uint32_t)(lane * TC_STG_LD + jj * 16) * 4u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(wa + 16u * q, merge_planes<PIECES>(d0[4 * q], d1[4 * q], d2[4 * q]),
+                 merge_planes<PIECES>(d0[4 * q + 1], d1[4 * q + 1], d2[4 * q + 1]),
+                 merge_planes<PIECES>(d0[4 * q + 2], d1[4 * q + 2], d2[4 * q + 2]),
+                 merge_planes<PIECES>(d0[4 * q + 3], d1[4 * q + 3], d2[4 * q + 3]));
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);              // the MMA warp may refill this accumulator now
+    // ---- phase 2: lane = (row % 4, channel quad); 8 steps of 4 rows x 128 bytes
+    if (warp_has_cols) {
+      const uint32_t ra = stg_addr + (uint32_t)(rsub * TC_STG_LD + 4 * cq) * 4u;
+      if (!UP_TMA && !p.up_prev) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = lds128(ra + (uint32_t)(4 * i * TC_STG_LD) * 4u);
+          if (orow[i] >= 0) {
+            float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
+            if (p.residual) { y0 += res[i].x; y1 += res[i].y; y2 += res[i].z; y3 += res[i].w; }
+            if (of_t) *reinterpret_cast<float4*>(of_t + orow[i]) = make_float4(y0, y1, y2, y3);
+            if (os_t) *reinterpret_cast<uint32_t*>(os_t + orow[i]) = pack_levels4_d8(y0, y1, y2, y3);
+          }
+        }
+      } else if (UP_TMA) {
+        const int us = it % 3;
+        mbar_wait(&up_full[us], (uint32_t)((it / 3) & 1));
+        const uint32_t pa = smem_u32(up_patch) + (uint32_t)us * (uint32_t)TC_UP_SLOT + (uint32_t)(half * 32 + 4 * cq) * 4u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = 4 * i + rsub;
+          const uint32_t pk = (uint32_t)__shfl_sync(0xffffffffu, u00, src);
+          const float lx = __shfl_sync(0xffffffffu, up_lx, src), ly = __shfl_sync(0xffffffffu, up_ly, src);
+          const float4 v = lds128(ra + (uint32_t)(4 * i * TC_STG_LD) * 4u);
+          if (orow[i] >= 0) {
+            const float hx = 1.f - lx, hy = 1.f - ly;
+            const float4 p00 = lds128(pa + (pk & 0xffu) * (TC_BN * 4u)), p01 = lds128(pa + ((pk >> 8) & 0xffu) * (TC_BN * 4u));
+            const float4 p10 = lds128(pa + ((pk >> 16) & 0xffu) * (TC_BN * 4u)), p11 = lds128(pa + (pk >> 24) * (TC_BN * 4u));
+            float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
+            if (p.residual) { y0 += res[i].x; y1 += res[i].y; y2 += res[i].z; y3 += res[i].w; }
+            y0 = y0 + (hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x));
+            y1 = y1 + (hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y));
+            y2 = y2 + (hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z));
+            y3 = y3 + (hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w));
+            if (of_t) *reinterpret_cast<float4*>(of_t + orow[i]) = make_float4(y0, y1, y2, y3);
+            if (os_t) *reinterpret_cast<uint32_t*>(os_t + orow[i]) = pack_levels4_d8(y0, y1, y2, y3);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = 4 * i + rsub;
+          const int s00 = __shfl_sync(0xffffffffu, u00, src), s01 = __shfl_sync(0xffffffffu, u01, src);
+          const int s10 = __shfl_sync(0xffffffffu, u10, src), s11 = __shfl_sync(0xffffffffu, u11, src);
+          const float lx = __shfl_sync(0xffffffffu, up_lx, src), ly = __shfl_sync(0xffffffffu, up_ly, src);
+          const float4 v = lds128(ra + (uint32_t)(4 * i * TC_STG_LD) * 4u);
+          if (orow[i] >= 0) {
+            const float hx = 1.f - lx, hy = 1.f - ly;
+            const float4 p00 = __ldg(reinterpret_cast<const float4*>(p.up_prev + (int64_t)s00 * p.Cout + cw));
+            const float4 p01 = __ldg(reinterpret_cast<const float4*>(p.up_prev + (int64_t)s01 * p.Cout + cw));
+            const float4 p10 = __ldg(reinterpret_cast<const float4*>(p.up_prev + (int64_t)s10 * p.Cout + cw));
+            const float4 p11 = __ldg(reinterpret_cast<const float4*>(p.up_prev + (int64_t)s11 * p.Cout + cw));
+            float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
+            if (p.residual) { y0 += res[i].x; y1 += res[i].y; y2 += res[i].z; y3 += res[i].w; }
+            // ATen upsample_bilinear2d: hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11), then cur + up
+            y0 = y0 + (hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x));
+            y1 = y1 + (hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y));
+            y2 = y2 + (hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z));
+            y3 = y3 + (hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w));
+            if (of_t) *reinterpret_cast<float4*>(of_t + orow[i]) = make_float4(y0, y1, y2, y3);
+            if (os_t) *reinterpret_cast<uint32_t*>(os_t + orow[i]) = pack_levels4_d8(y0, y1, y2, y3);
+          }
+        }
+      }
+    }
+    __syncwarp();                                              // the tile is free for the next phase 1
+    if (UP_TMA && lane == 0) mbar_arrive(&up_empty[it % 3]);
+  }
+}
+
+template <int PIECES, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_up, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int nB = TC_BN * PIECES;                    // MMA N
@@ -235,8 +521,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* tmem_full = empty + p.stages;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;               // [2]
   uint64_t* b_full = tmem_empty + 2;                  // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* up_full = b_full + 1;                     // [3] patches of the coarser FPN level (p.up_tma)
+  uint64_t* up_empty = up_full + 3;                   // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(up_empty + 3);
+  uint8_t* up_patch = reinterpret_cast<uint8_t*>(full) + TC_AUX_OFF;      // [3][TC_UP_SLOT], 512-byte aligned
   float* ss_stage = reinterpret_cast<float*>(tmem_slot + 2);      // [2][4][64] floats, 16-byte aligned
+  float* stg_all = ss_stage + 2 * 4 * TC_BN;                      // [8 warps][32][36] floats when p.staged
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x % p.tiles_n;
@@ -248,6 +538,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
     mbar_init(b_full, 1);
+    for (int s = 0; s < 3; ++s) { mbar_init(&up_full[s], 1); mbar_init(&up_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -268,9 +559,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       __syncwarp();
     }
-    int stage = 0, phase = 0;
-    for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n) {
+    int stage = 0, phase = 0, upi = 0;
+    for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++upi) {
       const TileOrigin o = tile_origin(p, tile_m);
+      if (EPI == EPI_STAGED_UP) {
+        const int us = upi % 3;
+        mbar_wait(&up_empty[us], (uint32_t)(((upi / 3) & 1) ^ 1));
+        if (elect_one()) {
+          mbar_expect_tx(&up_full[us], (uint32_t)(p.up_PW * p.up_PH * TC_BN * 4));
+          tma_load_4d(up_patch + (size_t)us * TC_UP_SLOT, &map_up, &up_full[us], tile_n * TC_BN, o.wo0 / 2 - 1, o.ho0 / 2 - 1, o.img);
+        }
+        __syncwarp();
+      }
       const int w_row0 = (p.w_img_rows ? o.img * p.w_img_rows : 0) + tile_n * nB;
       const int x0 = o.wo0 * p.stride - p.pad, y0 = o.ho0 * p.stride - p.pad, row0 = tile_m * TC_BM;
       int c = 0, cc = 0, kh = 0, kw = 0;                   // running chunk index / channel chunk / tap coordinates
@@ -299,6 +599,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (p.bk == 128) mma_role<PIECES, 4>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
     else if (p.bk == 64) mma_role<PIECES, 2>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
     else mma_role<PIECES, 1>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
+  } else if (EPI == EPI_SPIKE) {
+    epilogue_spike<PIECES>(p, ss_stage, tmem_full, tmem_empty, tmem_base, slot, tile_n, warp, lane);
+  } else if (EPI == EPI_STAGED || EPI == EPI_STAGED_UP) {
+    epilogue_staged<PIECES, EPI == EPI_STAGED_UP>(p, stg_all + (warp - 2) * TC_STG_FLOATS, tmem_full, tmem_empty, tmem_base, slot,
+                                                  tile_n, warp, lane, up_patch, up_full, up_empty);
   } else {
     // ===== epilogue (8 warps): warp w reads TMEM lanes [32*(w%4), +32) -- thread = one output row -- and one half
     // (32 channels) of the tile's columns.
@@ -521,6 +826,17 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   p.pieces = a->pieces; p.out_transposed = a->out_transposed; p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
   const int per_img_w = a->per_image_weights ? 1 : 0;
   p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
+  p.staged = (TC_EPI_WARPS == 8 && p.d_max == 8.f && !a->out_transposed && a->Cout % 4 == 0 && (a->out_f32 || a->residual || a->up_prev) &&
+              (!a->residual || (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0) &&
+              (!a->out_f32 || (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0) &&
+              (!a->out_spike || (reinterpret_cast<uintptr_t>(a->out_spike) & 3) == 0) &&
+              (reinterpret_cast<uintptr_t>(a->scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->shift) & 15) == 0 &&
+              (int64_t)p.M_total < (1ll << 31) && (!a->up_prev || (int64_t)a->n * a->up_H * a->up_W < (1ll << 31))) ? 1 : 0;
+  // fused FPN merge of an exact 2x coarser level: spatial 16x8 tiles, so that the tile's source pixels form one small
+  // box (TW/2 + 2 by TH/2 + 2) that the producer warp fetches with TMA next to the spike tile
+  const bool up2x = p.staged && a->up_prev && !per_img_w && Ho == 2 * a->up_H && Wo == 2 * a->up_W && Wo >= 8 && TC_EPI_WARPS == 8 &&
+                    a->Cout % 4 == 0 && (int64_t)a->n * Ho * Wo < (1ll << 31);
+  if (up2x) p.mode_conv = 1;
   const int nB = TC_BN * p.pieces;
   const int tiles_n = (a->Cout + TC_BN - 1) / TC_BN;
   if (per_img_w) {
@@ -569,10 +885,24 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   }
   p.tiles_n = tiles_n;
   p.tiles_m = tiles_m;
+  CUtensorMap map_up = map_b;
+  if (up2x) {
+    p.up_tma = 1; p.up_PW = p.TW / 2 + 2; p.up_PH = p.TH / 2 + 2;
+    S2F_REQUIRE(p.up_PW * p.up_PH * TC_BN * 4 <= TC_UP_SLOT && p.up_PW * p.up_PH <= 255, "gemm_i8_tc: FPN patch too large");
+    cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)a->up_W, (cuuint64_t)a->up_H, (cuuint64_t)a->n};
+    cuuint64_t strides[3] = {(cuuint64_t)a->Cout * 4, (cuuint64_t)a->up_W * a->Cout * 4, (cuuint64_t)a->up_H * a->up_W * a->Cout * 4};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BN, (cuuint32_t)p.up_PW, (cuuint32_t)p.up_PH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map_up, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->up_prev), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2F_ERR_CUDA, "gemm_i8_tc: cuTensorMapEncodeTiled(up_prev) failed (%s) code %lld", "", (long long)r);
+  }
 
   S2F_REQUIRE((int64_t)kpad * 8 * 64 * 129 < (1ll << 31), "gemm_i8_tc: K too large for the int32 plane merge");
   const int num_chunks = p.taps * p.cin_chunks;
-  const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 4 * TC_BN * sizeof(float);
+  const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 4 * TC_BN * sizeof(float) +
+                       (p.staged ? (size_t)TC_EPI_WARPS * TC_STG_FLOATS * sizeof(float) : 0) + (p.up_tma ? 3 * (size_t)TC_UP_SLOT : 0);
   const size_t budget = 226 * 1024 - fixed;
   const size_t b_all = (size_t)num_chunks * nB * p.bk;
   // weight-stationary when the whole K extent of the weight tile fits and still leaves >= 4 A stages
@@ -585,14 +915,12 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (p.stages < 2) p.stages = 2;
   size_t smem = (p.b_resident ? b_all : 0) + (size_t)p.stages * stage_bytes + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;          // never two CTAs on one SM: each allocates all 512 TMEM columns
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "gemm_i8_tc: smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  int epi = EPI_GENERIC;
+  if (p.up_tma) epi = EPI_STAGED_UP;
+  else if (p.staged) epi = EPI_STAGED;
+  else if (a->out_spike && !a->out_f32 && !a->residual && !a->up_prev && !a->out_transposed && !per_img_w && a->Cout % 16 == 0 &&
+           p.d_max == 8.f && (reinterpret_cast<uintptr_t>(a->out_spike) & 15) == 0)
+    epi = EPI_SPIKE;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -605,9 +933,29 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (per_n > tiles_m) per_n = tiles_m;
   p.ctas_per_n = per_n;
   const unsigned grid = (unsigned)(per_n * tiles_n);
-  if (p.pieces == 3) gemm_i8_tc_kernel<3><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-  else if (p.pieces == 2) gemm_i8_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-  else gemm_i8_tc_kernel<1><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  cudaError_t attr_err = cudaSuccess;
+#define S2F_TC_LAUNCH(P, E)                                                                                             \
+  do {                                                                                                                  \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      attr_err = cudaFuncSetAttribute(gemm_i8_tc_kernel<P, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      attr_set = attr_err == cudaSuccess;                                                                               \
+    }                                                                                                                   \
+    if (attr_err == cudaSuccess) gemm_i8_tc_kernel<P, E><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_up, p); \
+  } while (0)
+#define S2F_TC_EPI(P)                                               \
+  do {                                                              \
+    if (epi == EPI_SPIKE) S2F_TC_LAUNCH(P, EPI_SPIKE);              \
+    else if (epi == EPI_STAGED) S2F_TC_LAUNCH(P, EPI_STAGED);       \
+    else if (epi == EPI_STAGED_UP) S2F_TC_LAUNCH(P, EPI_STAGED_UP); \
+    else S2F_TC_LAUNCH(P, EPI_GENERIC);                             \
+  } while (0)
+  if (p.pieces == 3) S2F_TC_EPI(3);
+  else if (p.pieces == 2) S2F_TC_EPI(2);
+  else S2F_TC_EPI(1);
+#undef S2F_TC_EPI
+#undef S2F_TC_LAUNCH
+  if (attr_err != cudaSuccess) return fail(S2F_ERR_CUDA, "gemm_i8_tc: smem attribute: %s", cudaGetErrorString(attr_err));
   return check_launch("gemm_i8_tc_kernel");
 }
 

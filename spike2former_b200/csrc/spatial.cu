@@ -7,7 +7,7 @@ namespace s2f {
 // ------------------------------------------------------------------------------------------------
 // Depthwise k x k, stride 1, 'same' padding (or no padding when no_pad, output shrinks by k-1).
 // One thread = a strip of TW consecutive output pixels of one row x 4 channels.  Per kernel row it loads the
-// TW + k - 1 input pixels once (one 32-bit word = 4 int8 channels, unpacked with PRMT + FADD instead of I2F) and the
+// TW + k - 1 input pixels once (one 32-bit word = 4 int8 channels, one PRMT per byte, see unpack4) and the
 // k weight vectors once, so the inner loop is ~65 % FFMA.  Threads run over channels fastest: every warp access is a
 // contiguous row segment.  Weights are tap-major [k*k, C].  fp32 accumulation in the reference's tap order (kh, kw).
 // One input pixel x 4 channels as raw bits (int8: one 32-bit word; fp32: a float4), loaded unconditionally from a clamped
@@ -16,14 +16,22 @@ struct Raw8 { uint32_t w; };
 struct Raw32 { float4 v; };
 __device__ __forceinline__ Raw8 load_raw(const int8_t* p) { return Raw8{__ldg(reinterpret_cast<const uint32_t*>(p))}; }
 __device__ __forceinline__ Raw32 load_raw(const float* p) { return Raw32{__ldg(reinterpret_cast<const float4*>(p))}; }
+// int8 levels enter the FFMAs as fp32 *denormals*: the isolated byte b, reinterpreted as a float, is b * 2^-149, and
+// FFMA takes denormal operands at full rate (no -ftz in this build).  With the weights pre-multiplied by 2^DW_WEXP every
+// product and partial sum is the reference's value times 2^(DW_WEXP-149) -- a power of two, so each rounding is the
+// same as in the unscaled fp32 sum -- and the final affine multiplies by 2^(149-DW_WEXP).  One PRMT per byte instead of
+// PRMT + FADD (or I2F).
+constexpr int DW_WEXP = 100;
 __device__ __forceinline__ void unpack4(Raw8 r, bool ok, float& x0, float& x1, float& x2, float& x3) {
   const uint32_t raw = ok ? r.w : 0u;
-  // levels are 0..127: 0x4B0000xx is the float 8388608 + xx
-  x0 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7650)) - 8388608.f;
-  x1 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7651)) - 8388608.f;
-  x2 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7652)) - 8388608.f;
-  x3 = __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7653)) - 8388608.f;
+  x0 = __uint_as_float(__byte_perm(raw, 0u, 0x4440));
+  x1 = __uint_as_float(__byte_perm(raw, 0u, 0x4441));
+  x2 = __uint_as_float(__byte_perm(raw, 0u, 0x4442));
+  x3 = __uint_as_float(__byte_perm(raw, 0u, 0x4443));
 }
+template <typename AT> struct DwScale;
+template <> struct DwScale<int8_t> { static constexpr float w_pre = 0x1p100f, post = 0x1p49f; };   // 2^DW_WEXP, 2^(149-DW_WEXP)
+template <> struct DwScale<float> { static constexpr float w_pre = 1.f, post = 1.f; };
 __device__ __forceinline__ void unpack4(Raw32 r, bool ok, float& x0, float& x1, float& x2, float& x3) {
   x0 = ok ? r.v.x : 0.f; x1 = ok ? r.v.y : 0.f; x2 = ok ? r.v.z : 0.f; x3 = ok ? r.v.w : 0.f;
 }
@@ -32,7 +40,7 @@ template <> struct RawOf<int8_t> { using type = Raw8; };
 template <> struct RawOf<float> { using type = Raw32; };
 
 template <typename AT, int KS, int TW, int CT>      // CT: compile-time channel count (0 = use the runtime C)
-__global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, float a_scale,
+__global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a, float a_scale,
                                                      const float* __restrict__ w_tap, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, float* __restrict__ out_f32,
                                                      int8_t* __restrict__ out_spike, int n, int H, int W, int C_rt, int Ho,
@@ -70,9 +78,11 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
     }
 #pragma unroll
     for (int kh = 0; kh < KS; ++kh) {
+      // rows outside the map are loaded from the clamped row and masked: no branch, so the loads of all kernel rows can
+      // be scheduled ahead of the FFMAs of the first one
       const int hi = ho - pad + kh;
-      if (hi < 0 || hi >= H) continue;
-      const AT* row = base + (int64_t)hi * W * C;
+      const bool row_ok = hi >= 0 && hi < H;
+      const AT* row = base + (int64_t)min(max(hi, 0), H - 1) * W * C;
       RT raw[TW + KS - 1];
       if (CT && interior) {
         const AT* row0 = row + wi0 * CT;
@@ -84,11 +94,16 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
       }
       float4 wv[KS];
 #pragma unroll
-      for (int kw = 0; kw < KS; ++kw) wv[kw] = __ldg(reinterpret_cast<const float4*>(w_tap + (kh * KS + kw) * C + c));
+      for (int kw = 0; kw < KS; ++kw) {
+        wv[kw] = __ldg(reinterpret_cast<const float4*>(w_tap + (kh * KS + kw) * C + c));
+        if (sizeof(AT) == 1) {                          // exact: a power of two, |w| * 2^100 stays far below FLT_MAX
+          wv[kw].x *= DwScale<AT>::w_pre; wv[kw].y *= DwScale<AT>::w_pre; wv[kw].z *= DwScale<AT>::w_pre; wv[kw].w *= DwScale<AT>::w_pre;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < TW + KS - 1; ++i) {
         float x0, x1, x2, x3;
-        unpack4(raw[i], (valid >> i) & 1u, x0, x1, x2, x3);
+        unpack4(raw[i], row_ok && ((valid >> i) & 1u), x0, x1, x2, x3);
 #pragma unroll
         for (int kw = 0; kw < KS; ++kw) {
           const int t = i - kw;                       // compile-time after unrolling
@@ -100,10 +115,11 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const AT* __restrict__ a, f
       }
     }
     // y = acc * (a_scale * scale) + shift: one FFMA per output (a_scale is a power of two, so the product is exact)
-    float4 sc = make_float4(a_scale, a_scale, a_scale, a_scale), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float asc = a_scale * DwScale<AT>::post;       // a_scale is a power of two as well
+    float4 sc = make_float4(asc, asc, asc, asc), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (scale) {
       const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c));
-      sc = make_float4(s4.x * a_scale, s4.y * a_scale, s4.z * a_scale, s4.w * a_scale);
+      sc = make_float4(s4.x * asc, s4.y * asc, s4.z * asc, s4.w * asc);
       sh = __ldg(reinterpret_cast<const float4*>(shift + c));
     }
     const int64_t o0 = (((int64_t)img * Ho + ho) * Wo + wo0) * C + c;

@@ -76,6 +76,27 @@ def test_gemm_tc_transposed_and_no_residual():
     assert torch.equal(os_, torch.round(torch.clamp(of, 0, 8)).to(torch.int8))
 
 
+@pytest.mark.parametrize("cin,cout,k,H,W", [(256, 256, 1, 32, 32), (368, 100, 1, 10, 10), (64, 64, 3, 12, 20), (32, 256, 1, 64, 64)])
+def test_gemm_tc_epilogue_paths_agree(cin, cout, k, H, W):
+    """Spike-only launches keep the row-per-lane epilogue, fp32 / residual launches go through the shared-memory
+    transposed (coalesced) epilogue: same accumulators, same affine, so the levels must be identical."""
+    g = torch.Generator().manual_seed(11)
+    n = 3
+    a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8).cuda()
+    w = torch.randn(cout, k * k * cin, generator=g) / (cin * k * k) ** 0.5
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) + 1
+    packed, rowscale = ops.pack_weights_i8(w, k * k, cin, 3)
+    kw = dict(n=n, H=H, W=W, Cin=cin, Cout=cout, scale=(sc * rowscale / 8).cuda(), shift=sh.cuda(), k=k, pad=(k - 1) // 2)
+    _, s_only = ops.gemm_tc(a, packed.cuda(), want_spike=True, **kw)
+    f_both, s_both = ops.gemm_tc(a, packed.cuda(), want_f32=True, want_spike=True, **kw)
+    f_only, _ = ops.gemm_tc(a, packed.cuda(), want_f32=True, **kw)
+    f_tr, s_tr = ops.gemm_tc(a, packed.cuda(), want_f32=True, want_spike=True, transposed=True, **kw)
+    assert torch.equal(s_only, s_both)
+    assert torch.equal(f_only, f_both)
+    assert torch.equal(f_tr.view(n, cout, H * W).permute(0, 2, 1).reshape(n, H, W, cout), f_both)
+    assert torch.equal(s_tr.view(n, cout, H * W).permute(0, 2, 1).reshape(n, H, W, cout), s_both)
+
+
 def test_gemm_tc_matches_cuda_core_kernel_bitwise_spikes():
     """Same inputs through both kernels: fp32 outputs agree to fp32 rounding, spikes differ only at near-ties."""
     g = torch.Generator().manual_seed(5)

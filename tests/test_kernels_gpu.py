@@ -187,6 +187,22 @@ def test_dwconv_vs_torch(k, spike_in):
     assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
 
 
+@pytest.mark.parametrize("k,C,H,W", [(3, 256, 20, 37), (5, 512, 9, 16), (7, 64, 33, 40), (7, 24, 12, 12)])
+def test_dwconv_spike_operands_bitwise_equal_to_fp32_operands(k, C, H, W):
+    """The int8 path feeds the levels to the FFMAs as fp32 denormals against 2^100-scaled weights; every rounding must
+    be the one the plain fp32 sum of w * (level / 8) makes, so both operand types give identical bits."""
+    g = gen(21)
+    n = 2
+    a = _levels((n, H, W, C), g)
+    w_tap = (torch.randn(k * k, C, generator=g) / k).cuda()
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    f_i, s_i = ops.dwconv(a.cuda(), w_tap, n=n, H=H, W=W, C_=C, k=k, scale=sc, shift=sh, want_f32=True, want_spike=True)
+    f_f, s_f = ops.dwconv((a.float() / 8).cuda(), w_tap, n=n, H=H, W=W, C_=C, k=k, scale=sc, shift=sh, want_f32=True,
+                          want_spike=True)
+    assert torch.equal(f_i, f_f)
+    assert torch.equal(s_i, s_f)
+
+
 @pytest.mark.parametrize("n,Nq,Nk,heads,d", [(2, 64, 64, 4, 16), (1, 20, 300, 4, 16), (2, 100, 1024, 8, 32), (1, 64, 64, 8, 45)])
 def test_linear_attn_exact(n, Nq, Nk, heads, d):
     """(Q K^T) V == Q (K^T V) on integer levels; compared with the reference's op order in float64."""
