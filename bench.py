@@ -6,8 +6,9 @@
 One "step" = one forward pass of the whole hot path (SDTv2 backbone + DCN pixel decoder + MaskFormer
 head -> seg logits [B,150,512,512]) over one batch of B synthetic 512x512 images per GPU.
   value : whole-job images/s with the input batches already resident in HBM (CUDA events, max over ranks)
-  e2e   : the same through the public API with HOST buffers: pinned fp32 images -> H2D -> forward ->
-          argmax label map (uint8) -> D2H, every step, inside the timed region
+  e2e   : the same through the public API with HOST buffers: pinned uint8 images (the dataset format the reference's
+          SegDataPreProcessor receives) -> H2D -> normalise + forward -> argmax label map (uint8) -> D2H, every step,
+          inside the timed region
   roofline : the dominant kernel class (spike GEMM / conv) timed live with CUDA events on the launch stream
   cpu_baseline : the oracle port (CPU restatement of the reference, pinned bit-exact to it) on this box's host
           cores over a bounded sample, rank 0, N=1 only
@@ -96,16 +97,22 @@ def cpu_reference_run(steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 3, H, W, generator=g)
+    u8 = [torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8)]
+    dp = cfg["data_preprocessor"]
+
+    def one():       # SegDataPreProcessor + encode_decode + argmax, as BaseSegmentor.test_step does
+        x = port.data_preprocess(u8, mean=dp["mean"], std=dp["std"], bgr_to_rgb=dp["bgr_to_rgb"])
+        return port.predict(port.Ctx(P), cfg, x).argmax(1)
+
     with torch.no_grad():
         for _ in range(warmup):
-            port.predict(port.Ctx(P), cfg, x)
+            one()
         t0 = time.perf_counter()
         for _ in range(steps):
-            port.predict(port.Ctx(P), cfg, x)
+            one()
         dt = time.perf_counter() - t0
     return dict(value=steps / dt, unit="images/s", cores=cores, kind="port",
-                sample=f"{steps} forwards of one 512x512 image (batch 1), fp32, torch CPU {torch.__version__}, "
+                sample=f"{steps} x (preprocess + forward + argmax) of one 512x512 uint8 image (batch 1), fp32, torch CPU {torch.__version__}, "
                        f"{cores} threads, after {warmup} warm-up"), dt / steps * 1e3
 
 
@@ -229,8 +236,8 @@ def main():
     B = args.batch
     NBUF = 4                                   # rotate input batches: 4 x B x 3 MB > L2 for B >= 12; the per-step
     g = torch.Generator().manual_seed(1000 + rank)   # working set (GBs of activations) thrashes L2 anyway
-    host = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(NBUF)]
-    devin = [h.to(dev) for h in host]
+    devin = [torch.randn(B, 3, H, W, generator=g).to(dev) for _ in range(NBUF)]      # resident fp32 batches (`value`)
+    host = [torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
 
     def barrier():
         if dist is not None:
@@ -241,10 +248,11 @@ def main():
         with torch.no_grad():
             return seg.encode_decode(devin[i % NBUF])
 
-    # end-to-end: pinned host batch -> H2D (copy stream, double buffered so the copy of step i+1 overlaps the forward of
-    # step i) -> forward with fused argmax -> D2H of the uint8 label map; all of it inside the timed region
+    # end-to-end: pinned uint8 host batch -> H2D (copy stream, double buffered so the copy of step i+1 overlaps the
+    # forward of step i) -> SegDataPreProcessor kernel + forward with fused argmax (one CUDA graph) -> D2H of the uint8
+    # label map; all of it inside the timed region
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty(B, 3, H, W, device=dev) for _ in range(2)]
+    stage = [torch.empty(B, 3, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     host_outs = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -319,9 +327,11 @@ def main():
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
                    "weights": "seeded random init + shipped calibration statistics (spike2former_b200/synth.py)",
                    "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2",
+                   "value_input": "fp32 [B,3,512,512] resident in HBM (encode_decode -> fp32 logits [B,150,512,512])",
+                   "e2e_input": "uint8 [B,3,512,512] pinned host memory -> SegDataPreProcessor + predict -> uint8 labels -> host",
                    "alg_gflop_per_image": ALG_GFLOP_PER_IMG},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W,
                 "d2h_bytes_per_step": B * H * W},
         "gpu_launches": int(launches),
         "model_tflops": value * ALG_GFLOP_PER_IMG / 1e3,

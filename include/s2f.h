@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 3 */
+S2F_API int s2f_abi_version(void);   /* currently 4 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -173,6 +173,24 @@ S2F_API int s2f_upsample_add_lif(const float* cur, const float* prev, int8_t* ou
  * out_f32 = y, out_spike = NI-LIF(y) (either optional).  N % 4 == 0, C % 4 == 0. */
 S2F_API int s2f_affine_add_lif(const float* x, const float* scale, const float* residual, float* out_f32,
                        int8_t* out_spike, int64_t N, int C, float d_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Callers either side of the path.
+ *
+ * s2f_preprocess_u8 replaces SegDataPreProcessor.forward (mmseg/models/data_preprocessor.py:109-152) and the
+ * right/bottom padding of stack_batch (mmseg/utils/misc.py:77-93) for n equally sized uint8 images:
+ *   img  [n,3,H,W] (chw = 1: what PackSegInputs hands the preprocessor) or [n,H,W,3] (chw = 0: decoder output order)
+ *   out  fp32 [n,Hp,Wp,3] channels-last -- the layout the stem reads --
+ *        out[y,x,c] = (float(img[y,x,swap_rb ? 2-c : c]) - mean[c]) / std[c]   for y < H, x < W, else pad_val.
+ * mean / std are HOST pointers to 3 floats (NULL, NULL: no normalisation, data_preprocessor.py:125).  Bit-exact with
+ * the reference's fp32 sub + div. */
+S2F_API int s2f_preprocess_u8(const uint8_t* img, int chw, float* out, int n, int H, int W, int Hp, int Wp,
+                      const float* mean, const float* std, int swap_rb, float pad_val, void* stream);
+
+/* Histogram of spike levels: hist16[l] += #{i : levels[i] == l}, l = 0..15 (uint64, accumulated: zero it first).
+ * The firing-rate census of tools/cal_firing_num.py:140-171 (firing rate = 1 - hist[0]/N, mean level = sum l*hist[l]/N)
+ * taken from the int8 levels the kernels emit.  levels must be 16-byte aligned. */
+S2F_API int s2f_level_hist(const int8_t* levels, int64_t N, unsigned long long* hist16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Head tail.  sigmoid -> NI-LIF of the stacked decoder states (maskformer_head.py:572-573):

@@ -432,3 +432,33 @@ def count_ties(x, d_max=8.0):
     """Pre-activations that sit exactly on a rounding tie inside the clamp range."""
     fr = x - torch.floor(x)
     return int(((fr == 0.5) & (x > 0) & (x < d_max)).sum())
+
+
+# --------------------------------------------------------------------------- data preprocessor (SURVEY.md section 8f-2)
+def data_preprocess(inputs, mean=None, std=None, bgr_to_rgb=False, rgb_to_bgr=False, size=None, size_divisor=None,
+                    pad_val=0):
+    """SegDataPreProcessor.forward (mmseg/models/data_preprocessor.py:109-152) for a list of uint8 [3,H,W] images:
+    channel flip (:121-122), .float() (:124), (x - mean) / std (:125-126), then stack_batch's right/bottom padding
+    with pad_val (mmseg/utils/misc.py:68-93) -> fp32 [B,3,Hp,Wp]."""
+    if bgr_to_rgb or rgb_to_bgr:
+        inputs = [i[[2, 1, 0], ...] for i in inputs]
+    inputs = [i.float() for i in inputs]
+    if mean is not None:
+        m = torch.tensor(mean).view(-1, 1, 1)
+        sd = torch.tensor(std).view(-1, 1, 1)
+        inputs = [(i - m) / sd for i in inputs]
+    hmax = max(i.shape[-2] for i in inputs)
+    wmax = max(i.shape[-1] for i in inputs)
+    if size_divisor is not None and size_divisor > 1:
+        hmax = (hmax + size_divisor - 1) // size_divisor * size_divisor
+        wmax = (wmax + size_divisor - 1) // size_divisor * size_divisor
+    out = []
+    for t in inputs:
+        if size is not None:
+            pw, ph = max(size[-1] - t.shape[-1], 0), max(size[-2] - t.shape[-2], 0)
+        elif size_divisor is not None:
+            pw, ph = max(wmax - t.shape[-1], 0), max(hmax - t.shape[-2], 0)
+        else:
+            pw = ph = 0
+        out.append(F.pad(t, (0, pw, 0, ph), value=pad_val))
+    return torch.stack(out, dim=0)

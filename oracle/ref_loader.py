@@ -279,3 +279,22 @@ class SpikeTap:
     def close(self):
         for h in self.handles:
             h.remove()
+
+
+# --------------------------------------------------------------------------- data preprocessor
+class _BaseDataPreprocessor(nn.Module):
+    """mmengine.model.BaseDataPreprocessor stand-in: cast_data is the identity on CPU."""
+
+    def cast_data(self, data):
+        return data
+
+
+def load_data_preprocessor():
+    """Execute mmseg/utils/misc.py (stack_batch) and mmseg/models/data_preprocessor.py; returns the reference class."""
+    load()
+    sys.modules["mmengine.model"].BaseDataPreprocessor = _BaseDataPreprocessor
+    _shell("mmseg.utils.typing_utils", SampleList=list)       # misc.py:8 `from .typing_utils import SampleList`
+    misc = _exec("mmseg.utils.misc", "mmseg/utils/misc.py")
+    sys.modules["mmseg.utils"].stack_batch = misc.stack_batch
+    mod = _exec("mmseg.models.data_preprocessor_ref", "mmseg/models/data_preprocessor.py")
+    return mod.SegDataPreProcessor

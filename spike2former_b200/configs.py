@@ -18,6 +18,9 @@ def _model(embed_dim4, feat, num_classes, num_queries, enc_ffn, dec_ffn, num_hea
     ps_dim = feat // 2
     return dict(
         type="EncoderDecoder",
+        # cfg:13-20 (both the ADE20K and the Cityscapes config): ImageNet statistics, BGR -> RGB, no test-time padding
+        data_preprocessor=dict(type="SegDataPreProcessor", size=(img, img), mean=[123.675, 116.28, 103.53],
+                               std=[58.395, 57.12, 57.375], bgr_to_rgb=True, pad_val=0, seg_pad_val=255),
         backbone=dict(
             type="Spiking_vit_MetaFormer", img_size_h=img, img_size_w=img, patch_size=16, embed_dim=list(embed_dim4),
             num_heads=num_heads, mlp_ratios=4, in_channels=3, num_classes=num_classes, qkv_bias=False, depths=8,

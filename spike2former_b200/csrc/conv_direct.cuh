@@ -20,8 +20,8 @@ struct ConvP {
   int out_transposed, generic;
 };
 
-template <int PX, int NC, bool IS1X1>
-__global__ void __launch_bounds__(256) conv_direct_kernel(const ConvP p) {
+template <int PX, int NC, bool IS1X1, int CIN_CT = 0, int KW_CT = 0>      // CIN_CT / KW_CT: compile-time Cin and KW of the stem (0 = run time)
+__global__ void __launch_bounds__(256, CIN_CT > 0 ? 2 : 1) conv_direct_kernel(const ConvP p) {
   extern __shared__ __align__(16) float Ws[];                    // [K][NC], zero beyond Cout
   const int co0 = blockIdx.y * NC;
   for (int e = threadIdx.x; e < p.K * NC; e += blockDim.x) {
@@ -78,6 +78,41 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const ConvP p) {
         hb[i] = (r / p.Wo) * p.stride - p.pad;
         wb[i] = (r % p.Wo) * p.stride - p.pad;
       }
+      if constexpr (CIN_CT > 0) {
+        // the stem (Cin = 3, 7x7): one kernel row = KW * Cin k-steps, fully unrolled so that its 2 * 21 loads are issued
+        // back to back ahead of the 21 * 64 FFMAs (loads from clamped addresses, masked afterwards)
+        for (int kh = 0; kh < p.KH; ++kh) {
+          float av[PX][KW_CT * CIN_CT];
+#pragma unroll
+          for (int i = 0; i < PX; ++i) {
+            const int hi = hb[i] + kh;
+            const bool rok = hi >= 0 && hi < p.H;
+            const float* rowp = A + ((int64_t)img[i] * p.H + (rok ? hi : 0)) * p.W * CIN_CT;
+#pragma unroll
+            for (int kw = 0; kw < KW_CT; ++kw) {
+              const int wi = wb[i] + kw;
+              const bool ok = rok && wi >= 0 && wi < p.W;
+              const float* src = rowp + (ok ? wi : 0) * CIN_CT;
+#pragma unroll
+              for (int ci = 0; ci < CIN_CT; ++ci) { const float v = __ldg(src + ci); av[i][kw * CIN_CT + ci] = ok ? v : 0.f; }
+            }
+          }
+          const float* wrow = Ws + kh * (KW_CT * CIN_CT) * NC;
+#pragma unroll
+          for (int kk = 0; kk < KW_CT * CIN_CT; ++kk) {
+            const float4* wr = reinterpret_cast<const float4*>(wrow + kk * NC);
+#pragma unroll
+            for (int c4 = 0; c4 < NC / 4; ++c4) {
+              const float4 w = wr[c4];
+#pragma unroll
+              for (int i = 0; i < PX; ++i) {
+                acc[i][4 * c4] = fmaf(av[i][kk], w.x, acc[i][4 * c4]); acc[i][4 * c4 + 1] = fmaf(av[i][kk], w.y, acc[i][4 * c4 + 1]);
+                acc[i][4 * c4 + 2] = fmaf(av[i][kk], w.z, acc[i][4 * c4 + 2]); acc[i][4 * c4 + 3] = fmaf(av[i][kk], w.w, acc[i][4 * c4 + 3]);
+              }
+            }
+          }
+        }
+      } else {
       int k = 0;
       for (int kh = 0; kh < p.KH; ++kh)
         for (int kw = 0; kw < p.KW; ++kw) {
@@ -105,6 +140,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const ConvP p) {
             }
           }
         }
+      }
     }
     // ---- epilogue: same op order as conv_simt_kernel
 #pragma unroll
@@ -157,6 +193,9 @@ inline bool launch_conv_direct(const ConvP& p, bool a_is_spike, cudaStream_t st)
   if (is1x1) {
     cudaFuncSetAttribute(conv_direct_kernel<PX, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     conv_direct_kernel<PX, NC, true><<<grid, 256, smem, st>>>(p);
+  } else if (p.Cin == 3 && p.KW == 7) {
+    cudaFuncSetAttribute(conv_direct_kernel<PX, NC, false, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    conv_direct_kernel<PX, NC, false, 3, 7><<<grid, 256, smem, st>>>(p);
   } else {
     cudaFuncSetAttribute(conv_direct_kernel<PX, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     conv_direct_kernel<PX, NC, false><<<grid, 256, smem, st>>>(p);

@@ -13,6 +13,7 @@ them, which is how the teacher-forced parity tests drive each unit with the orac
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import torch
@@ -299,6 +300,43 @@ class NullProbe:
 NOPROBE = NullProbe()
 
 
+class FiringCensus:
+    """Firing-rate / energy census (tools/cal_firing_num.py:140-171 of the reference hooks every neuron and averages
+    its output): a probe that histograms the int8 levels of every neuron with s2f_level_hist -- one pass over 1 byte
+    per neuron, no fp32 spike tensor.  `report()` -> {neuron: elements, hist[0..8], firing_rate (non-zero fraction),
+    mean_level (the reference's mean output x 8)}.  Being a probe it disables the fusions that hide a neuron's
+    levels from the host (like the teacher-forcing probe of the tests), so it is an analysis mode, not the fast path."""
+    active = True
+
+    def __init__(self, prefix="", table=None, keep=False, kept=None):
+        self.prefix, self.table, self.keep = prefix, ({} if table is None else table), keep
+        self.kept = {} if kept is None else kept
+
+    def scoped(self, prefix):
+        return FiringCensus(self.prefix + prefix, self.table, self.keep, self.kept)
+
+    def spike(self, name, t, layout="cm"):
+        full = self.prefix + name
+        tc = t if t.is_contiguous() else t.contiguous()
+        self.table[full] = (ops.level_hist(tc, self.table[full][0] if full in self.table else None),
+                            (self.table[full][1] if full in self.table else 0) + t.numel())
+        if self.keep:
+            self.kept[full] = tc.clone()
+        return t
+
+    def real(self, name, t, layout="cm"):
+        return t
+
+    def report(self):
+        out = {}
+        for name, (hist, n) in self.table.items():
+            h = hist.cpu().tolist()
+            fired = n - h[0]
+            out[name] = dict(elements=n, hist=h, firing_rate=fired / max(n, 1),
+                             mean_level=sum(i * c for i, c in enumerate(h)) / max(n, 1))
+        return out
+
+
 # ------------------------------------------------------------------------------------------------ backbone
 def _conv_block(L, name, s, sp, n, H, W, pr):
     """MS_ConvBlock (sdtv2.py:207-219) on stream s with spike twin sp = LIF(s)."""
@@ -444,9 +482,15 @@ def _sepconv_spike(L, prefix, key, sp, n, H, W, pr, residual=None, want_spike=Tr
     return L[prefix + ".pw2"](a, n, H, W, residual=residual, f32=True, spike=want_spike)
 
 
-def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True):
+OVERLAP_FPN_TAIL = _os.environ.get("S2F_OVERLAP", "1") != "0"
+
+
+def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True, side_stream=None):
     """DCNTransformerEncoderPixelDecoder.forward (pixel_decoder.py:417-472).
-    Returns (mask_feature fp32 [n,H1,W1,C], memory levels, [y32, y64, y128] fp32 channels-last)."""
+    Returns (mask_feature fp32 [n,H1,W1,C], memory levels, [y32, y64, y128] fp32 channels-last).
+    side_stream: the finest FPN level (lateral + merge + output conv at H/2 x W/2, which only feeds mask_feature) is
+    enqueued there, so that it runs beside the transformer decoder's many small launches; the caller joins the stream
+    before it touches the first return value."""
     plan = plan_of(model, PixelDecoderPlan)
     L, pr = plan.layers, probe
     pd = "pixel_decoder."
@@ -492,26 +536,30 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True):
     outs = [y]
     hp, wp = H, W
     for i in range(model.num_inputs - 2, -1, -1):
-        s_i, sp_i = feats[i]
-        _, h, w, _ = s_i.shape
-        sp_i = pr.spike(pd + f"lateral_convs_spike.{i}", sp_i)
-        lat = L[f"lateral.{i}"]
-        if not pr.active and lat.tc is not None and n * h * w >= TC_MIN_ROWS and C % 16 == 0:
-            # lateral 1x1 + BN, bilinear upsample of the coarser level, add and NI-LIF in one launch: the fp32 lateral
-            # map (1 GB at batch 16 for the 256^2 level) is never written
-            _, ys = lat(sp_i, n, h, w, spike=True, up_prev=y)
-        else:
-            cur, _ = lat(sp_i, n, h, w, f32=True)
-            ys, yf = ops.upsample_add_lif(cur, y, n=n, H=h, W=w, Hp=hp, Wp=wp, C_=C, want_f32=pr.active)
-            if pr.active:
-                pr.real(pd + f"output_convs_spike.{i}", yf)
-        ys = pr.spike(pd + f"output_convs_spike.{i}", ys)
-        # the finest level only feeds mask_feature_spike: its fp32 map (1 GB at batch 16) is not materialised
-        y, ysp = L[f"output.{i}"](ys, n, h, w, f32=(i > 0 or pr.active), spike=(i == 0))
-        if y is not None:
-            y = pr.real(pd + f"y{model.num_inputs - 1 - i}", y)
-        outs.append(y)
-        hp, wp = h, w
+        forked = side_stream is not None and i == 0 and not pr.active and not want_mask_feature
+        if forked:
+            side_stream.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(side_stream) if forked else contextlib.nullcontext()):
+            s_i, sp_i = feats[i]
+            _, h, w, _ = s_i.shape
+            sp_i = pr.spike(pd + f"lateral_convs_spike.{i}", sp_i)
+            lat = L[f"lateral.{i}"]
+            if not pr.active and lat.tc is not None and n * h * w >= TC_MIN_ROWS and C % 16 == 0:
+                # lateral 1x1 + BN, bilinear upsample of the coarser level, add and NI-LIF in one launch: the fp32 lateral
+                # map (1 GB at batch 16 for the 256^2 level) is never written
+                _, ys = lat(sp_i, n, h, w, spike=True, up_prev=y)
+            else:
+                cur, _ = lat(sp_i, n, h, w, f32=True)
+                ys, yf = ops.upsample_add_lif(cur, y, n=n, H=h, W=w, Hp=hp, Wp=wp, C_=C, want_f32=pr.active)
+                if pr.active:
+                    pr.real(pd + f"output_convs_spike.{i}", yf)
+            ys = pr.spike(pd + f"output_convs_spike.{i}", ys)
+            # the finest level only feeds mask_feature_spike: its fp32 map (1 GB at batch 16) is not materialised
+            y, ysp = L[f"output.{i}"](ys, n, h, w, f32=(i > 0 or pr.active), spike=(i == 0))
+            if y is not None:
+                y = pr.real(pd + f"y{model.num_inputs - 1 - i}", y)
+            outs.append(y)
+            hp, wp = h, w
     if pr.active:
         pr.real(pd + "mask_feature_spike", y)
     ysp = pr.spike(pd + "mask_feature_spike", ysp)
@@ -558,7 +606,12 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
     Returns (cls [L,n,nq,K+1], mask levels int8 [L,n,nq,C], mask_feature [n,h,w,C]); L = 1 when last_only."""
     pd_model = model.pixel_decoder
     pr = probe
-    mf, memory, ms = pixel_decoder_forward(pd_model, feats, pr, want_mask_feature=False)   # mf: mask_feature_spike levels
+    side = None
+    if OVERLAP_FPN_TAIL and not pr.active and ops._PROF is None:
+        side = getattr(model, "_side_stream", None)
+        if side is None or side.device != feats[0][0].device:
+            side = model._side_stream = torch.cuda.Stream(device=feats[0][0].device)
+    mf, memory, ms = pixel_decoder_forward(pd_model, feats, pr, want_mask_feature=False, side_stream=side)   # mf: mask_feature_spike levels
     plan = plan_of(model, HeadPlan)
     L = plan.layers
     n = mf.shape[0]
@@ -622,6 +675,9 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
         pr.real("mask_embed_spike", m_f.view(Ls, n, nq, dim), "same")
     me = pr.spike("mask_embed_spike", me.view(Ls, n, nq, dim), "same")
     cls = cls.view(Ls, n, nq, -1)
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)              # mask_feature_spike is complete from here on
+        mf.record_stream(torch.cuda.current_stream())
     return cls, me, mf
 
 
@@ -736,6 +792,13 @@ def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
     """EncoderDecoder.encode_decode (encoder_decoder.py:125-133): internal tensors go straight to the head."""
     if seg.backbone.T != 1:
         raise NotImplementedError("T > 1 end-to-end inference is not used by any Spike2Former config")
+    if img.dtype == torch.uint8:
+        # SegDataPreProcessor fused in front of the stem (SURVEY.md section 8f-2): uint8 -> normalised channels-last fp32
+        pre = getattr(seg, "data_preprocessor", None)
+        if pre is None:
+            raise RuntimeError("uint8 input needs a data_preprocessor (mean / std / bgr_to_rgb) on the segmentor")
+        tc = pre.test_cfg or {}
+        img = pre.normalized(img, tc.get("size", None), tc.get("size_divisor", None)).permute(0, 3, 1, 2)
     feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if probe.active else probe)
     pr = probe.scoped("decode_head.") if probe.active else probe
     return _predict_from(seg.decode_head, feats, tuple(img.shape[-2:]), pr, labels)

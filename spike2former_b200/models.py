@@ -8,6 +8,7 @@ as the reference:
   MaskFormerHead                      Segmentation/mmseg/models/decode_heads/maskformer_head.py:22-180
                                       (+ mmdet parent dense_heads/maskformer_head.py:68-168, 498-586)
   EncoderDecoder (inference subset)   Segmentation/mmseg/models/segmentors/encoder_decoder.py:118-133
+  SegDataPreProcessor                 Segmentation/mmseg/models/data_preprocessor.py:14-152 (+ utils/misc.py:30-110)
 
 The modules own the parameters; the arithmetic is executed by engine.py on the
 sm_100a kernels.  There is no CPU path: calling forward on CPU tensors raises.
@@ -162,6 +163,89 @@ class MaskFormerHead(_Engined):
 
 
 @register_everywhere
+class SegDataPreProcessor(nn.Module):
+    """uint8 images -> normalised fp32 batch, on the device (data_preprocessor.py:14-152).
+
+    Same constructor keywords as the reference.  `forward(data, training)` takes `data['inputs']` as a list of uint8
+    [3,H,W] tensors (what PackSegInputs produces) or an already stacked uint8 [B,3,H,W] / [B,H,W,3] batch and returns
+    `dict(inputs=fp32 [B,3,Hp,Wp], data_samples=...)`.  The returned batch is an NCHW *view* of channels-last memory --
+    the layout the stem kernel reads -- so the backbone consumes it without a copy."""
+
+    def __init__(self, mean=None, std=None, size=None, size_divisor=None, pad_val=0, seg_pad_val=255, bgr_to_rgb=False,
+                 rgb_to_bgr=False, batch_augments=None, test_cfg=None):
+        super().__init__()
+        assert not (bgr_to_rgb and rgb_to_bgr), "`bgr2rgb` and `rgb2bgr` cannot be set to True at the same time"
+        self.size, self.size_divisor, self.pad_val, self.seg_pad_val = size, size_divisor, pad_val, seg_pad_val
+        self.channel_conversion = rgb_to_bgr or bgr_to_rgb
+        if mean is not None:
+            assert std is not None, ("To enable the normalization in preprocessing, please specify both `mean` and `std`.")
+            self._enable_normalize = True
+            self.register_buffer("mean", torch.tensor(mean).view(-1, 1, 1), False)
+            self.register_buffer("std", torch.tensor(std).view(-1, 1, 1), False)
+            # host copies of the fp32 buffer values: the kernel takes them by value (no device read during graph capture)
+            self._mean_host, self._std_host = self.mean.flatten().tolist(), self.std.flatten().tolist()
+        else:
+            self._enable_normalize = False
+        if batch_augments is not None:
+            raise NotImplementedError("batch_augments are training-time host glue (SURVEY.md section 2: OUT)")
+        self.batch_augments = None
+        self.test_cfg = test_cfg
+
+    def _padded_size(self, H, W, size, size_divisor):
+        if size is not None:
+            assert size_divisor is None, "only one of size and size_divisor should be valid"
+            return max(H, int(size[-2])), max(W, int(size[-1]))
+        if size_divisor is not None and size_divisor > 1:
+            return (H + size_divisor - 1) // size_divisor * size_divisor, (W + size_divisor - 1) // size_divisor * size_divisor
+        return H, W
+
+    def normalized(self, batch_u8, size=None, size_divisor=None, out=None):
+        """stacked uint8 batch -> fp32 channels-last memory [B,Hp,Wp,3] (one kernel launch)."""
+        from . import ops
+
+        _require_cuda(batch_u8, type(self).__name__)
+        chw = batch_u8.shape[1] == 3 and batch_u8.shape[3] != 3
+        H, W = (batch_u8.shape[2], batch_u8.shape[3]) if chw else (batch_u8.shape[1], batch_u8.shape[2])
+        hp, wp = self._padded_size(int(H), int(W), size, size_divisor)
+        mean = self._mean_host if self._enable_normalize else None
+        std = self._std_host if self._enable_normalize else None
+        return ops.preprocess_u8(batch_u8, mean=mean, std=std, swap_rb=self.channel_conversion, size=(hp, wp),
+                                 pad_val=float(self.pad_val), out=out)
+
+    def forward(self, data, training=False):
+        inputs = data["inputs"]
+        data_samples = data.get("data_samples", None)
+        if isinstance(inputs, (list, tuple)):
+            img_size = inputs[0].shape[1:]
+            assert all(i.shape[1:] == img_size for i in inputs), "The image size in a batch should be the same."
+            inputs = torch.stack([i.cuda(non_blocking=True) for i in inputs], dim=0)
+        else:
+            inputs = inputs.cuda(non_blocking=True)
+        size, div = (self.size, self.size_divisor) if training else \
+            ((self.test_cfg.get("size", None), self.test_cfg.get("size_divisor", None)) if self.test_cfg else (None, None))
+        if training:
+            assert data_samples is not None, "During training, `data_samples` must be define."
+        x = self.normalized(inputs, size, div)
+        if data_samples is not None and (size is not None or div is not None):
+            ph, pw = x.shape[1] - int(img_h(inputs)), x.shape[2] - int(img_w(inputs))
+            for ds in data_samples:                                 # label maps: right/bottom pad with seg_pad_val (misc.py:94-105)
+                if hasattr(ds, "gt_sem_seg"):
+                    ds.gt_sem_seg.data = nn.functional.pad(ds.gt_sem_seg.data, (0, pw, 0, ph), value=self.seg_pad_val)
+                if hasattr(ds, "set_metainfo"):
+                    ds.set_metainfo({"img_shape": tuple(ds.gt_sem_seg.data.shape[-2:]) if hasattr(ds, "gt_sem_seg") else None,
+                                     "pad_shape": (int(x.shape[1]), int(x.shape[2])), "padding_size": (0, pw, 0, ph)})
+        return dict(inputs=x.permute(0, 3, 1, 2), data_samples=data_samples)
+
+
+def img_h(b):
+    return b.shape[2] if (b.shape[1] == 3 and b.shape[3] != 3) else b.shape[1]
+
+
+def img_w(b):
+    return b.shape[3] if (b.shape[1] == 3 and b.shape[3] != 3) else b.shape[2]
+
+
+@register_everywhere
 class EncoderDecoder(_Engined):
     """Inference subset of mmseg's EncoderDecoder: extract_feat + decode_head.predict (whole mode)."""
 
@@ -170,6 +254,7 @@ class EncoderDecoder(_Engined):
         super().__init__()
         self.backbone = MODELS.build(backbone)
         self.decode_head = MODELS.build(decode_head)
+        self.data_preprocessor = MODELS.build(data_preprocessor) if isinstance(data_preprocessor, dict) else data_preprocessor
         self.test_cfg = test_cfg
         self.align_corners = self.decode_head.align_corners
         self.num_classes = self.decode_head.num_classes
@@ -202,7 +287,7 @@ class EncoderDecoder(_Engined):
             return engine.segmentor_logits(self, inputs, labels=labels)
         if torch.cuda.is_current_stream_capturing():
             return engine.segmentor_logits(self, inputs, labels=labels)
-        key = (tuple(inputs.shape), inputs.device.index, bool(labels))
+        key = (tuple(inputs.shape), inputs.device.index, bool(labels), inputs.dtype)
         g = self._graphs.get(key)
         if g is None:
             g = engine.GraphedForward(self, inputs, labels)
@@ -213,7 +298,9 @@ class EncoderDecoder(_Engined):
         return self.backbone(inputs)
 
     def encode_decode(self, inputs, batch_img_metas=None):
-        """fp32 [B,3,H,W] -> seg logits [B,K,H,W] (encoder_decoder.py:125-133), whole-image mode."""
+        """fp32 [B,3,H,W] -> seg logits [B,K,H,W] (encoder_decoder.py:125-133), whole-image mode.
+        A uint8 batch ([B,3,H,W] or [B,H,W,3]) is first normalised by `self.data_preprocessor` inside the same
+        captured graph (BaseSegmentor.test_step = data_preprocessor + predict, mmengine base_model)."""
         _require_cuda(inputs, type(self).__name__)
         return self._run(inputs, labels=False)
 
@@ -229,5 +316,9 @@ class EncoderDecoder(_Engined):
 
 def build_segmentor(cfg) -> EncoderDecoder:
     cfg = dict(cfg)
-    cfg.pop("data_preprocessor", None)
+    dp = cfg.get("data_preprocessor", None)
+    if isinstance(dp, dict):
+        dp = dict(dp)
+        dp.setdefault("type", "SegDataPreProcessor")
+        cfg["data_preprocessor"] = dp
     return MODELS.build(cfg)

@@ -311,6 +311,50 @@ def sigmoid_lif(x, d_max=D_MAX):
     return out
 
 
+def preprocess_u8(img, *, mean=None, std=None, swap_rb=False, size=None, pad_val=0.0, out=None):
+    """SegDataPreProcessor arithmetic (data_preprocessor.py:121-126) + stack_batch padding for a uint8 batch
+    [n,3,H,W] (CHW) or [n,H,W,3] (HWC).  Returns fp32 channels-last memory [n,Hp,Wp,3]."""
+    if not isinstance(img, torch.Tensor) or not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4:
+        raise S2FError("preprocess_u8: CUDA uint8 [n,3,H,W] or [n,H,W,3] tensor required (no CPU path)")
+    if not img.is_contiguous():
+        raise S2FError("preprocess_u8: img must be contiguous")
+    chw = img.shape[1] == 3 and img.shape[3] != 3
+    if not chw and img.shape[3] != 3:
+        raise S2FError("preprocess_u8: three channels expected")
+    n = int(img.shape[0])
+    H, W = (int(img.shape[2]), int(img.shape[3])) if chw else (int(img.shape[1]), int(img.shape[2]))
+    Hp, Wp = (max(H, int(size[0])), max(W, int(size[1]))) if size is not None else (H, W)
+    if out is None:
+        out = torch.empty((n, Hp, Wp, 3), dtype=torch.float32, device=img.device)
+    elif tuple(out.shape) != (n, Hp, Wp, 3):
+        raise S2FError("preprocess_u8: out must be fp32 [n,Hp,Wp,3]")
+    m3 = s3 = None
+    if mean is not None:
+        # fp32 values of torch.tensor(mean) / torch.tensor(std) (data_preprocessor.py:88-91)
+        m3 = (C.c_float * 3)(*[float(torch.tensor(float(v), dtype=torch.float32)) for v in mean])
+        s3 = (C.c_float * 3)(*[float(torch.tensor(float(v), dtype=torch.float32)) for v in std])
+    e0 = _p0()
+    check(_lib.lib().s2f_preprocess_u8(C.c_void_p(img.data_ptr()), int(chw), _ptr(out, torch.float32, "out"), n, H, W, Hp, Wp,
+                                       C.cast(m3, C.c_void_p) if m3 is not None else None,
+                                       C.cast(s3, C.c_void_p) if s3 is not None else None, int(bool(swap_rb)),
+                                       float(pad_val), _stream()), "s2f_preprocess_u8")
+    _p1(e0, "elementwise", 0, _nb(img, out), f"preprocess {n}x{H}x{W}")
+    return out
+
+
+def level_hist(levels, hist=None):
+    """hist[l] += number of elements at level l (l = 0..15); uint64-valued int64 tensor [16] on the device."""
+    if levels.dtype != torch.int8 or not levels.is_cuda or not levels.is_contiguous():
+        raise S2FError("level_hist: contiguous CUDA int8 levels required (no CPU path)")
+    if hist is None:
+        hist = torch.zeros(16, dtype=torch.int64, device=levels.device)
+    e0 = _p0()
+    check(_lib.lib().s2f_level_hist(C.c_void_p(levels.data_ptr()), int(levels.numel()), _ptr(hist, torch.int64, "hist"),
+                                    _stream()), "s2f_level_hist")
+    _p1(e0, "elementwise", 0, _nb(levels))
+    return hist
+
+
 def semantic_tail(mask_pred, cls, *, n, Q, K, h, w, H, W, want_logits=True, want_labels=False):
     """Tensor-core tail: softmax(cls)[..., :-1] x sigmoid(bilinear(mask_pred)) -> (logits [n,K,H,W] | None,
     labels uint8 [n,H,W] | None).  Falls outside the tcgen05 kernel's shape range only for Q > 128 or K > 256."""

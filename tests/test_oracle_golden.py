@@ -92,3 +92,28 @@ def test_port_bit_exact_against_live_reference_tiny():
         assert torch.equal(x.reshape(-1), xr.reshape(-1)), n
         assert torch.equal(s.reshape(-1), (orf * 8).reshape(-1)), n
     assert torch.equal(out, ref)
+
+
+def test_data_preprocess_port_matches_reference_golden():
+    """golden_preproc.pt: outputs of the reference's SegDataPreProcessor (make_golden_preproc.py): flip, normalise, pad."""
+    g = torch.load(os.path.join(GOLD, "golden_preproc.pt"))
+    for c in g["cases"]:
+        kw = dict(c["kw"])
+        tc = kw.pop("test_cfg", None) or {}
+        kw.pop("seg_pad_val", None)
+        train_size = kw.pop("size", None)            # `size` pads in training only (data_preprocessor.py:128-136)
+        out = port.data_preprocess(list(c["imgs"]), size=tc.get("size"), size_divisor=tc.get("size_divisor"), **kw)
+        assert torch.equal(out, c["out"]), c["kw"]
+    table = port.data_preprocess([g["ramp"]], mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], bgr_to_rgb=True)
+    assert torch.equal(table, g["table"])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference")
+def test_data_preprocess_port_against_live_reference():
+    cls = ref_loader.load_data_preprocessor()
+    gen = torch.Generator().manual_seed(3)
+    imgs = [torch.randint(0, 256, (3, 33, 47), generator=gen, dtype=torch.uint8) for _ in range(2)]
+    kw = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], bgr_to_rgb=True)
+    want = cls(**kw)(dict(inputs=[i.clone() for i in imgs]), training=False)["inputs"]
+    assert torch.equal(port.data_preprocess(imgs, **kw), want)
