@@ -23,11 +23,12 @@ namespace s2f {
 
 constexpr int TC_BM = 128;        // rows (pixels / tokens) per tile == UMMA M
 constexpr int TC_BN = 64;         // output channels per tile
-#ifndef S2F_EPI_WARPS
-#define S2F_EPI_WARPS 8
-#endif
-constexpr int TC_EPI_WARPS = S2F_EPI_WARPS;                 // 8 or 16: column split of the epilogue (32 or 16 channels per warp)
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0 TMA, warp 1 MMA, the rest epilogue
+// Epilogue warps per CTA (template parameter EW): 8 -> 32 channels per warp, 16 -> 16 channels per warp.  Measured on
+// B200: EW = 16 (4 warps per scheduler, 96 registers) changes nothing -- 14.3 us vs 14.4 us for 256->512 at 16 K rows.
+// The small-K layers are bound by draining the accumulator: three int32 planes = 96 KB of tcgen05.ld per 128x64 tile at
+// ~64 B/clk/SM = 1536 clk, during which the MMAs of the next tile make little progress; per-tile time fits
+// 3*K + 1536 clk (K=256: 2300 measured, K=512: ~3000, K=2304: ~8400 = 82 % MMA).  EW = 8 is the default.
+__host__ __device__ constexpr int tc_threads(int ew) { return 64 + 32 * ew; }       // warp 0 TMA, warp 1 MMA, the rest epilogue
 
 __host__ __device__ inline int tc_bk(int cin) { return cin >= 128 ? 128 : (cin >= 64 ? 64 : 32); }
 __host__ __device__ inline int tc_cin_pad(int cin) { const int bk = tc_bk(cin); return (cin + bk - 1) / bk * bk; }
@@ -127,6 +128,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | SBO>>4 @32 | version=1 @46 | layout @61
@@ -170,8 +181,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 // Stage the per-channel epilogue constants of one channel tile: ss[0][64] = scale, ss[1][64] = shift.
 // (The digit planes are merged before the affine: y = (d0 * 128^(P-1) + merged low planes) * scale + shift.)
+template <int EW>
 __device__ __forceinline__ void stage_affine(const TcParams& p, float* ss, int co_base, int img, int et) {
-  for (; et < 2 * TC_BN; et += 32 * TC_EPI_WARPS) {
+  for (; et < 2 * TC_BN; et += 32 * EW) {
     const int which = et >> 6, ch = co_base + (et & (TC_BN - 1));
     float v = 0.f;
     if (ch < p.Cout) v = __ldg((which ? p.shift : p.scale) + (int64_t)img * p.ss_img_stride + ch);
@@ -232,6 +244,19 @@ constexpr int EPI_GENERIC = 0;     // every combination (transposed / ragged / p
 constexpr int EPI_SPIKE = 1;       // int8 levels only, Cout % 16 == 0, d_max = 8: the bulk of the network's launches
 constexpr int EPI_STAGED = 2;      // fp32 / residual outputs through the shared-memory transpose
 constexpr int EPI_STAGED_UP = 3;   // the same + fused FPN merge from TMA patches
+#ifndef S2F_EW_SPIKE
+#define S2F_EW_SPIKE 8
+#endif
+#ifndef S2F_EW_STAGED
+#define S2F_EW_STAGED 8
+#endif
+#ifndef S2F_EW_UP
+#define S2F_EW_UP 8
+#endif
+#ifndef S2F_LDTM_X32
+#define S2F_LDTM_X32 1
+#endif
+constexpr int EW_SPIKE = S2F_EW_SPIKE, EW_STAGED = S2F_EW_STAGED, EW_UP = S2F_EW_UP;      // epilogue warps per kind
 
 // exact plane merge: d0 * 128^(P-1) + (low planes merged in int32), one rounding
 template <int PIECES>
@@ -245,21 +270,25 @@ __device__ __forceinline__ float merge_planes(uint32_t d0, uint32_t d1, uint32_t
 // back to back and the accumulator is handed back to the MMA warp as soon as they have landed in registers.
 // ss: [64] scale/8, [64] shift/8 (the power-of-two scaling is exact), so that the level is
 //   rne(8 * sat(v * scale/8 + shift/8)):  FFMA.SAT + FFMA (2^23 trick) per output, then PRMT packing.
-template <int PIECES>
+template <int PIECES, int EW>
 __device__ __forceinline__ void epilogue_spike(const TcParams& p, float* ss, uint64_t* tmem_full, uint64_t* tmem_empty,
                                                uint32_t tmem_base, int slot, int tile_n, int warp, int lane) {
-  const int quad = warp & 3, half = (warp - 2) >> 2;
+  constexpr int COLS = TC_BN / (EW / 4);                   // channels per warp: 32 or 16
+  constexpr int NCH = COLS / 16;                           // 16-column TMEM loads per plane
+  const int quad = warp & 3, slice = (warp - 2) >> 2;
   const int r = quad * 32 + lane;
   const int et = threadIdx.x - 64;
   const int co_base = tile_n * TC_BN;
-  for (int e = et; e < 2 * TC_BN; e += 32 * TC_EPI_WARPS) {
+  for (int e = et; e < 2 * TC_BN; e += 32 * EW) {
     const int ch = co_base + (e & (TC_BN - 1));
     ss[e] = ch < p.Cout ? 0.125f * __ldg(((e >> 6) ? p.shift : p.scale) + ch) : 0.f;
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-  const int cw0 = co_base + half * 32;                     // this warp's first channel
-  const int nchunks = cw0 >= p.Cout ? 0 : (cw0 + 16 >= p.Cout ? 1 : 2);      // Cout % 16 == 0 on this path
-  const uint32_t ss_addr = smem_u32(ss) + (uint32_t)(half * 32) * 4u;
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+  const int cw0 = co_base + slice * COLS;                  // this warp's first channel
+  int nchunks = 0;                                         // Cout % 16 == 0 on this path
+#pragma unroll
+  for (int jj = 0; jj < NCH; ++jj) nchunks += (cw0 + 16 * jj < p.Cout) ? 1 : 0;
+  const uint32_t ss_addr = smem_u32(ss) + (uint32_t)(slice * COLS) * 4u;
   int it = 0;
   for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
     const int acc = it & 1;
@@ -275,14 +304,20 @@ __device__ __forceinline__ void epilogue_spike(const TcParams& p, float* ss, uin
     int8_t* dst = p.out_spike + m * p.Cout + cw0;
     mbar_wait(&tmem_full[acc], (it >> 1) & 1);
     tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS) + (uint32_t)(half * 32);
-    uint32_t d[2][3][16];
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS) + (uint32_t)(slice * COLS);
+    uint32_t d[3][COLS];                                      // [plane][channel of this warp's slice]
     if (nchunks > 0) {
+      if (NCH == 2 && S2F_LDTM_X32) {                         // one 32-column load per plane
+        tmem_ld32(trow, d[0]);
+        if (PIECES > 1) tmem_ld32(trow + TC_BN, d[1]);
+        if (PIECES > 2) tmem_ld32(trow + 2 * TC_BN, d[2]);
+      } else {
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        tmem_ld16(trow + jj * 16, d[jj][0]);
-        if (PIECES > 1) tmem_ld16(trow + TC_BN + jj * 16, d[jj][1]);
-        if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + jj * 16, d[jj][2]);
+        for (int jj = 0; jj < NCH; ++jj) {
+          tmem_ld16(trow + jj * 16, d[0] + 16 * jj);
+          if (PIECES > 1) tmem_ld16(trow + TC_BN + jj * 16, d[1] + 16 * jj);
+          if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + jj * 16, d[2] + 16 * jj);
+        }
       }
       tmem_ld_wait();
     }
@@ -291,7 +326,7 @@ __device__ __forceinline__ void epilogue_spike(const TcParams& p, float* ss, uin
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);            // accumulator drained: the next tile's MMAs may start
     if (m < 0) continue;
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
+    for (int jj = 0; jj < NCH; ++jj) {
       if (jj < nchunks) {
         uint32_t w[4];
 #pragma unroll
@@ -303,7 +338,7 @@ __device__ __forceinline__ void epilogue_spike(const TcParams& p, float* ss, uin
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = 4 * q + e;
-            const float v = merge_planes<PIECES>(d[jj][0][j], d[jj][1][j], d[jj][2][j]);
+            const float v = merge_planes<PIECES>(d[0][16 * jj + j], d[1][16 * jj + j], d[2][16 * jj + j]);
             b[e] = __float_as_uint(fmaf(__saturatef(fmaf(v, s4[e], h4[e])), 8.f, 8388608.f));
           }
           w[q] = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
@@ -321,26 +356,31 @@ __device__ __forceinline__ void epilogue_spike(const TcParams& p, float* ss, uin
 // 32 rows x 32 channels of merged accumulators in a private shared-memory tile (row stride 36 floats: conflict-free for
 // both the row-per-lane STS.128 and the 4-rows-x-128-byte LDS.128), releases the TMEM accumulator, and then walks the
 // tile with lane = (row % 4, channel quad): every global access is 4 rows x 128 contiguous bytes.
-constexpr int TC_STG_LD = 36;                               // floats per staged row (32 + 4 padding)
-constexpr int TC_STG_FLOATS = 32 * TC_STG_LD;               // per epilogue warp
+__host__ __device__ constexpr int tc_stg_ld(int ew) { return TC_BN / (ew / 4) + 4; }          // floats per staged row: 36 / 20
+__host__ __device__ constexpr int tc_stg_floats(int ew) { return 32 * tc_stg_ld(ew); }        // per epilogue warp
 constexpr int TC_UP_SLOT = 60 * TC_BN * 4;                  // one patch: <= 60 source pixels x 64 channels fp32 (TW x TH = 16x8 or 8x16)
-constexpr int TC_AUX_OFF = 512 + 2 * 4 * TC_BN * 4 + TC_EPI_WARPS * TC_STG_FLOATS * 4;   // barriers | affine | staging -> patches
+__host__ __device__ constexpr int tc_aux_off(int ew) { return 512 + 2 * 4 * TC_BN * 4 + ew * tc_stg_floats(ew) * 4; }   // barriers | affine | staging -> patches
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int PIECES, bool UP_TMA>
+template <int PIECES, bool UP_TMA, int EW>
 __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, uint64_t* tmem_full, uint64_t* tmem_empty,
                                                 uint32_t tmem_base, int slot, int tile_n, int warp, int lane,
                                                 const uint8_t* up_patch, uint64_t* up_full, uint64_t* up_empty) {
-  static_assert(TC_EPI_WARPS == 8, "the staged epilogue assumes 32 channels per epilogue warp");
-  const int quad = warp & 3, half = (warp - 2) >> 2;
+  constexpr int COLS = TC_BN / (EW / 4);                      // channels per warp: 32 or 16
+  constexpr int NCH = COLS / 16;
+  constexpr int LD = tc_stg_ld(EW);
+  constexpr int LPR = COLS / 4;                               // lanes per row in phase 2: 8 or 4
+  constexpr int RPS = 32 / LPR;                               // rows per phase-2 step: 4 or 8
+  constexpr int NSTEP = 32 / RPS;                             // 8 or 4
+  const int quad = warp & 3, slice = (warp - 2) >> 2;
   const int r = quad * 32 + lane;
-  const int cq = lane & 7, rsub = lane >> 3;
-  const int cw = tile_n * TC_BN + half * 32 + 4 * cq;         // this lane's four channels in phase 2
+  const int cq = lane % LPR, rsub = lane / LPR;
+  const int cw = tile_n * TC_BN + slice * COLS + 4 * cq;      // this lane's four channels in phase 2
   const bool cvalid = cw < p.Cout;                            // Cout % 4 == 0 on this path
-  const bool warp_has_cols = tile_n * TC_BN + half * 32 < p.Cout;
+  const bool warp_has_cols = tile_n * TC_BN + slice * COLS < p.Cout;
   const uint32_t stg_addr = smem_u32(stg);
   float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
   int loaded_img = -1;
@@ -390,19 +430,19 @@ __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, u
     // the 64-bit part of every address is a per-tile, warp-uniform base
     const int64_t mt0 = p.mode_conv ? ((int64_t)o.img * p.Ho + o.ho0) * p.Wo + o.wo0 : (int64_t)tile_m * TC_BM;
     const int rel_c = m >= 0 ? (m - (int)mt0) * p.Cout : INT_MIN / 2;
-    int orow[8];
+    int orow[NSTEP];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = __shfl_sync(0xffffffffu, rel_c, 4 * i + rsub);
+    for (int i = 0; i < NSTEP; ++i) {
+      const int t = __shfl_sync(0xffffffffu, rel_c, RPS * i + rsub);
       orow[i] = cvalid ? t + cw : -1;                           // cvalid: this lane's channel quad exists
     }
     const float* res_t = p.residual ? p.residual + mt0 * p.Cout : nullptr;
     float* of_t = p.out_f32 ? p.out_f32 + mt0 * p.Cout : nullptr;
     int8_t* os_t = p.out_spike ? p.out_spike + mt0 * p.Cout : nullptr;
-    float4 res[8];
+    float4 res[NSTEP];
     if (p.residual) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < NSTEP; ++i) {
         res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (orow[i] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(res_t + orow[i]));
       }
@@ -414,14 +454,14 @@ __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, u
     // residual rows already occupy 32 registers)
     if (warp_has_cols) {
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j0 = half * 32 + jj * 16;
+      for (int jj = 0; jj < NCH; ++jj) {
+        const int j0 = slice * COLS + jj * 16;
         uint32_t d0[16], d1[16], d2[16];
         tmem_ld16(trow + j0, d0);
         if (PIECES > 1) tmem_ld16(trow + TC_BN + j0, d1);
         if (PIECES > 2) tmem_ld16(trow + 2 * TC_BN + j0, d2);
         tmem_ld_wait();
-        const uint32_t wa = stg_addr + (uint32_t)(lane * TC_STG_LD + jj * 16) * 4u;
+        const uint32_t wa = stg_addr + (uint32_t)(lane * LD + jj * 16) * 4u;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           sts128(wa + 16u * q, merge_planes<PIECES>(d0[4 * q], d1[4 * q], d2[4 * q]),
@@ -435,11 +475,11 @@ __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, u
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);              // the MMA warp may refill this accumulator now
     // ---- phase 2: lane = (row % 4, channel quad); 8 steps of 4 rows x 128 bytes
     if (warp_has_cols) {
-      const uint32_t ra = stg_addr + (uint32_t)(rsub * TC_STG_LD + 4 * cq) * 4u;
+      const uint32_t ra = stg_addr + (uint32_t)(rsub * LD + 4 * cq) * 4u;
       if (!UP_TMA && !p.up_prev) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 v = lds128(ra + (uint32_t)(4 * i * TC_STG_LD) * 4u);
+        for (int i = 0; i < NSTEP; ++i) {
+          const float4 v = lds128(ra + (uint32_t)(RPS * i * LD) * 4u);
           if (orow[i] >= 0) {
             float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
             if (p.residual) { y0 += res[i].x; y1 += res[i].y; y2 += res[i].z; y3 += res[i].w; }
@@ -450,13 +490,13 @@ __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, u
       } else if (UP_TMA) {
         const int us = it % 3;
         mbar_wait(&up_full[us], (uint32_t)((it / 3) & 1));
-        const uint32_t pa = smem_u32(up_patch) + (uint32_t)us * (uint32_t)TC_UP_SLOT + (uint32_t)(half * 32 + 4 * cq) * 4u;
+        const uint32_t pa = smem_u32(up_patch) + (uint32_t)us * (uint32_t)TC_UP_SLOT + (uint32_t)(slice * COLS + 4 * cq) * 4u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int src = 4 * i + rsub;
+        for (int i = 0; i < NSTEP; ++i) {
+          const int src = RPS * i + rsub;
           const uint32_t pk = (uint32_t)__shfl_sync(0xffffffffu, u00, src);
           const float lx = __shfl_sync(0xffffffffu, up_lx, src), ly = __shfl_sync(0xffffffffu, up_ly, src);
-          const float4 v = lds128(ra + (uint32_t)(4 * i * TC_STG_LD) * 4u);
+          const float4 v = lds128(ra + (uint32_t)(RPS * i * LD) * 4u);
           if (orow[i] >= 0) {
             const float hx = 1.f - lx, hy = 1.f - ly;
             const float4 p00 = lds128(pa + (pk & 0xffu) * (TC_BN * 4u)), p01 = lds128(pa + ((pk >> 8) & 0xffu) * (TC_BN * 4u));
@@ -473,12 +513,12 @@ __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, u
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int src = 4 * i + rsub;
+        for (int i = 0; i < NSTEP; ++i) {
+          const int src = RPS * i + rsub;
           const int s00 = __shfl_sync(0xffffffffu, u00, src), s01 = __shfl_sync(0xffffffffu, u01, src);
           const int s10 = __shfl_sync(0xffffffffu, u10, src), s11 = __shfl_sync(0xffffffffu, u11, src);
           const float lx = __shfl_sync(0xffffffffu, up_lx, src), ly = __shfl_sync(0xffffffffu, up_ly, src);
-          const float4 v = lds128(ra + (uint32_t)(4 * i * TC_STG_LD) * 4u);
+          const float4 v = lds128(ra + (uint32_t)(RPS * i * LD) * 4u);
           if (orow[i] >= 0) {
             const float hx = 1.f - lx, hy = 1.f - ly;
             const float4 p00 = __ldg(reinterpret_cast<const float4*>(p.up_prev + (int64_t)s00 * p.Cout + cw));
@@ -503,8 +543,8 @@ __device__ __forceinline__ void epilogue_staged(const TcParams& p, float* stg, u
   }
 }
 
-template <int PIECES, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int PIECES, int EPI, int EW>
+__global__ void __launch_bounds__(tc_threads(EW), 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_up, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -524,9 +564,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* up_full = b_full + 1;                     // [3] patches of the coarser FPN level (p.up_tma)
   uint64_t* up_empty = up_full + 3;                   // [3]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(up_empty + 3);
-  uint8_t* up_patch = reinterpret_cast<uint8_t*>(full) + TC_AUX_OFF;      // [3][TC_UP_SLOT], 512-byte aligned
+  uint8_t* up_patch = reinterpret_cast<uint8_t*>(full) + tc_aux_off(EW);      // [3][TC_UP_SLOT], 512-byte aligned
   float* ss_stage = reinterpret_cast<float*>(tmem_slot + 2);      // [2][4][64] floats, 16-byte aligned
-  float* stg_all = ss_stage + 2 * 4 * TC_BN;                      // [8 warps][32][36] floats when p.staged
+  float* stg_all = ss_stage + 2 * 4 * TC_BN;                      // [EW warps][32][COLS + 4] floats when p.staged
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x % p.tiles_n;
@@ -536,9 +576,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EW); }
     mbar_init(b_full, 1);
-    for (int s = 0; s < 3; ++s) { mbar_init(&up_full[s], 1); mbar_init(&up_empty[s], TC_EPI_WARPS); }
+    for (int s = 0; s < 3; ++s) { mbar_init(&up_full[s], 1); mbar_init(&up_empty[s], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -600,23 +640,23 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     else if (p.bk == 64) mma_role<PIECES, 2>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
     else mma_role<PIECES, 1>(p, smem_u32(ring), smem_u32(b_res), stage_bytes, full, empty, tmem_full, tmem_empty, tmem_base, slot);
   } else if (EPI == EPI_SPIKE) {
-    epilogue_spike<PIECES>(p, ss_stage, tmem_full, tmem_empty, tmem_base, slot, tile_n, warp, lane);
+    epilogue_spike<PIECES, EW>(p, ss_stage, tmem_full, tmem_empty, tmem_base, slot, tile_n, warp, lane);
   } else if (EPI == EPI_STAGED || EPI == EPI_STAGED_UP) {
-    epilogue_staged<PIECES, EPI == EPI_STAGED_UP>(p, stg_all + (warp - 2) * TC_STG_FLOATS, tmem_full, tmem_empty, tmem_base, slot,
+    epilogue_staged<PIECES, EPI == EPI_STAGED_UP, EW>(p, stg_all + (warp - 2) * tc_stg_floats(EW), tmem_full, tmem_empty, tmem_base, slot,
                                                   tile_n, warp, lane, up_patch, up_full, up_empty);
   } else {
     // ===== epilogue (8 warps): warp w reads TMEM lanes [32*(w%4), +32) -- thread = one output row -- and one half
     // (32 channels) of the tile's columns.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;                   // column slice: 64 / (TC_EPI_WARPS / 4) channels each
-    constexpr int COLS_PER_WARP = TC_BN / (TC_EPI_WARPS / 4);
+    const int half = (warp - 2) >> 2;                   // column slice: 64 / (EW / 4) channels each
+    constexpr int COLS_PER_WARP = TC_BN / (EW / 4);
     const int r = quad * 32 + lane;
     const int et = threadIdx.x - 64;                    // 0..255 within the epilogue group
     const int co_base = tile_n * TC_BN;
     const bool per_tile_affine = p.ss_img_stride != 0;
     if (!per_tile_affine) {
-      stage_affine(p, ss_stage, co_base, 0, et);
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");     // epilogue warps only
+      stage_affine<EW>(p, ss_stage, co_base, 0, et);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");     // epilogue warps only
     }
     int it = 0, staged_img = -1, staged_buf = 0;
     for (int tile_m = slot; tile_m < p.tiles_m; tile_m += p.ctas_per_n, ++it) {
@@ -624,8 +664,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int acc = it & 1;
       if (per_tile_affine && o.img != staged_img) {      // per-image weights: constants change with the image only
         staged_buf ^= 1;                                 // the other buffer may still be read by a slower warp
-        stage_affine(p, ss_stage + staged_buf * (4 * TC_BN), co_base, o.img, et);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        stage_affine<EW>(p, ss_stage + staged_buf * (4 * TC_BN), co_base, o.img, et);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
         staged_img = o.img;
       }
       const uint32_t ss_addr = smem_u32(ss_stage + staged_buf * (4 * TC_BN));
@@ -826,7 +866,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   p.pieces = a->pieces; p.out_transposed = a->out_transposed; p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
   const int per_img_w = a->per_image_weights ? 1 : 0;
   p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
-  p.staged = (TC_EPI_WARPS == 8 && p.d_max == 8.f && !a->out_transposed && a->Cout % 4 == 0 && (a->out_f32 || a->residual || a->up_prev) &&
+  p.staged = (p.d_max == 8.f && !a->out_transposed && a->Cout % 4 == 0 && (a->out_f32 || a->residual || a->up_prev) &&
               (!a->residual || (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0) &&
               (!a->out_f32 || (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0) &&
               (!a->out_spike || (reinterpret_cast<uintptr_t>(a->out_spike) & 3) == 0) &&
@@ -834,9 +874,16 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
               (int64_t)p.M_total < (1ll << 31) && (!a->up_prev || (int64_t)a->n * a->up_H * a->up_W < (1ll << 31))) ? 1 : 0;
   // fused FPN merge of an exact 2x coarser level: spatial 16x8 tiles, so that the tile's source pixels form one small
   // box (TW/2 + 2 by TH/2 + 2) that the producer warp fetches with TMA next to the spike tile
-  const bool up2x = p.staged && a->up_prev && !per_img_w && Ho == 2 * a->up_H && Wo == 2 * a->up_W && Wo >= 8 && TC_EPI_WARPS == 8 &&
+  const bool up2x = p.staged && a->up_prev && !per_img_w && Ho == 2 * a->up_H && Wo == 2 * a->up_W && Wo >= 8 &&
                     a->Cout % 4 == 0 && (int64_t)a->n * Ho * Wo < (1ll << 31);
   if (up2x) p.mode_conv = 1;
+  int epi = EPI_GENERIC;
+  if (up2x) epi = EPI_STAGED_UP;
+  else if (p.staged) epi = EPI_STAGED;
+  else if (a->out_spike && !a->out_f32 && !a->residual && !a->up_prev && !a->out_transposed && !per_img_w && a->Cout % 16 == 0 &&
+           p.d_max == 8.f && (reinterpret_cast<uintptr_t>(a->out_spike) & 15) == 0)
+    epi = EPI_SPIKE;
+  const int ew = epi == EPI_SPIKE ? EW_SPIKE : (epi == EPI_STAGED ? EW_STAGED : (epi == EPI_STAGED_UP ? EW_UP : 8));
   const int nB = TC_BN * p.pieces;
   const int tiles_n = (a->Cout + TC_BN - 1) / TC_BN;
   if (per_img_w) {
@@ -902,7 +949,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   S2F_REQUIRE((int64_t)kpad * 8 * 64 * 129 < (1ll << 31), "gemm_i8_tc: K too large for the int32 plane merge");
   const int num_chunks = p.taps * p.cin_chunks;
   const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 4 * TC_BN * sizeof(float) +
-                       (p.staged ? (size_t)TC_EPI_WARPS * TC_STG_FLOATS * sizeof(float) : 0) + (p.up_tma ? 3 * (size_t)TC_UP_SLOT : 0);
+                       (p.staged ? (size_t)ew * tc_stg_floats(ew) * sizeof(float) : 0) + (p.up_tma ? 3 * (size_t)TC_UP_SLOT : 0);
   const size_t budget = 226 * 1024 - fixed;
   const size_t b_all = (size_t)num_chunks * nB * p.bk;
   // weight-stationary when the whole K extent of the weight tile fits and still leaves >= 4 A stages
@@ -915,12 +962,6 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (p.stages < 2) p.stages = 2;
   size_t smem = (p.b_resident ? b_all : 0) + (size_t)p.stages * stage_bytes + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;          // never two CTAs on one SM: each allocates all 512 TMEM columns
-  int epi = EPI_GENERIC;
-  if (p.up_tma) epi = EPI_STAGED_UP;
-  else if (p.staged) epi = EPI_STAGED;
-  else if (a->out_spike && !a->out_f32 && !a->residual && !a->up_prev && !a->out_transposed && !per_img_w && a->Cout % 16 == 0 &&
-           p.d_max == 8.f && (reinterpret_cast<uintptr_t>(a->out_spike) & 15) == 0)
-    epi = EPI_SPIKE;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -934,21 +975,21 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   p.ctas_per_n = per_n;
   const unsigned grid = (unsigned)(per_n * tiles_n);
   cudaError_t attr_err = cudaSuccess;
-#define S2F_TC_LAUNCH(P, E)                                                                                             \
+#define S2F_TC_LAUNCH(P, E, W)                                                                                            \
   do {                                                                                                                  \
     static bool attr_set = false;                                                                                       \
     if (!attr_set) {                                                                                                    \
-      attr_err = cudaFuncSetAttribute(gemm_i8_tc_kernel<P, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      attr_err = cudaFuncSetAttribute(gemm_i8_tc_kernel<P, E, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       attr_set = attr_err == cudaSuccess;                                                                               \
     }                                                                                                                   \
-    if (attr_err == cudaSuccess) gemm_i8_tc_kernel<P, E><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_up, p); \
+    if (attr_err == cudaSuccess) gemm_i8_tc_kernel<P, E, W><<<grid, tc_threads(W), smem, (cudaStream_t)stream>>>(map_a, map_b, map_up, p); \
   } while (0)
 #define S2F_TC_EPI(P)                                               \
   do {                                                              \
-    if (epi == EPI_SPIKE) S2F_TC_LAUNCH(P, EPI_SPIKE);              \
-    else if (epi == EPI_STAGED) S2F_TC_LAUNCH(P, EPI_STAGED);       \
-    else if (epi == EPI_STAGED_UP) S2F_TC_LAUNCH(P, EPI_STAGED_UP); \
-    else S2F_TC_LAUNCH(P, EPI_GENERIC);                             \
+    if (epi == EPI_SPIKE) S2F_TC_LAUNCH(P, EPI_SPIKE, EW_SPIKE);    \
+    else if (epi == EPI_STAGED) S2F_TC_LAUNCH(P, EPI_STAGED, EW_STAGED); \
+    else if (epi == EPI_STAGED_UP) S2F_TC_LAUNCH(P, EPI_STAGED_UP, EW_UP); \
+    else S2F_TC_LAUNCH(P, EPI_GENERIC, 8);                          \
   } while (0)
   if (p.pieces == 3) S2F_TC_EPI(3);
   else if (p.pieces == 2) S2F_TC_EPI(2);
