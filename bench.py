@@ -141,6 +141,9 @@ def kernel_microbench(dev):
     t = timed(lambda: ops.nilif(x, out=lv))
     nilif = dict(workload="NI-LIF B=64 N=1024 C=512 T=1 D=8", us=t * 1e6, gbs=x.numel() * 5 / t / 1e9,
                  algorithmic_bytes=x.numel() * 5)
+    bn_s, bn_b = (torch.rand(512, generator=g) + 0.5).to(dev), torch.randn(512, generator=g).to(dev)
+    t = timed(lambda: ops.nilif(x, scale=bn_s, shift=bn_b, out=lv))
+    nilif["with_folded_bn_affine"] = dict(us=t * 1e6, gbs=x.numel() * 5 / t / 1e9)
     n, Hh, Ww, cin, cout = 64, 32, 32, 512, 2048
     a = torch.randint(0, 9, (n, Hh, Ww, cin), generator=g, dtype=torch.int8).to(dev)
     w = torch.randn(cout, cin, generator=g) / cin ** 0.5
@@ -355,6 +358,7 @@ def main():
     if micro:
         micro["nilif_cfg2"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["gbs"] / pk["hbm"]
         micro["nilif_cfg2"]["frac_of_8tbs_nominal"] = micro["nilif_cfg2"]["gbs"] / 8000.0
+        micro["nilif_cfg2"]["with_folded_bn_affine"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["with_folded_bn_affine"]["gbs"] / pk["hbm"]
         # int8 tensor peak is taken as 2x the measured bf16 peak; the kernel executes 3 int8 MACs (digit planes) per
         # algorithmic MAC, so utilisation of the int8 pipe = 3 * algorithmic / (2 * bf16 peak)
         micro["gemm_cfg2"]["int8_pipe_utilisation_est"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] / (2.0 * pk["bf16_sustained"])

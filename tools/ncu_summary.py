@@ -1,6 +1,6 @@
 """Summarise ncu captures into the tracked profiles/ directory (run in the build container, no GPU needed).
 
-    python tools/ncu_summary.py launches gpurun_out/X_launches.csv profiles/X_launches.md [last_n]
+    python tools/ncu_summary.py launches gpurun_out/X_launches.csv profiles/X_launches.md [last_n] [batch]
         per-kernel table (launch count, total / mean device time, share) from a
         `ncu --metrics gpu__time_duration.sum --csv` launch list; `last_n` keeps only the last n launches
         (one forward) so that warm-up passes do not count.
@@ -27,32 +27,61 @@ def short(name):
     return name[:70]
 
 
-def launches(src, dst, last_n=None):
-    rows = []
+def launches(src, dst, last_n=None, batch=None):
+    """Per-kernel table from an ncu launch list; with dram__bytes_read/write.sum in the list it also reports the DRAM
+    traffic and (batch given) refreshes profiles/traffic.json, which bench.py reads for roofline.traffic."""
     with open(src, newline="") as f:
         lines = [ln for ln in f if not ln.startswith("==")]
+    per = {}                                   # launch id -> [name, us, dram bytes]
+    order = []
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in csv.DictReader(io.StringIO("".join(lines))):
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+        lid = r["ID"]
+        if lid not in per:
+            per[lid] = [short(r["Kernel Name"]), 0.0, 0.0, False]
+            order.append(lid)
         v = float(r["Metric Value"].replace(",", ""))
         unit = r["Metric Unit"]
-        us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
-        rows.append((short(r["Kernel Name"]), us, r["Grid Size"], r["Block Size"]))
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            per[lid][1] = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+        elif r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            per[lid][2] += v * mult.get(unit, 1)
+            per[lid][3] = True
+    rows = [per[i] for i in order]
     if last_n:
         rows = rows[-int(last_n):]
+    has_dram = any(r[3] for r in rows)
     agg = {}
-    for name, us, grid, block in rows:
-        a = agg.setdefault(name, [0, 0.0])
+    for name, us, by, _ in rows:
+        a = agg.setdefault(name, [0, 0.0, 0.0])
         a[0] += 1
         a[1] += us
+        a[2] += by
     tot = sum(a[1] for a in agg.values())
+    totb = sum(a[2] for a in agg.values())
     with open(dst, "w") as f:
         f.write(f"# ncu launch list summary ({src})\n\n")
-        f.write(f"{len(rows)} launches, {tot / 1e3:.3f} ms of device time (ncu: cold-cache, serialised -- compare shares, not absolutes)\n\n")
-        f.write("| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
-        for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f"| `{name}` | {cnt} | {us:.1f} | {us / cnt:.1f} | {100 * us / tot:.1f}% |\n")
+        f.write(f"{len(rows)} launches, {tot / 1e3:.3f} ms of device time (ncu: cold-cache, serialised -- compare shares, not absolutes)")
+        if has_dram:
+            f.write(f"; DRAM traffic {totb / 1e9:.2f} GB" + (f" = {totb / 1e6 / int(batch):.0f} MB per image" if batch else ""))
+        f.write("\n\n| kernel | launches | total us | mean us | share |" + (" DRAM read+write | per launch |" if has_dram else "") + "\n")
+        f.write("|---|---:|---:|---:|---:|" + ("---:|---:|" if has_dram else "") + "\n")
+        for name, (cnt, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{name}` | {cnt} | {us:.1f} | {us / cnt:.1f} | {100 * us / tot:.1f}% |" +
+                    (f" {by / 1e6:.0f} MB | {by / 1e6 / cnt:.1f} MB |" if has_dram else "") + "\n")
     print(open(dst).read())
+    if has_dram and batch:
+        import json
+        import os
+        g = [(c, us, by) for n, (c, us, by) in agg.items() if n.startswith("gemm_i8_tc_kernel")]
+        if g:
+            cnt, us, by = (sum(x[i] for x in g) for i in range(3))
+            tj = os.path.join(os.path.dirname(os.path.abspath(dst)), "traffic.json")
+            json.dump({"gemm_i8_tc_kernel<3>": {"launches_per_forward": cnt, "dram_bytes_per_launch": by / cnt,
+                                                "share_of_step_under_ncu": us / tot, "batch": int(batch),
+                                                "source": os.path.relpath(dst, os.path.dirname(os.path.dirname(os.path.abspath(dst))))}},
+                      open(tj, "w"), indent=1)
+            print("wrote", tj)
 
 
 def full(src, dst):
@@ -84,6 +113,6 @@ def full(src, dst):
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "launches":
-        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else None)
     else:
         full(sys.argv[2], sys.argv[3])
