@@ -79,37 +79,49 @@ __global__ void __launch_bounds__(256, CIN_CT > 0 ? 2 : 1) conv_direct_kernel(co
         wb[i] = (r % p.Wo) * p.stride - p.pad;
       }
       if constexpr (CIN_CT > 0) {
-        // the stem (Cin = 3, 7x7): one kernel row = KW * Cin k-steps, fully unrolled so that its 2 * 21 loads are issued
-        // back to back ahead of the 21 * 64 FFMAs (loads from clamped addresses, masked afterwards)
-        for (int kh = 0; kh < p.KH; ++kh) {
-          float av[PX][KW_CT * CIN_CT];
+        // the stem (Cin = 3, 7x7): a ROLLED loop over the 49 taps, two taps per iteration (ping-pong registers), the
+        // loads of the next tap in flight under the 3 * 64 FFMAs of the current one.  The body is ~7 KB of SASS; the
+        // version that unrolled a whole kernel row (24 KB) stalled on instruction fetch as often as it issued
+        // (ncu: no_instruction 0.93 per issue, FMA pipe 42 %).
+        const int ntaps = p.KH * KW_CT;
+        auto load_tap = [&](int kh, int kw, float (&dst)[PX][CIN_CT]) {
 #pragma unroll
           for (int i = 0; i < PX; ++i) {
-            const int hi = hb[i] + kh;
-            const bool rok = hi >= 0 && hi < p.H;
-            const float* rowp = A + ((int64_t)img[i] * p.H + (rok ? hi : 0)) * p.W * CIN_CT;
+            const int hi = hb[i] + kh, wi = wb[i] + kw;
+            const bool ok = hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            const float* src = A + (((int64_t)img[i] * p.H + (ok ? hi : 0)) * p.W + (ok ? wi : 0)) * CIN_CT;
 #pragma unroll
-            for (int kw = 0; kw < KW_CT; ++kw) {
-              const int wi = wb[i] + kw;
-              const bool ok = rok && wi >= 0 && wi < p.W;
-              const float* src = rowp + (ok ? wi : 0) * CIN_CT;
-#pragma unroll
-              for (int ci = 0; ci < CIN_CT; ++ci) { const float v = __ldg(src + ci); av[i][kw * CIN_CT + ci] = ok ? v : 0.f; }
-            }
+            for (int ci = 0; ci < CIN_CT; ++ci) { const float v = __ldg(src + ci); dst[i][ci] = ok ? v : 0.f; }
           }
-          const float* wrow = Ws + kh * (KW_CT * CIN_CT) * NC;
+        };
+        auto fma_tap = [&](int tap, const float (&av)[PX][CIN_CT]) {
+          const float* wrow = Ws + tap * CIN_CT * NC;
 #pragma unroll
-          for (int kk = 0; kk < KW_CT * CIN_CT; ++kk) {
-            const float4* wr = reinterpret_cast<const float4*>(wrow + kk * NC);
+          for (int ci = 0; ci < CIN_CT; ++ci) {
+            const float4* wr = reinterpret_cast<const float4*>(wrow + ci * NC);
 #pragma unroll
             for (int c4 = 0; c4 < NC / 4; ++c4) {
               const float4 w = wr[c4];
 #pragma unroll
               for (int i = 0; i < PX; ++i) {
-                acc[i][4 * c4] = fmaf(av[i][kk], w.x, acc[i][4 * c4]); acc[i][4 * c4 + 1] = fmaf(av[i][kk], w.y, acc[i][4 * c4 + 1]);
-                acc[i][4 * c4 + 2] = fmaf(av[i][kk], w.z, acc[i][4 * c4 + 2]); acc[i][4 * c4 + 3] = fmaf(av[i][kk], w.w, acc[i][4 * c4 + 3]);
+                acc[i][4 * c4] = fmaf(av[i][ci], w.x, acc[i][4 * c4]); acc[i][4 * c4 + 1] = fmaf(av[i][ci], w.y, acc[i][4 * c4 + 1]);
+                acc[i][4 * c4 + 2] = fmaf(av[i][ci], w.z, acc[i][4 * c4 + 2]); acc[i][4 * c4 + 3] = fmaf(av[i][ci], w.w, acc[i][4 * c4 + 3]);
               }
             }
+          }
+        };
+        float va[PX][CIN_CT], vb[PX][CIN_CT];
+        int kh = 0, kw = 0;
+        auto advance = [&]() { if (++kw == KW_CT) { kw = 0; ++kh; } };
+        load_tap(0, 0, va);
+        advance();
+#pragma unroll 1
+        for (int tap = 0; tap < ntaps; tap += 2) {
+          if (tap + 1 < ntaps) { load_tap(kh, kw, vb); advance(); }
+          fma_tap(tap, va);
+          if (tap + 1 < ntaps) {
+            if (tap + 2 < ntaps) { load_tap(kh, kw, va); advance(); }
+            fma_tap(tap + 1, vb);
           }
         }
       } else {
