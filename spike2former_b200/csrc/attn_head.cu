@@ -261,6 +261,95 @@ __global__ void __launch_bounds__(256) qkv_fast_kernel(const int8_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Q (K^T V) on the int8 tensor-core path as well.  kv = K^T V is an int32 matrix (up to Nk * 64 per entry), so it is
+// split -- exactly like a weight matrix of the spike GEMM -- into three signed base-128 digit planes in shared memory
+// (laid out [head][plane][j][i], i contiguous: the "col" B operand of mma.sync.m16n8k32), after which
+//   out[tok][h*d + j] = sum_p 128^(2-p) * (Q_h digits_p)[tok][j]
+// is three s8 MMAs per 16 tokens x 8 channels and an exact int32 merge.  A warp owns 16 tokens and walks the heads;
+// its A fragments are four 32-bit loads straight from the q rows.  ~1300 instructions per 16 tokens x 256 channels
+// against ~6400 for the IMAD loop of qkv_fast_kernel.
+template <int KB>      // 32-wide K blocks: ceil(d / 32)
+__global__ void __launch_bounds__(256) qkv_mma_kernel(const int8_t* __restrict__ q, const int32_t* __restrict__ kv,
+                                                      int8_t* __restrict__ out_spike, float* __restrict__ out_f32, int Nq,
+                                                      int heads, int d, int q_ld, int out_ld, float out_scale, float d_max,
+                                                      int hpb) {
+  extern __shared__ __align__(16) uint8_t planes[];          // [hpb heads of this block][3][d][KPAD]
+  constexpr int KPAD = 32 * KB + 16;                         // conflict-free fragment loads (12 / 20 words per row)
+  const int img = blockIdx.y;
+  const int C = heads * d;
+  const int h_first = blockIdx.z * hpb;                      // blockIdx.z: group of hpb heads (small Nq: more blocks)
+  const int32_t* kvb = kv + ((int64_t)img * heads + h_first) * d * d;
+  for (int e = threadIdx.x; e < hpb * d * d; e += blockDim.x) {
+    const int h = e / (d * d), r = e % (d * d), i = r / d, j = r % d;
+    int v = __ldg(kvb + e);
+    const int d2 = ((v + 64) & 127) - 64; v = (v - d2) >> 7;
+    const int d1 = ((v + 64) & 127) - 64; v = (v - d1) >> 7;
+    uint8_t* dst = planes + ((size_t)(h * 3) * d + j) * KPAD + i;
+    dst[0] = (uint8_t)(int8_t)v; dst[(size_t)d * KPAD] = (uint8_t)(int8_t)d1; dst[(size_t)2 * d * KPAD] = (uint8_t)(int8_t)d2;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tok0 = blockIdx.x * 128 + warp * 16;
+  if (tok0 >= Nq) return;
+  const int r0 = tok0 + g, r1 = tok0 + g + 8;
+  const bool ok0 = r0 < Nq, ok1 = r1 < Nq;
+  const int8_t* q0 = q + ((int64_t)img * Nq + (ok0 ? r0 : 0)) * q_ld;
+  const int8_t* q1 = q + ((int64_t)img * Nq + (ok1 ? r1 : 0)) * q_ld;
+  const int64_t o0 = ((int64_t)img * Nq + r0) * out_ld, o1 = ((int64_t)img * Nq + r1) * out_ld;
+  const int ntiles = d >> 3;
+  for (int hl = 0; hl < hpb; ++hl) {
+    const int h = h_first + hl;
+    uint32_t a[KB][4];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      const int k0 = kb * 32 + 4 * t, k1 = k0 + 16;
+      a[kb][0] = (ok0 && k0 < d) ? __ldg(reinterpret_cast<const uint32_t*>(q0 + h * d + k0)) : 0u;
+      a[kb][1] = (ok1 && k0 < d) ? __ldg(reinterpret_cast<const uint32_t*>(q1 + h * d + k0)) : 0u;
+      a[kb][2] = (ok0 && k1 < d) ? __ldg(reinterpret_cast<const uint32_t*>(q0 + h * d + k1)) : 0u;
+      a[kb][3] = (ok1 && k1 < d) ? __ldg(reinterpret_cast<const uint32_t*>(q1 + h * d + k1)) : 0u;
+    }
+    const uint8_t* ph = planes + (size_t)(hl * 3) * d * KPAD;
+    for (int nt = 0; nt < ntiles; ++nt) {
+      int acc[3][4];
+#pragma unroll
+      for (int pz = 0; pz < 3; ++pz) {
+        acc[pz][0] = acc[pz][1] = acc[pz][2] = acc[pz][3] = 0;
+        const uint8_t* pb = ph + ((size_t)pz * d + nt * 8 + g) * KPAD + 4 * t;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t b[2] = {*reinterpret_cast<const uint32_t*>(pb + kb * 32), *reinterpret_cast<const uint32_t*>(pb + kb * 32 + 16)};
+          mma_s8(acc[pz], a[kb], b);
+        }
+      }
+      float y[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) y[r] = (float)((acc[0][r] * 128 + acc[1][r]) * 128 + acc[2][r]) * out_scale;
+      const int c = h * d + nt * 8 + 2 * t;
+      if (ok0) {
+        if (out_f32) *reinterpret_cast<float2*>(out_f32 + o0 + c) = make_float2(y[0], y[1]);
+        if (out_spike) *reinterpret_cast<uint16_t*>(out_spike + o0 + c) =
+            (uint16_t)((level_bits(y[0], d_max) & 0xffu) | ((level_bits(y[1], d_max) & 0xffu) << 8));
+      }
+      if (ok1) {
+        if (out_f32) *reinterpret_cast<float2*>(out_f32 + o1 + c) = make_float2(y[2], y[3]);
+        if (out_spike) *reinterpret_cast<uint16_t*>(out_spike + o1 + c) =
+            (uint16_t)((level_bits(y[2], d_max) & 0xffu) | ((level_bits(y[3], d_max) & 0xffu) << 8));
+      }
+    }
+  }
+  // channel padding of the output rows (TMA needs 16-byte rows): zeros
+  if (blockIdx.z == 0)
+  for (int e = lane; e < 16 * (out_ld - C); e += 32) {
+    const int rr = tok0 + e / (out_ld - C), c = C + e % (out_ld - C);
+    if (rr < Nq) {
+      const int64_t o = ((int64_t)img * Nq + rr) * out_ld + c;
+      if (out_f32) out_f32[o] = 0.f;
+      if (out_spike) out_spike[o] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sigmoid_lif_kernel(const float* __restrict__ x, int8_t* __restrict__ levels,
                                                           int64_t N, float d_max) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
@@ -356,9 +445,9 @@ extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v
   const bool fast_kv = d % 4 == 0 && kv_ld % 4 == 0 && al4(k) && al4(v);
   int rc;
   if (fast_kv) {
-    // token slices of >= 512 tokens, enough blocks for ~2 per SM
-    int splits = (int)ceil_div(148 * 2, (int64_t)n * heads);
-    const int max_splits = (int)ceil_div(Nk, 512);
+    // token slices of >= 256 tokens; ~6 of these 4-warp blocks per SM keep enough loads in flight
+    int splits = (int)ceil_div(148 * 6, (int64_t)n * heads);
+    const int max_splits = (int)ceil_div(Nk, 256);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     const int tok_per_block = (int)ceil_div(ceil_div(Nk, splits), KT_TOK) * KT_TOK;
@@ -385,6 +474,27 @@ extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v
   S2F_REQUIRE(sm <= 200 * 1024, "linear_attn: heads*d*d too large for shared memory");
   const bool fast_q = d % 4 == 0 && q_ld % 4 == 0 && out_ld % 4 == 0 && al4(q) && al16(kv_ws) && (!out_f32 || al16(out_f32)) &&
                       (!out_spike || al4(out_spike));
+  const bool narrow = (double)8 * 64 * (double)Nk * d < 2147483648.0 && (double)Nk * 64 < 127.0 * 16384.0;
+  if (fast_q && narrow && d % 8 == 0 && (out_ld & 1) == 0 && (!out_spike || (reinterpret_cast<uintptr_t>(out_spike) & 1) == 0) &&
+      (!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 7) == 0)) {
+    const int KB = (d + 31) / 32;
+    // heads per block: all of them when the token tiles alone fill the GPU, fewer (a divisor of heads) otherwise
+    const int64_t tok_blocks = ceil_div(Nq, 128) * n;
+    int hpb = heads;
+    while (hpb > 1 && hpb % 2 == 0 && tok_blocks * (heads / hpb) < 148 * 2) hpb /= 2;
+    const size_t smq = (size_t)hpb * 3 * d * (32 * KB + 16);
+    if (smq <= 200 * 1024) {
+      const dim3 grid((unsigned)ceil_div(Nq, 128), n, (unsigned)(heads / hpb));
+      if (KB == 1) {
+        if (smq > 48 * 1024) cudaFuncSetAttribute(qkv_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq);
+        qkv_mma_kernel<1><<<grid, 256, smq, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld, out_ld, out_scale, d_max, hpb);
+      } else {
+        if (smq > 48 * 1024) cudaFuncSetAttribute(qkv_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq);
+        qkv_mma_kernel<2><<<grid, 256, smq, st>>>(q, kv_ws, out_spike, out_f32, Nq, heads, d, q_ld, out_ld, out_scale, d_max, hpb);
+      }
+      return check_launch("qkv_mma_kernel");
+    }
+  }
   if (fast_q) {
     const bool wide = (double)8 * 64 * (double)Nk * d >= 2147483648.0;
     // tokens per block: amortise the kv staging, keep >= ~2 blocks per SM
