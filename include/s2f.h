@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 4 */
+S2F_API int s2f_abi_version(void);   /* currently 5 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -58,6 +58,16 @@ S2F_API int s2f_nilif_fwd(const float* x, const float* scale, const float* shift
                   int64_t residual_period, const float* v_in, float* v_out, int8_t* levels, float* y_norm,
                   int T, int64_t N, int C, float d_max, float norm, int transpose_rows, int transpose_cols,
                   unsigned long long* ties, void* stream);
+
+/* Two stateless neurons on one read of x (T = 1):
+ *   levels_with_res    = NI-LIF(x*scale + shift + residual[i % residual_period])
+ *   levels_without_res = NI-LIF(x*scale + shift)
+ * -- the key / value inputs of one pyramid level of the transformer decoder, LIF(y + level_embed + pos) and
+ * LIF(y + level_embed) (dense_heads/maskformer_head.py:535-549 feeding mmcv_spike/transformer.py:318-361).
+ * N % 16 == 0, C % 4 == 0, residual_period % 4 == 0 (0: residual has N elements), 16-byte aligned pointers. */
+S2F_API int s2f_nilif_pair(const float* x, const float* scale, const float* shift, const float* residual,
+                   int64_t residual_period, int8_t* levels_with_res, int8_t* levels_without_res, int64_t N, int C,
+                   float d_max, void* stream);
 
 /* Surrogate-gradient backward of the neuron for T=1, v0=0 (quant.backward, surrogate.py:531-538,
  * then the /norm of neuron.py:197):  gx = gy / norm * 1[0 <= u <= d_max],  u as above. */

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S2F_LIB") or os.path.join(_HERE, "libs2f.so")      # S2F_LIB: experiment builds only
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class ConvArgs(C.Structure):
@@ -44,6 +44,7 @@ SIGNATURES = {
     "s2f_abi_version": (_I, []),
     "s2f_launch_count": (C.c_uint64, []),
     "s2f_nilif_fwd": (_I, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _I, _L, _I, _F, _F, _I, _I, _P, _P]),
+    "s2f_nilif_pair": (_I, [_P, _P, _P, _P, _L, _P, _P, _L, _I, _F, _P]),
     "s2f_nilif_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P]),
     "s2f_conv_simt": (_I, [C.POINTER(ConvArgs), _P]),
     "s2f_gemm_i8_tc": (_I, [C.POINTER(GemmTcArgs), _P]),

@@ -262,6 +262,86 @@ extern "C" int s2f_nilif_fwd(const float* x, const float* scale, const float* sh
   return check_launch("nilif_scalar_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two neurons on one read of x (stateless, T = 1):  with_res = NI-LIF(x*scale + shift + residual),
+// without_res = NI-LIF(x*scale + shift).  The decoder's key and value inputs of one pyramid level are
+// LIF(y + level_embed + pos) and LIF(y + level_embed) (maskformer_head.py:535-549, mmcv_spike/transformer.py:318-361):
+// y (0.5 GB at 128^2, batch 32) is read once instead of twice.  9 B per neuron instead of 14.
+namespace s2f {
+__global__ void __launch_bounds__(256, 3) nilif_pair_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ residual, int64_t res_period,
+                                                            int8_t* __restrict__ lv_res, int8_t* __restrict__ lv_plain,
+                                                            int64_t N, int C, float d_max) {
+  const int64_t nchunks = N >> 4;
+  const bool hoisted = ((int64_t)gridDim.x * blockDim.x * 16) % C == 0;
+  bool have = false;
+  float sc[16], sh[16];
+  for (int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; chunk < nchunks;
+       chunk += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = chunk << 4;
+    if (!(hoisted && have)) {
+      const int c0 = (int)(i0 % C);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int c = c0 + 4 * j;
+        if (C >= 16) { if (c >= C) c -= C; } else { c %= C; }
+        const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(shift + c));
+        sc[4 * j] = a.x; sc[4 * j + 1] = a.y; sc[4 * j + 2] = a.z; sc[4 * j + 3] = a.w;
+        sh[4 * j] = b.x; sh[4 * j + 1] = b.y; sh[4 * j + 2] = b.z; sh[4 * j + 3] = b.w;
+      }
+      have = true;
+    }
+    float u[16], w[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 q = ldg_stream(reinterpret_cast<const float4*>(x + i0) + j);
+      u[4 * j] = q.x; u[4 * j + 1] = q.y; u[4 * j + 2] = q.z; u[4 * j + 3] = q.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) u[j] = __fadd_rn(__fmul_rn(u[j], sc[j]), sh[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t r = i0 + 4 * j;
+      if (res_period > 0) r %= res_period;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(residual + r));
+      w[4 * j] = u[4 * j] + q.x; w[4 * j + 1] = u[4 * j + 1] + q.y; w[4 * j + 2] = u[4 * j + 2] + q.z; w[4 * j + 3] = u[4 * j + 3] + q.w;
+    }
+    int4 o1, o2;
+    o1.x = (int)pack_levels4(w[0], w[1], w[2], w[3], d_max); o1.y = (int)pack_levels4(w[4], w[5], w[6], w[7], d_max);
+    o1.z = (int)pack_levels4(w[8], w[9], w[10], w[11], d_max); o1.w = (int)pack_levels4(w[12], w[13], w[14], w[15], d_max);
+    o2.x = (int)pack_levels4(u[0], u[1], u[2], u[3], d_max); o2.y = (int)pack_levels4(u[4], u[5], u[6], u[7], d_max);
+    o2.z = (int)pack_levels4(u[8], u[9], u[10], u[11], d_max); o2.w = (int)pack_levels4(u[12], u[13], u[14], u[15], d_max);
+    stg_stream(reinterpret_cast<int4*>(lv_res + i0), o1);
+    stg_stream(reinterpret_cast<int4*>(lv_plain + i0), o2);
+  }
+}
+}  // namespace s2f
+
+extern "C" int s2f_nilif_pair(const float* x, const float* scale, const float* shift, const float* residual,
+                              int64_t residual_period, int8_t* levels_with_res, int8_t* levels_without_res, int64_t N,
+                              int C, float d_max, void* stream) {
+  if (N == 0) return S2F_OK;
+  S2F_REQUIRE(x && scale && shift && residual && levels_with_res && levels_without_res, "nilif_pair: null pointer");
+  S2F_REQUIRE(N % 16 == 0 && C % 4 == 0 && C >= 4 && residual_period % 4 == 0 && d_max > 0.f && d_max <= 127.f,
+              "nilif_pair: N % 16, C % 4 and residual_period % 4 must be 0");
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  S2F_REQUIRE(al(x) && al(scale) && al(shift) && al(residual) && al(levels_with_res) && al(levels_without_res),
+              "nilif_pair: pointers must be 16-byte aligned");
+  const int64_t want = ceil_div(N / 16, 256);
+  int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
+  if (want > 148 * 6) {                                            // one resident wave whose stride is a multiple of C
+    int64_t g = C, t = 4096;
+    while (t) { const int64_t r = g % t; g = t; t = r; }
+    const int64_t m = C / g;
+    if (m <= 148 * 3) blocks = (int)((148 * 3 / m) * m);
+  }
+  nilif_pair_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, residual, residual_period, levels_with_res,
+                                                             levels_without_res, N, C, d_max);
+  return check_launch("nilif_pair_kernel");
+}
+
 extern "C" int s2f_nilif_bwd(const float* x, const float* scale, const float* shift, const float* residual,
                              const float* gy, float* gx, int64_t N, int C, float d_max, float norm, void* stream) {
   S2F_REQUIRE(x && gy && gx, "nilif_bwd: x, gy, gx are required");

@@ -4,6 +4,12 @@
 
 // kernel sizes >= S2F_DW_ROLL_MIN keep the loop over kernel rows rolled: the fully unrolled 7x7 body (~60 KB of SASS)
 // thrashes the instruction cache (stall_no_instruction was the top stall; 0.62 -> 0.49 ms at 256^2 x 64 ch, batch 32)
+#ifndef S2F_DCN_MINB
+#define S2F_DCN_MINB 3
+#endif
+#ifndef S2F_DCN_UNROLL
+#define S2F_DCN_UNROLL 3
+#endif
 #ifndef S2F_DW_ROLL_MIN
 #define S2F_DW_ROLL_MIN 7
 #endif
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a
 //   loc = ref + grid*os + off*os/size ; g = 2*loc - 1 ; ix = ((g + 1)*size - 1)/2   (padded image coords)
 // One thread = one (pixel, group, 4 channels).  x is read through the 1-pixel zero border analytically.
 template <int CQ>      // float4 channel quads per group handled by one thread (Cg = 4 * CQ)
-__global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+__global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                     const int8_t* __restrict__ mask, float mask_scale,
                                                     float* __restrict__ out, int n, int H, int W, int G, int K,
                                                     float os) {
@@ -176,7 +182,8 @@ __global__ void __launch_bounds__(256) dcnv3_kernel(const float* __restrict__ x,
     float acc[CQ][4];
 #pragma unroll
     for (int c = 0; c < CQ; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
-#pragma unroll 3
+    constexpr int PT_UNROLL = S2F_DCN_UNROLL;
+#pragma unroll PT_UNROLL
     for (int pt = 0; pt < P; ++pt) {
       const float2 o2 = __ldg(reinterpret_cast<const float2*>(off) + pt);     // (x, y) offset of this point: 8-byte aligned
       const float m = (float)mk[pt] * mask_scale;

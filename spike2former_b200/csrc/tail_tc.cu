@@ -310,6 +310,13 @@ __device__ __forceinline__ float t2_sigmoid(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return r;
 }
+// the same from z = -x * log2(e): the scaling is folded into the vertical interpolation weights by the caller
+__device__ __forceinline__ float t2_sigmoid_l2(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 
 __device__ __forceinline__ uint32_t t2_pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -448,7 +455,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
             const float wt = dy ? 0.25f : 0.75f, wb = dy ? 0.75f : 0.25f;
             float sv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sv[j] = t2_sigmoid(wt * top[dx][j] + wb * bot[dx][j]) * qmask[j];
+            for (int j = 0; j < 8; ++j) sv[j] = t2_sigmoid(wt * top[dx][j] + wb * bot[dx][j]);
+            if (q0 + 8 > p.Q) {                                    // padding queries of the last group contribute 0
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sv[j] *= qmask[j];
+            }
             t2_store8(dstA, a_plane, (2 * kr + dy) * 32 + ox, g, sv);
           }
         }

@@ -627,9 +627,12 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
         _, h, w, _ = y.shape
         pe = plan.sine_pe(h, w, dev)
         ones = torch.ones(dim, dtype=torch.float32, device=dev)
-        ksp, _, _ = ops.nilif(y, scale=ones, shift=plan.level_embed[i].contiguous(), residual=pe,
-                              residual_period=pe.numel())
-        vsp, _, _ = ops.nilif(y, scale=ones, shift=plan.level_embed[i].contiguous())
+        if y.numel() % 16 == 0 and dim % 4 == 0 and pe.numel() % 4 == 0:
+            ksp, vsp = ops.nilif_pair(y, ones, plan.level_embed[i].contiguous(), pe, residual_period=pe.numel())
+        else:
+            ksp, _, _ = ops.nilif(y, scale=ones, shift=plan.level_embed[i].contiguous(), residual=pe,
+                                  residual_period=pe.numel())
+            vsp, _, _ = ops.nilif(y, scale=ones, shift=plan.level_embed[i].contiguous())
         lvl_k.append(ksp.view(n, h * w, dim)); lvl_v.append(vsp.view(n, h * w, dim)); lvl_n.append(h * w)
     states = [qf]
     for i in range(plan.num_layers):

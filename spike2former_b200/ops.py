@@ -107,6 +107,21 @@ def nilif(x, scale=None, shift=None, residual=None, residual_period=0, v_in=None
     return levels, v_out, y
 
 
+def nilif_pair(x, scale, shift, residual, residual_period=0, C_=None, d_max=D_MAX):
+    """(NI-LIF(x*scale + shift + residual), NI-LIF(x*scale + shift)) from one read of x -- the decoder's key / value
+    inputs of a pyramid level.  Returns two int8 level tensors shaped like x."""
+    _ptr(x, torch.float32, "x")
+    C_ = int(C_ if C_ is not None else x.shape[-1])
+    a = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    b = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    e0 = _p0()
+    check(_lib.lib().s2f_nilif_pair(_ptr(x), _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                    _ptr(residual, torch.float32, "residual"), int(residual_period), _ptr(a), _ptr(b),
+                                    int(x.numel()), C_, float(d_max), _stream()), "s2f_nilif_pair")
+    _p1(e0, "nilif", 0, _nb(x, a, b), f"{tuple(x.shape)} pair")
+    return a, b
+
+
 def nilif_bwd(x, gy, scale=None, shift=None, residual=None, C_=None, d_max=D_MAX, norm=NORM):
     """Surrogate gradient of the neuron (T=1): quant.backward, surrogate.py:531-538."""
     gx = torch.empty_like(x)

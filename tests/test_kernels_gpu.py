@@ -90,6 +90,20 @@ def test_nilif_positional_broadcast_and_transpose():
     assert torch.equal(got_t.cpu().view(n, N, C), want_t)
 
 
+@pytest.mark.parametrize("shape,period", [((2, 16, 16, 64), 16 * 16 * 64), ((3, 100, 256), 100 * 256), ((1, 128, 128, 256), 128 * 128 * 256)])
+def test_nilif_pair_equals_two_single_launches(shape, period):
+    """One read of x, two neurons (with / without the positional residual): bit-equal to two s2f_nilif_fwd launches."""
+    g = gen(31)
+    x = (torch.rand(shape, generator=g) * 12 - 2).cuda()
+    C = shape[-1]
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    res = torch.randn(period, generator=g).cuda()
+    a, b = ops.nilif_pair(x, sc, sh, res, residual_period=period)
+    a1, _, _ = ops.nilif(x, scale=sc, shift=sh, residual=res, residual_period=period)
+    b1, _, _ = ops.nilif(x, scale=sc, shift=sh)
+    assert torch.equal(a, a1) and torch.equal(b, b1)
+
+
 def test_nilif_backward_ste():
     """quant.backward (surrogate.py:531-538) through the reference's own autograd graph."""
     g = gen(6)
