@@ -89,6 +89,8 @@ S2F_API int s2f_nilif_bwd(const float* x, const float* scale, const float* shift
  *   reference then reinterprets (dcnv3.py:214-215, mmcv_spike/transformer.py:781,829).
  *   Generic A strides: a_stride_m / a_stride_k (in elements) are used when KH=KW=1 and they are
  *   non-zero: A[m,k] = base + img*a_img_stride + m*a_stride_m + k*a_stride_k (covers transposed operands).
+ *   The fp32 7x7 stem (Cin = 3) honours them too, with m = input pixel index and k = channel: a_stride_m = 1,
+ *   a_stride_k = H*W reads the planar NCHW image the reference's backbone receives without an NHWC copy.
  */
 typedef struct {
   const void* a; int a_is_spike; float a_scale;

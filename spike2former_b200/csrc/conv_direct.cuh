@@ -84,14 +84,16 @@ __global__ void __launch_bounds__(256, CIN_CT > 0 ? 2 : 1) conv_direct_kernel(co
         // version that unrolled a whole kernel row (24 KB) stalled on instruction fetch as often as it issued
         // (ncu: no_instruction 0.93 per issue, FMA pipe 42 %).
         const int ntaps = p.KH * KW_CT;
+        const int64_t sm = p.a_stride_m ? p.a_stride_m : CIN_CT, sk = p.a_stride_k ? p.a_stride_k : 1;
         auto load_tap = [&](int kh, int kw, float (&dst)[PX][CIN_CT]) {
 #pragma unroll
           for (int i = 0; i < PX; ++i) {
             const int hi = hb[i] + kh, wi = wb[i] + kw;
             const bool ok = hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-            const float* src = A + (((int64_t)img[i] * p.H + (ok ? hi : 0)) * p.W + (ok ? wi : 0)) * CIN_CT;
+            // pixel / channel strides: channels-last (Cin, 1) or the planar NCHW image as the caller holds it (1, H*W)
+            const float* src = A + (int64_t)img[i] * p.a_img_stride + ((int64_t)(ok ? hi : 0) * p.W + (ok ? wi : 0)) * sm;
 #pragma unroll
-            for (int ci = 0; ci < CIN_CT; ++ci) { const float v = __ldg(src + ci); dst[i][ci] = ok ? v : 0.f; }
+            for (int ci = 0; ci < CIN_CT; ++ci) { const float v = __ldg(src + ci * sk); dst[i][ci] = ok ? v : 0.f; }
           }
         };
         auto fma_tap = [&](int tap, const float (&av)[PX][CIN_CT]) {
@@ -188,7 +190,9 @@ inline bool launch_conv_direct(const ConvP& p, bool a_is_spike, cudaStream_t st)
   constexpr int PX = 2, NC = 32;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (a_is_spike || p.generic || p.w_img_stride != 0 || p.out_transposed || (p.Cout & 3)) return false;
+  const bool stem = !(p.KH == 1 && p.KW == 1) && p.Cin == 3 && p.KW == 7;
   if (p.a_img_stride != (int64_t)p.H * p.W * p.Cin) return false;
+  if (!stem && (p.a_stride_m || p.a_stride_k)) return false;
   if (!al16(p.scale) || !al16(p.shift) || !al16(p.residual) || !al16(p.out_f32) || (reinterpret_cast<uintptr_t>(p.out_spike) & 3)) return false;
   const bool is1x1 = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
   if (is1x1 && ((p.Cin & 3) || !al16(p.a))) return false;

@@ -168,6 +168,8 @@ extern "C" int s2f_conv_simt(const s2f_conv_args* a, void* stream) {
   S2F_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv_simt: empty output");
   if (launch_pw_tf32(p, a->a_is_spike != 0, (cudaStream_t)stream)) return check_launch("pw_tf32_kernel");
   if (launch_conv_direct(p, a->a_is_spike != 0, (cudaStream_t)stream)) return check_launch("conv_direct_kernel");
+  S2F_REQUIRE(p.generic || (a->a_stride_m == 0 && a->a_stride_k == 0),
+              "conv_simt: A strides are supported for 1x1 layers and for the fp32 7x7 stem (Cin = 3) only");
   const int M = p.Ho * p.Wo;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p.Cout, BN), (unsigned)p.n);
   S2F_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_simt: grid too large");

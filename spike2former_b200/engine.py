@@ -401,10 +401,15 @@ def backbone_forward(model, img, probe=NOPROBE):
     L, pr = plan.layers, probe
     B, cin, H, W = img.shape
     n = B * model.T
-    x = img.permute(0, 2, 3, 1).contiguous()
-    if model.T > 1:
-        x = x.unsqueeze(0).expand(model.T, -1, -1, -1, -1).reshape(n, H, W, cin).contiguous()
-    s, sp = L["stem"](x, n, H, W, f32=True, spike=True)
+    if model.T == 1 and cin == 3 and img.is_contiguous() and img.dtype == torch.float32:
+        # the planar NCHW batch as the caller holds it: the stem kernel reads it through pixel / channel strides, so the
+        # NHWC copy of the image is never made
+        s, sp = L["stem"](img, n, H, W, f32=True, spike=True, a_stride_m=1, a_stride_k=H * W, a_img_stride=cin * H * W)
+    else:
+        x = img.permute(0, 2, 3, 1).contiguous()       # a no-op for channels-last memory (SegDataPreProcessor output)
+        if model.T > 1:
+            x = x.unsqueeze(0).expand(model.T, -1, -1, -1, -1).reshape(n, H, W, cin).contiguous()
+        s, sp = L["stem"](x, n, H, W, f32=True, spike=True)
     H, W = H // 2, W // 2
     feats = []
 
