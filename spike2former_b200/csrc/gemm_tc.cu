@@ -568,7 +568,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   float* ss_stage = reinterpret_cast<float*>(tmem_slot + 2);      // [2][4][64] floats, 16-byte aligned
   float* stg_all = ss_stage + 2 * 4 * TC_BN;                      // [EW warps][32][COLS + 4] floats when p.staged
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform (role branches on the uniform datapath,
+  // descriptors and barrier addresses in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x % p.tiles_n;
   const int slot = blockIdx.x / p.tiles_n;
 

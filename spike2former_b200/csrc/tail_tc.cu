@@ -338,6 +338,9 @@ __device__ __forceinline__ void t2_store8(uint8_t* sA, int a_plane, int r, int g
   *reinterpret_cast<uint4*>(sA + a_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// HWC: compile-time H*W of the output (0 = run time).  With a constant plane size the per-class store offsets
+// (c * H*W * 4 bytes) fold into the STG immediates; with a run-time one every store paid six integer instructions.
+template <int HWC>
 __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) {
   extern __shared__ __align__(1024) uint8_t t2_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(t2_raw) + 1023) & ~uintptr_t(1023));
@@ -352,7 +355,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
   float* s_best = reinterpret_cast<float*>(tmem_slot + 4);          // [2 stages][128] partial argmax of the upper class half
   int* s_bidx = reinterpret_cast<int*>(s_best + 2 * TL_BM);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches on the uniform
+  // datapath and the global-memory descriptors in uniform registers (no per-store R2UR pair)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int img = blockIdx.y;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -452,10 +457,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
           if (ox < 0 || ox >= 32) continue;
 #pragma unroll
           for (int dy = 0; dy < 2; ++dy) {
-            const float wt = dy ? 0.25f : 0.75f, wb = dy ? 0.75f : 0.25f;
+            // vertical weights pre-multiplied by -log2(e): the interpolation directly yields the ex2 argument
+            const float wt = (dy ? 0.25f : 0.75f) * -1.4426950408889634f, wb = (dy ? 0.75f : 0.25f) * -1.4426950408889634f;
             float sv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sv[j] = t2_sigmoid(wt * top[dx][j] + wb * bot[dx][j]);
+            for (int j = 0; j < 8; ++j) sv[j] = t2_sigmoid_l2(wt * top[dx][j] + wb * bot[dx][j]);
             if (q0 + 8 > p.Q) {                                    // padding queries of the last group contribute 0
 #pragma unroll
               for (int j = 0; j < 8; ++j) sv[j] *= qmask[j];
@@ -522,7 +528,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * T2_ACC_COLS);
       float best = -INFINITY;
       int best_c = 0;
-      float* lg = (p.logits && ok) ? p.logits + (int64_t)img * p.K * HW + pix : nullptr;
+      // warp-uniform null-ness (p.logits), lane predicate `ok` on every store: inside a lane-divergent branch the
+      // compiler re-materialises the global-memory descriptor (2 x R2UR) for each of the 150 stores
+      float* lg = p.logits ? p.logits + (int64_t)img * p.K * HW + (ok ? pix : 0) : nullptr;
       for (int cb = (p.debug & 1) ? cb_end : cb_begin; cb < cb_end; cb += 2) {
         uint32_t v[32];
         tl_ld16(trow + cb * 16, v);
@@ -532,13 +540,25 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
         const int c0 = cb * 16;
         const int nv = min(two ? 32 : 16, p.K - c0);               // valid classes among the loaded columns
         if (lg) {
-          if (nv == 32) {
+          if (HWC > 0) {
+            float* pj = lg + (size_t)c0 * HWC;                       // one 64-bit address per 32 classes
+            if (nv == 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) lg[(uint32_t)(c0 + j) * HW4] = __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j)
+                if (ok) pj[(size_t)j * HWC] = __uint_as_float(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ok && j < nv) pj[(size_t)j * HWC] = __uint_as_float(v[j]);
+            }
           } else {
+            char* pj = reinterpret_cast<char*>(lg) + (size_t)c0 * HW4 * 4u;
+            const size_t stride = (size_t)HW4 * 4u;                  // running pointer: one 64-bit add per store
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) lg[(uint32_t)(c0 + j) * HW4] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) {
+              if (ok && j < nv) *reinterpret_cast<float*>(pj) = __uint_as_float(v[j]);
+              pj += stride;
+            }
           }
         }
         if (p.labels) {
@@ -622,11 +642,13 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
     { const char* dbg = getenv("S2F_TAIL_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
     static bool attr2 = false;
     if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(tail_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(tail_x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_x2_kernel<512 * 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "semantic_tail_tc: smem attribute: %s", cudaGetErrorString(e));
       attr2 = true;
     }
-    tail_x2_kernel<<<dim3(per_img, n), T2_THREADS, smem2, st>>>(q);
+    if ((int64_t)H * W == 512 * 512) tail_x2_kernel<512 * 512><<<dim3(per_img, n), T2_THREADS, smem2, st>>>(q);
+    else tail_x2_kernel<0><<<dim3(per_img, n), T2_THREADS, smem2, st>>>(q);
     return check_launch("tail_x2_kernel");
   }
   TailP p;
