@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) kv_mma_kernel(const int8_t* __restrict__ 
   uint8_t* kt = tiles;
   uint8_t* vt = tiles + DP * KT_LD;
   const int img = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int t_begin = blockIdx.y * tok_per_block;
   const int t_end = min(Nk, t_begin + tok_per_block);
   const int8_t* kb = k + ((int64_t)img * Nk) * ld + h * d;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) qkv_mma_kernel(const int8_t* __restrict__
     dst[0] = (uint8_t)(int8_t)v; dst[(size_t)d * KPAD] = (uint8_t)(int8_t)d1; dst[(size_t)2 * d * KPAD] = (uint8_t)(int8_t)d2;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int tok0 = blockIdx.x * 128 + warp * 16;
   if (tok0 >= Nq) return;
   const int r0 = tok0 + g, r1 = tok0 + g + 8;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : (NT <= 8 ? 3 : 2))) pw_tf3
   float* Cs = reinterpret_cast<float*>(tf_smem);              // epilogue tile [128][NP + 4], reuses the operand space
   const float* A = reinterpret_cast<const float*>(p.a);
   const int64_t M_total = (int64_t)p.n * p.Ho * p.Wo;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t tiles = ceil_div(M_total, TF_BM);
   // Register-staged software pipeline: the global loads of the next chunk (possibly the next tile's first chunk) are
   // in flight while the tensor cores work on the current one and while the epilogue runs.

@@ -261,8 +261,17 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
 // Tile geometry: output rows Y = 4*ty - 1 + {0..3} (cell rows kc = 2*ty - 1, 2*ty; rows are offset by one so that the two
 // rows of a cell never straddle tiles), columns X = 32*tx + {0..31} (cells jc = 16*tx - 1 .. 16*tx + 15; the first and
 // last cell contribute one column each).  Clamped corner indices reproduce upsample_bilinear2d's border rule.
-constexpr int T2_PROD_WARPS = 7;                            // 224 threads: 442 tasks per tile = two balanced rounds; 16 warps total -> 128 registers
-constexpr int T2_EPI_WARPS = 8;                             // two per TMEM lane quadrant, half of the classes each
+#ifndef S2F_T2_PROD
+#define S2F_T2_PROD 14
+#endif
+#ifndef S2F_T2_EPI
+#define S2F_T2_EPI 4
+#endif
+// 7 producer warps: 442 tasks per tile = two balanced rounds of 224 threads; 14: one round (the producers are a chain
+// of dependent loads / SFU ops at ~0.14 IPC per warp, so the tile time is the per-warp task count).
+constexpr int T2_PROD_WARPS = S2F_T2_PROD;
+constexpr int T2_EPI_WARPS = S2F_T2_EPI;                    // 8: two per TMEM lane quadrant, half of the classes each; 4: one per quadrant
+static_assert(T2_EPI_WARPS == 4 || T2_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quadrant");
 constexpr int T2_THREADS = (T2_PROD_WARPS + 1 + T2_EPI_WARPS) * 32;    // 544
 constexpr int T2_CELLS_X = 17;
 constexpr int T2_ACC_COLS = 256;                            // TMEM columns per accumulator buffer
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
     const int quad = warp & 3;
     const int half = (warp - (T2_PROD_WARPS + 1)) >> 2;
     const int ncol16 = p.Np / 16;
-    const int cb_begin = half ? (ncol16 + 1) / 2 : 0, cb_end = half ? ncol16 : (ncol16 + 1) / 2;
+    const int cb_begin = half ? (ncol16 + 1) / 2 : 0, cb_end = (half || T2_EPI_WARPS == 4) ? ncol16 : (ncol16 + 1) / 2;
     const uint32_t HW4 = (uint32_t)HW;
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles_img; tile += p.ctas_per_img, ++it) {
@@ -571,11 +580,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_x2_kernel(const Tail2P p) 
       }
       if (p.labels) {                                               // combine the two class halves: first maximum wins
         const int r = quad * 32 + lane;
-        if (half) { s_best[s * TL_BM + r] = best; s_bidx[s * TL_BM + r] = best_c; }
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
-        if (!half && ok) {
-          const float b1 = s_best[s * TL_BM + r];
-          p.labels[(int64_t)img * HW + pix] = (uint8_t)((b1 > best) ? s_bidx[s * TL_BM + r] : best_c);
+        if (T2_EPI_WARPS == 4) {
+          if (ok) p.labels[(int64_t)img * HW + pix] = (uint8_t)best_c;
+        } else {
+          if (half) { s_best[s * TL_BM + r] = best; s_bidx[s * TL_BM + r] = best_c; }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+          if (!half && ok) {
+            const float b1 = s_best[s * TL_BM + r];
+            p.labels[(int64_t)img * HW + pix] = (uint8_t)((b1 > best) ? s_bidx[s * TL_BM + r] : best_c);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
