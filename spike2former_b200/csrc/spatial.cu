@@ -4,6 +4,9 @@
 
 // kernel sizes >= S2F_DW_ROLL_MIN keep the loop over kernel rows rolled: the fully unrolled 7x7 body (~60 KB of SASS)
 // thrashes the instruction cache (stall_no_instruction was the top stall; 0.62 -> 0.49 ms at 256^2 x 64 ch, batch 32)
+#ifndef S2F_DCN_SPLIT8
+#define S2F_DCN_SPLIT8 0
+#endif
 #ifndef S2F_DCN_MINB
 #define S2F_DCN_MINB 3
 #endif
@@ -156,18 +159,21 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a
 // unnormalise) so sampling coordinates agree with the reference to the last bits:
 //   loc = ref + grid*os + off*os/size ; g = 2*loc - 1 ; ix = ((g + 1)*size - 1)/2   (padded image coords)
 // One thread = one (pixel, group, 4 channels).  x is read through the 1-pixel zero border analytically.
-template <int CQ>      // float4 channel quads per group handled by one thread (Cg = 4 * CQ)
+// SPLIT threads share one (pixel, group): each takes CQ of the group's channel quads (shorter dependent gather chains,
+// more warps in flight; the coordinate arithmetic is repeated, the kernel is latency-bound).
+template <int CQ, int SPLIT = 1>      // float4 channel quads per thread (Cg = 4 * CQ * SPLIT)
 __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                     const int8_t* __restrict__ mask, float mask_scale,
                                                     float* __restrict__ out, int n, int H, int W, int G, int K,
                                                     float os) {
-  constexpr int Cg = 4 * CQ;
+  constexpr int Cg = 4 * CQ * SPLIT;
   const int C = G * Cg, P = K * K, pad = (K - 1) / 2;
   const float Hin = (float)(H + 2 * pad), Win = (float)(W + 2 * pad);
-  const int64_t total = (int64_t)n * H * W * G;
+  const int64_t total = (int64_t)n * H * W * G * SPLIT;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx;
+    const int part = (int)(r % SPLIT); r /= SPLIT;
     const int g = (int)(r % G); r /= G;
     const int wo = (int)(r % W); r /= W;
     const int ho = (int)(r % H);
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* _
     const int64_t pix = ((int64_t)img * H + ho) * W + wo;
     const float* off = offset + pix * (int64_t)(G * P * 2) + (int64_t)g * P * 2;
     const int8_t* mk = mask + pix * (int64_t)(G * P) + (int64_t)g * P;
-    const float* xb = x + (int64_t)img * H * W * C + g * Cg;
+    const float* xb = x + (int64_t)img * H * W * C + g * Cg + part * 4 * CQ;
     const float half = (float)pad;   // dilation 1: (K-1)/2
     const float ref_x = __fdiv_rn((float)wo + half + 0.5f, Win);
     const float ref_y = __fdiv_rn((float)ho + half + 0.5f, Hin);
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* _
     }
 #pragma unroll
     for (int c = 0; c < CQ; ++c)
-      *reinterpret_cast<float4*>(out + pix * C + g * Cg + c * 4) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+      *reinterpret_cast<float4*>(out + pix * C + g * Cg + part * 4 * CQ + c * 4) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
   }
 }
 
@@ -352,7 +358,10 @@ extern "C" int s2f_dcnv3_gather(const float* x, const float* offset, const int8_
   cudaStream_t st = (cudaStream_t)stream;
   switch (Cg / 4) {
     case 1: dcnv3_kernel<1><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
-    case 2: dcnv3_kernel<2><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+    case 2:
+      if (S2F_DCN_SPLIT8) dcnv3_kernel<1, 2><<<grid_for(total * 2, 256), 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale);
+      else dcnv3_kernel<2><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale);
+      break;
     case 3: dcnv3_kernel<3><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
     default: dcnv3_kernel<4><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
   }
