@@ -251,11 +251,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tail_tc_kernel(const TailP p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Exact x2 upsampling (H == 2h, W == 2w; every Spike2Former config): warp-specialised, pipelined version.
 //
-//   warps 0..6   producers: build the A operand (sigmoid of the bilinear x2 upsample, fp16 hi + lo) of a 4 x 32 pixel
+//   warps 0..13  producers: build the A operand (sigmoid of the bilinear x2 upsample, fp16 hi + lo) of a 4 x 32 pixel
 //                tile.  One task = one low-resolution cell (its 4 corners are shared by a 2 x 2 block of output pixels)
 //                x 8 queries: 8 x LDG.128, 32 sigmoids, 8 x STS.128 straight into the SWIZZLE_128B K-major image.
-//   warp  7      one thread issues tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo) into one of two TMEM accumulators.
-//   warps 8..15  epilogue: tcgen05.ld the other accumulator, store the NCHW logits (128 B per class per warp) and/or the
+//   warp  14     one thread issues tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo) into one of two TMEM accumulators.
+//   warps 15..18 epilogue (one per TMEM lane quadrant): tcgen05.ld the other accumulator, store the NCHW logits (128 B
+//                per class per warp, class offsets folded into the STG immediates when H*W is the compile-time 512^2) or the
 //                fused argmax label.
 // Two A stages in shared memory and two accumulators in TMEM keep the three roles running on different tiles.
 // Tile geometry: output rows Y = 4*ty - 1 + {0..3} (cell rows kc = 2*ty - 1, 2*ty; rows are offset by one so that the two
