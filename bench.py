@@ -359,9 +359,13 @@ def main():
         micro["nilif_cfg2"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["gbs"] / pk["hbm"]
         micro["nilif_cfg2"]["frac_of_8tbs_nominal"] = micro["nilif_cfg2"]["gbs"] / 8000.0
         micro["nilif_cfg2"]["with_folded_bn_affine"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["with_folded_bn_affine"]["gbs"] / pk["hbm"]
-        # int8 tensor peak is taken as 2x the measured bf16 peak; the kernel executes 3 int8 MACs (digit planes) per
-        # algorithmic MAC, so utilisation of the int8 pipe = 3 * algorithmic / (2 * bf16 peak)
-        micro["gemm_cfg2"]["int8_pipe_utilisation_est"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] / (2.0 * pk["bf16_sustained"])
+        # the kernel executes 3 int8 MACs (digit planes) per algorithmic MAC; int8 dense peak: nominal 4.5 POP/s (2x the
+        # nominal 2.25 PFLOP/s bf16), no int8 figure is in MEASURED_PEAKS.json.  The measured tensor-pipe activity of the
+        # same launch is in the committed ncu capture.
+        micro["gemm_cfg2"]["int8_ops_executed_per_s"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] * 1e12
+        micro["gemm_cfg2"]["frac_of_nominal_int8_4500T"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] / 4500.0
+        micro["gemm_cfg2"]["algorithmic_vs_measured_bf16_burst"] = micro["gemm_cfg2"]["tflops_algorithmic"] / pk["bf16"]
+        micro["gemm_cfg2"]["ncu_tensor_pipe_active"] = "77.4 % (profiles/r1z_gemm_cfg2fc1_full.md)"
         out["kernels"] = micro
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference_run(6, 1)
