@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 5 */
+S2F_API int s2f_abi_version(void);   /* currently 6 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -198,6 +198,22 @@ S2F_API int s2f_affine_add_lif(const float* x, const float* scale, const float* 
  * the reference's fp32 sub + div. */
 S2F_API int s2f_preprocess_u8(const uint8_t* img, int chw, float* out, int n, int H, int W, int Hp, int Wp,
                       const float* mean, const float* std, int swap_rb, float pad_val, void* stream);
+
+/* SegDataPreProcessor fused INTO the stem (data_preprocessor.py:121-126 + sdtv2.py:412-421, first MS_DownSampling):
+ * uint8 image -> conv 7x7 stride 2 pad 3 over the normalised image + bias + BatchNorm -> fp32 stream and int8 levels,
+ * on tcgen05.mma.kind::i8 with an unsigned A operand (pixels are exact integers).  The fp32 image is never formed.
+ *   img        uint8 [n,H,W,3] (chw = 0) or [n,3,H,W] (chw = 1)
+ *   w_packed   three int8 digit planes of W[co, cm, kh, kw] / std[cm] in the s2f_pack_weights_i8 layout for a
+ *              [Cout, 192] matrix (taps = 1, Cin = 192), K index = kh*24 + j with j running over the 21 bytes of one
+ *              kernel row in the image's own memory order ((kw, c) for HWC, (c, kw) for CHW; channel flip folded in),
+ *              zeros elsewhere; w_ld = row length in bytes (256)
+ *   scale      [Cout]  bn_scale * rowscale
+ *   shift_tab  [4][4][4][4][Cout]  folded shift for every (top, bottom, left, right) count of kernel rows / columns cut
+ *              off by the image border: bn_shift + bn_scale * (bias - sum over the in-bounds taps of Wq * mean)
+ * Cout in {16, 32, 48, 64}; outputs channels-last [n, H/2, W/2, Cout], 16-byte aligned. */
+S2F_API int s2f_stem_u8(const uint8_t* img, int chw, const int8_t* w_packed, int w_ld, const float* scale,
+                const float* shift_tab, float* out_f32, int8_t* out_spike, int n, int H, int W, int Cout, float d_max,
+                void* stream);
 
 /* Histogram of spike levels: hist16[l] += #{i : levels[i] == l}, l = 0..15 (uint64, accumulated: zero it first).
  * The firing-rate census of tools/cal_firing_num.py:140-171 (firing rate = 1 - hist[0]/N, mean level = sum l*hist[l]/N)

@@ -77,6 +77,52 @@ class Dw:
                           want_f32=f32, want_spike=spike)
 
 
+class StemU8:
+    """The first MS_DownSampling (7x7 / 2, no LIF in front: sdtv2.py:412-421) with SegDataPreProcessor folded in
+    (data_preprocessor.py:121-126): weights W / std as int8 digit planes over the raw pixel bytes, and the mean
+    subtraction as a shift tabulated for every pattern of kernel rows / columns cut off by the image border
+    (the reference zero-pads the *normalised* image).  See csrc/stem_u8.cu."""
+
+    def __init__(self, sd, mean, std, swap_rb, chw, device):
+        w = sd["downsample1_1.encode_conv.weight"].double()                 # [Cout, 3, 7, 7]
+        s, t = fold.conv_bn(sd, "downsample1_1.encode_conv", "downsample1_1.encode_bn")
+        cout = int(w.shape[0])
+        mean = torch.tensor([float(torch.tensor(float(v), dtype=torch.float32)) for v in mean], dtype=torch.float64)
+        std = torch.tensor([float(torch.tensor(float(v), dtype=torch.float32)) for v in std], dtype=torch.float64)
+        # stored channel cs of the image is the model's channel cm = 2 - cs after inputs[[2, 1, 0]]
+        cm_of = [2, 1, 0] if swap_rb else [0, 1, 2]
+        w2d = torch.zeros(cout, 192, dtype=torch.float64)
+        mean_k = torch.zeros(192, dtype=torch.float64)
+        kh_of = torch.full((192,), -1, dtype=torch.long)
+        kw_of = torch.full((192,), -1, dtype=torch.long)
+        for kh in range(7):
+            for j in range(21):
+                kw, cs = ((j % 7), (j // 7)) if chw else ((j // 3), (j % 3))
+                cm = cm_of[cs]
+                k = kh * 24 + j
+                w2d[:, k] = w[:, cm, kh, kw] / std[cm]
+                mean_k[k], kh_of[k], kw_of[k] = mean[cm], kh, kw
+        packed, rowscale = ops.pack_weights_i8(w2d.float(), 1, 192, 3)
+        packed = packed.view(-1, 256)[:192].contiguous()                    # [3 planes x 64 channel slots, kpad = 256]
+        dig = packed.view(3, 64, 256)[:, :cout, :192].double()
+        wq = (dig[0] * 16384 + dig[1] * 128 + dig[2]) * rowscale.double()[:, None]      # the weights the kernel really uses
+        tab = torch.zeros(4, 4, 4, 4, cout, dtype=torch.float64)
+        for top in range(4):
+            for bot in range(4):
+                for lef in range(4):
+                    for rig in range(4):
+                        inb = (kh_of >= top) & (kh_of < 7 - bot) & (kw_of >= lef) & (kw_of < 7 - rig)
+                        m = (wq[:, inb] * mean_k[inb][None, :]).sum(1)
+                        tab[top, bot, lef, rig] = t - s * m
+        self.cout, self.chw = cout, chw
+        self.packed = packed.to(device)
+        self.scale = fold.f32(s * rowscale.double(), device)
+        self.tab = fold.f32(tab.reshape(256, cout), device)
+
+    def __call__(self, img_u8):
+        return ops.stem_u8(img_u8, self.packed, self.scale, self.tab, Cout=self.cout)
+
+
 def pad16(c):
     """Channel counts are padded to 16 so that every int8 activation row is a legal TMA row (16-byte strides)."""
     return (c + 15) // 16 * 16
@@ -394,14 +440,25 @@ def _ms_block(L, name, s, sp, n, H, W, heads, pr, C):
     return L[name + ".fc2"](a, n, H, W, residual=s2, f32=True, spike=True)
 
 
-def backbone_forward(model, img, probe=NOPROBE):
+def backbone_forward(model, img, probe=NOPROBE, pre=None):
     """Spiking_vit_MetaFormer.forward_features (sdtv2.py:614-651).  img fp32 [B,3,H,W] (NCHW, as the reference
     receives it).  Returns [(stream fp32 [n,h,w,C], levels int8 [n,h,w,C])] for x1..x4."""
     plan = plan_of(model, BackbonePlan)
     L, pr = plan.layers, probe
     B, cin, H, W = img.shape
     n = B * model.T
-    if model.T == 1 and cin == 3 and img.is_contiguous() and img.dtype == torch.float32:
+    if img.dtype == torch.uint8:
+        # uint8 batch: data preprocessor + stem in one tensor-core launch (SURVEY.md section 8f-2)
+        chw = img.shape[1] == 3 and img.shape[3] != 3
+        if not chw:
+            B, H, W, cin = img.shape
+        key = ("stem_u8", chw, bool(pre.channel_conversion), tuple(pre._mean_host), tuple(pre._std_host))
+        if key not in L:
+            sd = {k: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith("downsample1_1.")}
+            L[key] = StemU8(sd, pre._mean_host, pre._std_host, pre.channel_conversion, chw, img.device)
+        n = B * model.T
+        s, sp = L[key](img)
+    elif model.T == 1 and cin == 3 and img.is_contiguous() and img.dtype == torch.float32:
         # the planar NCHW batch as the caller holds it: the stem kernel reads it through pixel / channel strides, so the
         # NHWC copy of the image is never made
         s, sp = L["stem"](img, n, H, W, f32=True, spike=True, a_stride_m=1, a_stride_k=H * W, a_img_stride=cin * H * W)
@@ -488,6 +545,7 @@ def _sepconv_spike(L, prefix, key, sp, n, H, W, pr, residual=None, want_spike=Tr
 
 
 OVERLAP_FPN_TAIL = _os.environ.get("S2F_OVERLAP", "1") != "0"
+FUSE_STEM_U8 = _os.environ.get("S2F_FUSE_STEM", "1") != "0"      # uint8 input: preprocessor folded into the tensor-core stem
 
 
 def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True, side_stream=None):
@@ -800,13 +858,25 @@ def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
     """EncoderDecoder.encode_decode (encoder_decoder.py:125-133): internal tensors go straight to the head."""
     if seg.backbone.T != 1:
         raise NotImplementedError("T > 1 end-to-end inference is not used by any Spike2Former config")
+    pre = None
+    img_hw = tuple(img.shape[-2:])
     if img.dtype == torch.uint8:
-        # SegDataPreProcessor fused in front of the stem (SURVEY.md section 8f-2): uint8 -> normalised channels-last fp32
         pre = getattr(seg, "data_preprocessor", None)
         if pre is None:
             raise RuntimeError("uint8 input needs a data_preprocessor (mean / std / bgr_to_rgb) on the segmentor")
         tc = pre.test_cfg or {}
-        img = pre.normalized(img, tc.get("size", None), tc.get("size_divisor", None)).permute(0, 3, 1, 2)
-    feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if probe.active else probe)
+        chw = img.shape[1] == 3 and img.shape[3] != 3
+        h_, w_ = (img.shape[2], img.shape[3]) if chw else (img.shape[1], img.shape[2])
+        cout0 = seg.backbone.embed_dim[0] // 2
+        fused = (FUSE_STEM_U8 and pre._enable_normalize and tc.get("size") is None and tc.get("size_divisor") is None and
+                 seg.backbone.T == 1 and min(h_, w_) >= 8 and cout0 % 16 == 0 and cout0 <= 64 and img.is_contiguous())
+        if not fused:
+            # separate preprocessing kernel (padding requested, or a stem width the fused kernel does not cover)
+            img = pre.normalized(img, tc.get("size", None), tc.get("size_divisor", None)).permute(0, 3, 1, 2)
+            pre = None
+            img_hw = tuple(img.shape[-2:])
+        else:
+            img_hw = (int(h_), int(w_))
+    feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if probe.active else probe, pre=pre)
     pr = probe.scoped("decode_head.") if probe.active else probe
-    return _predict_from(seg.decode_head, feats, tuple(img.shape[-2:]), pr, labels)
+    return _predict_from(seg.decode_head, feats, img_hw, pr, labels)

@@ -357,6 +357,25 @@ def preprocess_u8(img, *, mean=None, std=None, swap_rb=False, size=None, pad_val
     return out
 
 
+def stem_u8(img, w_packed, scale, shift_tab, *, Cout, want_f32=True, want_spike=True, d_max=D_MAX):
+    """Preprocessor + 7x7/2 stem + BN (+ NI-LIF) from the uint8 batch ([n,3,H,W] or [n,H,W,3]) in one launch."""
+    if not isinstance(img, torch.Tensor) or not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or not img.is_contiguous():
+        raise S2FError("stem_u8: contiguous CUDA uint8 [n,3,H,W] or [n,H,W,3] batch required (no CPU path)")
+    chw = img.shape[1] == 3 and img.shape[3] != 3
+    n = int(img.shape[0])
+    H, W = (int(img.shape[2]), int(img.shape[3])) if chw else (int(img.shape[1]), int(img.shape[2]))
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    of = torch.empty((n, Ho, Wo, Cout), dtype=torch.float32, device=img.device) if want_f32 else None
+    os_ = torch.empty((n, Ho, Wo, Cout), dtype=torch.int8, device=img.device) if want_spike else None
+    e0 = _p0()
+    check(_lib.lib().s2f_stem_u8(C.c_void_p(img.data_ptr()), int(chw), _ptr(w_packed, torch.int8, "w_packed"),
+                                 int(w_packed.shape[-1]), _ptr(scale, torch.float32, "scale"),
+                                 _ptr(shift_tab, torch.float32, "shift_tab"), _ptr(of), _ptr(os_), n, H, W, int(Cout),
+                                 float(d_max), _stream()), "s2f_stem_u8")
+    _p1(e0, "stem_u8", 2.0 * n * Ho * Wo * Cout * 147, _nb(img, of, os_), f"{n}x{H}x{W} uint8 3->{Cout} k7s2")
+    return of, os_
+
+
 def level_hist(levels, hist=None):
     """hist[l] += number of elements at level l (l = 0..15); uint64-valued int64 tensor [16] on the device."""
     if levels.dtype != torch.int8 or not levels.is_cuda or not levels.is_contiguous():

@@ -58,12 +58,18 @@ def test_level_hist_exact(N):
     assert torch.equal(hist.cpu(), 2 * want)
 
 
-def test_uint8_images_through_the_segmentor_equal_preprocessed_fp32():
-    """encode_decode(uint8 batch) == encode_decode(reference-preprocessed fp32 batch), bit for bit, eager and graphed."""
+def _tiny_segmentor():
     cfg = s2f.configs.tiny()
     seg = s2f.build_segmentor(cfg)
     seg.load_state_dict(weights.calibrated_state(cfg, 64, 64), strict=True)
-    seg = seg.cuda()
+    return seg.cuda()
+
+
+def test_uint8_images_through_the_segmentor_equal_preprocessed_fp32(monkeypatch):
+    """Separate preprocessing kernel: encode_decode(uint8 batch) == encode_decode(reference-preprocessed fp32 batch),
+    bit for bit, eager and graphed."""
+    monkeypatch.setattr(engine, "FUSE_STEM_U8", False)
+    seg = _tiny_segmentor()
     gen = torch.Generator().manual_seed(8)
     imgs = [torch.randint(0, 256, (3, 64, 64), generator=gen, dtype=torch.uint8) for _ in range(2)]
     x = port.data_preprocess(imgs, mean=MEAN, std=STD, bgr_to_rgb=True).cuda()
@@ -74,6 +80,61 @@ def test_uint8_images_through_the_segmentor_equal_preprocessed_fp32():
         assert torch.equal(got, want)
         assert torch.equal(seg.encode_decode(u8), want)          # CUDA-graph replay with a uint8 static input
         assert torch.equal(seg.predict_labels(u8).long(), want.argmax(1))
+
+
+@pytest.mark.parametrize("H,W,layout", [(64, 64, "chw"), (64, 64, "hwc"), (37, 53, "chw"), (512, 512, "hwc"), (8, 24, "chw")])
+def test_fused_uint8_stem_vs_oracle_and_fp32_stem(H, W, layout):
+    """s2f_stem_u8 (preprocessor folded into an int8 tensor-core stem) against (i) the oracle: reference preprocessing
+    + float64 convolution + BN, (ii) the fp32 stem kernel fed by the preprocessing kernel.  The pre-activations agree
+    to 2e-5 of scale; levels may differ only where the pre-activation is within 1e-4 of a rounding boundary."""
+    import torch.nn.functional as F
+
+    from spike2former_b200 import fold
+
+    seg = _tiny_segmentor()
+    bb = seg.backbone
+    gen = torch.Generator().manual_seed(H * 1000 + W)
+    imgs = [torch.randint(0, 256, (3, H, W), generator=gen, dtype=torch.uint8) for _ in range(2)]
+    imgs[0][:, :4, :4] = 255
+    imgs[1][:, -4:, -4:] = 0
+    u8 = torch.stack(imgs)
+    dev_in = (u8 if layout == "chw" else u8.permute(0, 2, 3, 1).contiguous()).cuda()
+    sd = {k: v.detach().cpu() for k, v in bb.state_dict().items()}
+    x = port.data_preprocess(imgs, mean=MEAN, std=STD, bgr_to_rgb=True).double()
+    s_, t_ = fold.conv_bn(sd, "downsample1_1.encode_conv", "downsample1_1.encode_bn")
+    ref = F.conv2d(x, sd["downsample1_1.encode_conv.weight"].double(), stride=2, padding=3)
+    ref = (ref * s_.view(1, -1, 1, 1) + t_.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    stem = engine.StemU8(sd, MEAN, STD, True, layout == "chw", torch.device("cuda"))
+    of, os_ = stem(dev_in)
+    of, os_ = of.cpu(), os_.cpu()
+    assert of.shape == ref.shape
+    scale = max(1.0, ref.abs().max().item())
+    assert (of.double() - ref).abs().max().item() < 2e-5 * scale
+    assert torch.equal(os_, torch.round(torch.clamp(of, 0, 8)).to(torch.int8))
+    want_lv = torch.round(torch.clamp(ref, 0, 8)).to(torch.int8)
+    flips = os_ != want_lv
+    assert int((flips & ((ref - ref.floor() - 0.5).abs() > 1e-4)).sum()) == 0
+    # (ii) the unfused path of this library
+    pre = seg.data_preprocessor
+    xf = pre.normalized(dev_in)
+    plan = engine.plan_of(bb, engine.BackbonePlan)
+    f2, s2 = plan.layers["stem"](xf, 2, H, W, f32=True, spike=True)
+    assert (of - f2.cpu()).abs().max().item() < 2e-5 * scale
+    d = os_ != s2.cpu()
+    assert int((d & ((ref - ref.floor() - 0.5).abs() > 1e-4)).sum()) == 0
+
+
+def test_fused_uint8_stem_end_to_end_graph_equals_eager():
+    seg = _tiny_segmentor()
+    gen = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (2, 3, 64, 64), generator=gen, dtype=torch.uint8).cuda()
+    with torch.no_grad():
+        eager = engine.segmentor_logits(seg, u8).clone()
+        assert torch.isfinite(eager).all()
+        assert torch.equal(seg.encode_decode(u8), eager)
+        assert torch.equal(seg.predict_labels(u8).long(), eager.argmax(1))
+        hwc = u8.permute(0, 2, 3, 1).contiguous()
+        assert torch.equal(engine.segmentor_logits(seg, hwc), eager)     # same pixels, other memory order
 
 
 def test_firing_rate_census():
