@@ -27,6 +27,8 @@ constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
 constexpr int ACC_COLS = 256;
 constexpr int A_STAGE = NCHUNK * BM * 32;                       // 24 KB
 constexpr int B_BYTES = NCHUNK * NB * 32;                       // 36 KB
+constexpr int PATCH_ROWS = 2 * TH + 5, PATCH_LD = 132;          // input rows of a tile; 111 (HWC) / 3 x 40 (CHW) bytes used; 132: rows shift by one bank
+constexpr int PATCH_BYTES = PATCH_ROWS * PATCH_LD;
 
 struct Params {
   const uint8_t* img; const int8_t* w_packed; int w_ld;         // packed weights: [192 rows][w_ld bytes]
@@ -81,6 +83,41 @@ __device__ __forceinline__ uint32_t swz(int rows, int r, int k) {
   return (uint32_t)((k >> 5) * rows * 32 + r * 32 + ((((k >> 4) & 1) ^ ((r >> 2) & 1)) << 4) + (k & 15));
 }
 
+// One 32-byte K chunk of output pixel r: bytes k = 32*C .. 32*C+31 of the row (k = kh*24 + j, j < 21 pixel bytes of kernel
+// row kh in the image's memory order, zeros otherwise), gathered from the staged patch and written as two 16-byte units.
+// With lanes = consecutive pixels the two STS.128 of a quarter warp cover all 32 banks (that is what the swizzle is for).
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int C, bool CHW>
+__device__ __forceinline__ void build_chunk(uint32_t patch, uint32_t dst, int r) {
+  const uint32_t base = patch + (uint32_t)((2 * (r >> 4)) * PATCH_LD + (CHW ? 2 : 6) * (r & 15));
+  uint32_t w[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t word = 0u;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      constexpr int dummy = 0; (void)dummy;
+      const int k = 32 * C + 4 * q + b, kh = k / KROW, j = k % KROW;       // compile-time after unrolling
+      if (kh < 7 && j < 21) word |= lds_u8(base + (uint32_t)(kh * PATCH_LD + (CHW ? (j / 7) * 40 + (j % 7) : j))) << (8 * b);
+    }
+    w[q] = word;
+  }
+  const uint32_t sw = (uint32_t)((r >> 2) & 1);
+  const uint32_t row = dst + (uint32_t)(C * BM * 32 + r * 32);
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + ((0u ^ sw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + ((1u ^ sw) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+template <bool CHW>
+__device__ __forceinline__ void build_tile(uint32_t patch, uint32_t dst, int ptid) {
+  const int r = ptid & (BM - 1);
+  if (ptid < BM) { build_chunk<0, CHW>(patch, dst, r); build_chunk<2, CHW>(patch, dst, r); build_chunk<4, CHW>(patch, dst, r); }
+  else { build_chunk<1, CHW>(patch, dst, r); build_chunk<3, CHW>(patch, dst, r); build_chunk<5, CHW>(patch, dst, r); }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) stem_u8_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -91,6 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_u8_kernel(const Params p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);     // [64]
   float* s_tab = s_scale + 64;                                  // [256][Cout]
+  uint8_t* s_patch = reinterpret_cast<uint8_t*>(s_tab + 256 * p.Cout);    // [2][PATCH_BYTES]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -117,53 +155,53 @@ __global__ void __launch_bounds__(THREADS, 1) stem_u8_kernel(const Params p) {
   const int per_img = p.tiles_w * p.tiles_h;
 
   if (warp < PROD_WARPS) {
-    // ================================================================== producers: 128 pixels x 7 kernel rows = 896 runs
+    // ================================================================== producers
+    // (1) the tile's input patch (21 rows x 37 pixels x 3 channels, zeros outside the image) -> shared memory with
+    //     byte loads that run along the image rows: ~9 independent loads per thread, one latency per tile;
+    // (2) producer-only barrier; (3) 128 pixels x 8 K-rows of 24 bytes are assembled from shared memory into the
+    //     swizzled A image.  The patch buffer is double buffered like the A stage.
+    const bool chw = p.ch_stride != 1;
+    const int ptid = threadIdx.x;
+    constexpr int NIT = (PATCH_ROWS * 111 + PROD_WARPS * 32 - 1) / (PROD_WARPS * 32);
+    // per-thread patch bytes: position inside the patch (tile independent) and the registers of the NEXT tile's values
+    int po[NIT], pry[NIT], pdx[NIT], pc[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int e = ptid + i * PROD_WARPS * 32;
+      const int ee = e < PATCH_ROWS * 111 ? e : 0;
+      const int ry = ee / 111, j = ee % 111;
+      pc[i] = chw ? j / 37 : j % 3; pdx[i] = chw ? j % 37 : j / 3; pry[i] = ry;
+      po[i] = e < PATCH_ROWS * 111 ? ry * PATCH_LD + (chw ? pc[i] * 40 + pdx[i] : j) : -1;
+    }
+    uint32_t pv[NIT];
+    // all loads of a tile are issued back to back (unconditional, from clamped addresses): interleaved with the stores,
+    // every store waited for its own load -- ten DRAM / L2 latencies per tile
+    auto load_patch = [&](int tile_) {
+      const int img_ = tile_ / per_img, tt_ = tile_ % per_img;
+      const int ys_ = 2 * ((tt_ / p.tiles_w) * TH) - 3, xs_ = 2 * ((tt_ % p.tiles_w) * TW) - 3;
+      const uint8_t* ib_ = p.img + (int64_t)img_ * p.img_stride;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int y = ys_ + pry[i], x = xs_ + pdx[i];
+        const bool inb = y >= 0 && y < p.H && x >= 0 && x < p.W;
+        const uint32_t v = __ldg(ib_ + (int64_t)(inb ? y : 0) * p.row_stride + (int64_t)(inb ? x : 0) * p.px_stride + (int64_t)pc[i] * p.ch_stride);
+        pv[i] = inb ? v : 0u;
+      }
+    };
+    if (blockIdx.x < p.tiles) load_patch(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += p.ctas, ++it) {
       const int s = it & 1;
+      const uint32_t patch_s = s32(s_patch + s * PATCH_BYTES);
+#pragma unroll
+      for (int i = 0; i < NIT; ++i)
+        if (po[i] >= 0) asm volatile("st.shared.u8 [%0], %1;" ::"r"(patch_s + (uint32_t)po[i]), "r"(pv[i]) : "memory");
+      if (tile + p.ctas < p.tiles) load_patch(tile + p.ctas);    // in flight under the barrier and the A build below
       bar_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
-      uint8_t* dst = sA + s * A_STAGE;
-      const int img = tile / per_img, tt = tile % per_img;
-      const int ho0 = (tt / p.tiles_w) * TH, wo0 = (tt % p.tiles_w) * TW;
-      const uint8_t* ib = p.img + (int64_t)img * p.img_stride;
-      for (int e = threadIdx.x; e < BM * 8; e += PROD_WARPS * 32) {
-        const int r = e >> 3, kh = e & 7;                       // kh == 7: the 24 bytes of K padding (168..191)
-        uint32_t w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-        const int ho = ho0 + (r >> 4), wo = wo0 + (r & 15);
-        const int y = 2 * ho - 3 + kh, x0 = 2 * wo - 3;
-        if (kh < 7 && ho < p.Ho && wo < p.Wo && y >= 0 && y < p.H) {
-          const uint8_t* rowp = ib + (int64_t)y * p.row_stride;
-          uint32_t b[21];
-          if (p.ch_stride == 1) {                               // HWC: (kw, c) byte order
-#pragma unroll
-            for (int kw = 0; kw < 7; ++kw) {
-              const int x = x0 + kw;
-              const bool ok = x >= 0 && x < p.W;
-              const uint8_t* px = rowp + (int64_t)(ok ? x : 0) * p.px_stride;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) { const uint32_t v = __ldg(px + c); b[kw * 3 + c] = ok ? v : 0u; }
-            }
-          } else {                                              // CHW: (c, kw) byte order, three 7-byte runs
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const uint8_t* pc = rowp + (int64_t)c * p.ch_stride;
-#pragma unroll
-              for (int kw = 0; kw < 7; ++kw) {
-                const int x = x0 + kw;
-                const bool ok = x >= 0 && x < p.W;
-                const uint32_t v = __ldg(pc + (ok ? x : 0));
-                b[c * 7 + kw] = ok ? v : 0u;
-              }
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 5; ++q) w[q] = b[4 * q] | (b[4 * q + 1] << 8) | (b[4 * q + 2] << 16) | (b[4 * q + 3] << 24);
-          w[5] = b[20];
-        }
-        const int k0 = kh * KROW;                               // 24-byte runs: 4-byte words never straddle a 16-byte unit
-#pragma unroll
-        for (int q = 0; q < 6; ++q) *reinterpret_cast<uint32_t*>(dst + swz(BM, r, k0 + 4 * q)) = w[q];
-      }
+      asm volatile("bar.sync 2, %0;" ::"n"(PROD_WARPS * 32) : "memory");
+      const uint32_t dst = s32(sA + s * A_STAGE);
+      if (chw) build_tile<true>(patch_s, dst, ptid);
+      else build_tile<false>(patch_s, dst, ptid);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive(&a_full[s]);
@@ -274,7 +312,7 @@ extern "C" int s2f_stem_u8(const uint8_t* img, int chw, const int8_t* w_packed, 
   p.tiles = (int)tiles;
   p.ctas = (int)(tiles < 148 ? tiles : 148);
   p.d_max = d_max > 0.f ? d_max : 8.f;
-  const size_t smem = 1024 + stem::B_BYTES + 2 * stem::A_STAGE + 128 + 64 * 4 + (size_t)256 * Cout * 4 + 64;
+  const size_t smem = 1024 + stem::B_BYTES + 2 * stem::A_STAGE + 128 + 64 * 4 + (size_t)256 * Cout * 4 + 64 + 2 * stem::PATCH_BYTES;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(stem::stem_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
