@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(THREADS, 1) stem_u8_kernel(const Params p) {
       // taps cut off by the image border: rows above / below, columns left / right (each 0..3)
       const int top = min(max(3 - 2 * ho, 0), 3), bot = min(max(2 * ho + 4 - p.H, 0), 3);
       const int lef = min(max(3 - 2 * wo, 0), 3), rig = min(max(2 * wo + 4 - p.W, 0), 3);
-      const float* tab = s_tab + (((top * 4 + bot) * 4 + lef) * 4 + rig) * p.Cout;
+      const uint32_t tab_s = s32(s_tab) + (uint32_t)((((top * 4 + bot) * 4 + lef) * 4 + rig) * p.Cout) * 4u;
+      const uint32_t scale_s = s32(s_scale);
       const int64_t o = (((int64_t)img * p.Ho + (ok ? ho : 0)) * p.Wo + (ok ? wo : 0)) * p.Cout;
       bar_wait(&t_full[s], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -251,9 +252,17 @@ __global__ void __launch_bounds__(THREADS, 1) stem_u8_kernel(const Params p) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float y[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float v = fmaf((float)(int)d0[j], 16384.f, (float)((int)d1[j] * 128 + (int)d2[j]));
-          y[j] = fmaf(v, s_scale[j0 + j], tab[j0 + j]);
+        for (int q = 0; q < 4; ++q) {                            // explicit LDS.128 (generic loads otherwise)
+          float4 sc, sh;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(scale_s + (uint32_t)(j0 + 4 * q) * 4u));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w) : "r"(tab_s + (uint32_t)(j0 + 4 * q) * 4u));
+          const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, h4[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            const float v = fmaf((float)(int)d0[j], 16384.f, (float)((int)d1[j] * 128 + (int)d2[j]));
+            y[j] = fmaf(v, s4[e], h4[e]);
+          }
         }
         if (ok) {
           if (p.out_f32) {

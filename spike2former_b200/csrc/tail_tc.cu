@@ -344,8 +344,11 @@ __device__ __forceinline__ void t2_store8(uint8_t* sA, int a_plane, int r, int g
     lo[j] = t2_pack_half2(s[2 * j] - back.x, s[2 * j + 1] - back.y);
   }
   const int off = (g >> 3) * (TL_BM * 128) + r * 128 + ((((g & 7) ^ (r & 7))) << 4);
-  *reinterpret_cast<uint4*>(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(sA + a_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  // explicit shared-memory stores: through the generic pointer these were ST.E.128 (generic address resolution, and
+  // the compiler has to order them against the global corner loads)
+  const uint32_t a0 = tl_smem_u32(sA) + (uint32_t)off;
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + (uint32_t)a_plane), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
 }
 
 // HWC: compile-time H*W of the output (0 = run time).  With a constant plane size the per-class store offsets
