@@ -92,21 +92,34 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a
       }
     }
     constexpr int KH_UNROLL = KS >= S2F_DW_ROLL_MIN ? 1 : KS;
+    constexpr bool PREFETCH = (KS >= S2F_DW_ROLL_MIN) && sizeof(AT) == 1;     // rolled row loop: fetch row kh+1 under row kh
+    auto load_row = [&](int kh_, RT (&dst)[TW + KS - 1]) {
+      const int hi_ = ho - pad + kh_;
+      const AT* row_ = base + (int64_t)min(max(hi_, 0), H - 1) * W * C;
+      if (CT && interior) {
+        const AT* row0 = row_ + wi0 * CT;
+#pragma unroll
+        for (int i = 0; i < TW + KS - 1; ++i) dst[i] = load_raw(row0 + i * CT);
+      } else {
+#pragma unroll
+        for (int i = 0; i < TW + KS - 1; ++i) dst[i] = load_raw(row_ + off[i]);
+      }
+    };
+    RT nxt[TW + KS - 1];
+    if (PREFETCH) load_row(0, nxt);
 #pragma unroll KH_UNROLL
     for (int kh = 0; kh < KS; ++kh) {
       // rows outside the map are loaded from the clamped row and masked: no branch, so the loads of all kernel rows can
       // be scheduled ahead of the FFMAs of the first one
       const int hi = ho - pad + kh;
       const bool row_ok = hi >= 0 && hi < H;
-      const AT* row = base + (int64_t)min(max(hi, 0), H - 1) * W * C;
       RT raw[TW + KS - 1];
-      if (CT && interior) {
-        const AT* row0 = row + wi0 * CT;
+      if (PREFETCH) {
 #pragma unroll
-        for (int i = 0; i < TW + KS - 1; ++i) raw[i] = load_raw(row0 + i * CT);
+        for (int i = 0; i < TW + KS - 1; ++i) raw[i] = nxt[i];
+        if (kh + 1 < KS) load_row(kh + 1, nxt);
       } else {
-#pragma unroll
-        for (int i = 0; i < TW + KS - 1; ++i) raw[i] = load_raw(row + off[i]);
+        load_row(kh, raw);
       }
       float4 wv[KS];
 #pragma unroll
