@@ -172,13 +172,15 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a
 // unnormalise) so sampling coordinates agree with the reference to the last bits:
 //   loc = ref + grid*os + off*os/size ; g = 2*loc - 1 ; ix = ((g + 1)*size - 1)/2   (padded image coords)
 // One thread = one (pixel, group, 4 channels).  x is read through the 1-pixel zero border analytically.
+struct DcnGrid { float gx[25], gy[25]; };       // per sampling point: grid offset * offset_scale (K <= 5)
+
 // SPLIT threads share one (pixel, group): each takes CQ of the group's channel quads (shorter dependent gather chains,
 // more warps in flight; the coordinate arithmetic is repeated, the kernel is latency-bound).
 template <int CQ, int SPLIT = 1>      // float4 channel quads per thread (Cg = 4 * CQ * SPLIT)
 __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                     const int8_t* __restrict__ mask, float mask_scale,
                                                     float* __restrict__ out, int n, int H, int W, int G, int K,
-                                                    float os) {
+                                                    float os, const DcnGrid grid) {
   constexpr int Cg = 4 * CQ * SPLIT;
   const int C = G * Cg, P = K * K, pad = (K - 1) / 2;
   const float Hin = (float)(H + 2 * pad), Win = (float)(W + 2 * pad);
@@ -206,11 +208,10 @@ __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* _
     for (int pt = 0; pt < P; ++pt) {
       const float2 o2 = __ldg(reinterpret_cast<const float2*>(off) + pt);     // (x, y) offset of this point: 8-byte aligned
       const float m = (float)mk[pt] * mask_scale;
-      // point order of _generate_dilation_grids: x index is the slow one (dcnv3_func.py:125-137)
-      const float gx = __fdiv_rn((float)(pt / K) - half, Win);
-      const float gy = __fdiv_rn((float)(pt % K) - half, Hin);
-      const float lx = __fadd_rn(__fadd_rn(ref_x, __fmul_rn(gx, os)), __fdiv_rn(__fmul_rn(o2.x, os), Win));
-      const float ly = __fadd_rn(__fadd_rn(ref_y, __fmul_rn(gy, os)), __fdiv_rn(__fmul_rn(o2.y, os), Hin));
+      // point order of _generate_dilation_grids: x index is the slow one (dcnv3_func.py:125-137); the per-point grid
+      // terms (gx * os, gy * os) depend on the point only and come precomputed (same fp32 operations, done once)
+      const float lx = __fadd_rn(__fadd_rn(ref_x, grid.gx[pt]), __fdiv_rn(__fmul_rn(o2.x, os), Win));
+      const float ly = __fadd_rn(__fadd_rn(ref_y, grid.gy[pt]), __fdiv_rn(__fmul_rn(o2.y, os), Hin));
       const float sgx = __fadd_rn(__fmul_rn(2.f, lx), -1.f), sgy = __fadd_rn(__fmul_rn(2.f, ly), -1.f);
       const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgx, 1.f), Win), -1.f), 0.5f);
       const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgy, 1.f), Hin), -1.f), 0.5f);
@@ -369,14 +370,25 @@ extern "C" int s2f_dcnv3_gather(const float* x, const float* offset, const int8_
   const int64_t total = (int64_t)n * H * W * G;
   const int grid = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  S2F_REQUIRE(K <= 5, "dcnv3_gather: K must be <= 5");
+  DcnGrid dg;
+  {
+    const int pad = (K - 1) / 2;
+    const float Hin = (float)(H + 2 * pad), Win = (float)(W + 2 * pad), half = (float)pad;
+    for (int pt = 0; pt < K * K; ++pt) {      // the same fp32 operations the kernel used to repeat per thread
+      const volatile float gx = ((float)(pt / K) - half) / Win, gy = ((float)(pt % K) - half) / Hin;
+      const volatile float gxs = gx * offset_scale, gys = gy * offset_scale;
+      dg.gx[pt] = gxs; dg.gy[pt] = gys;
+    }
+  }
   switch (Cg / 4) {
-    case 1: dcnv3_kernel<1><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+    case 1: dcnv3_kernel<1><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg); break;
     case 2:
-      if (S2F_DCN_SPLIT8) dcnv3_kernel<1, 2><<<grid_for(total * 2, 256), 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale);
-      else dcnv3_kernel<2><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale);
+      if (S2F_DCN_SPLIT8) dcnv3_kernel<1, 2><<<grid_for(total * 2, 256), 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg);
+      else dcnv3_kernel<2><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg);
       break;
-    case 3: dcnv3_kernel<3><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
-    default: dcnv3_kernel<4><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale); break;
+    case 3: dcnv3_kernel<3><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg); break;
+    default: dcnv3_kernel<4><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg); break;
   }
   return check_launch("dcnv3_kernel");
 }
