@@ -5,12 +5,14 @@
 //   B  fp32 weights split on the host into `pieces` signed base-128 digit planes (int8) with one power-of-two
 //      scale per output channel; the planes of a 64-channel tile are stacked along N, so ONE
 //      tcgen05.mma.kind::i8 (M=128, N=64*pieces, K=32) feeds all planes and the int32 accumulation is exact;
-//   D  int32 accumulators in TMEM, read back with tcgen05.ld by four epilogue warps that recombine the digit
-//      planes, apply the folded BatchNorm affine (+ residual) and emit fp32 and/or NI-LIF int8 levels.
+//   D  int32 accumulators in TMEM, read back with tcgen05.ld by the epilogue warps, which recombine the digit planes,
+//      apply the folded BatchNorm affine (+ residual / fused FPN merge) and emit fp32 and/or NI-LIF int8 levels.
+//      The epilogue is compiled per output kind (EPI_GENERIC / EPI_SPIKE / EPI_STAGED / EPI_STAGED_UP, see below).
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, column half = (warp_id - 2) / 4).  The kernel is
 // persistent (one CTA per SM) with two accumulators in TMEM, so the epilogue of a tile overlaps the next main loop.
+// The warp index is taken through a shuffle so that the compiler treats the role branches as warp-uniform.
 #include <cuda.h>
 #include <limits.h>
 #include <math.h>
