@@ -7,6 +7,7 @@ declared in include/s2f.h (csrc/ -> libs2f.so).  No CPU fallback.
 """
 from . import configs  # noqa: F401
 from .registry import MODELS, ConfigDict  # noqa: F401
+from .neuron import Q_IFNode  # noqa: F401
 from .models import (  # noqa: F401
     DCNTransformerEncoderPixelDecoder,
     EncoderDecoder,
@@ -16,4 +17,4 @@ from .models import (  # noqa: F401
 )
 
 __all__ = ["MODELS", "ConfigDict", "Spiking_vit_MetaFormer", "MaskFormerHead",
-           "DCNTransformerEncoderPixelDecoder", "EncoderDecoder", "build_segmentor", "configs"]
+           "DCNTransformerEncoderPixelDecoder", "EncoderDecoder", "build_segmentor", "configs", "Q_IFNode"]

@@ -130,6 +130,34 @@ def test_nilif_backward_ste():
     assert torch.equal(got.cpu(), x.grad)
 
 
+def test_q_ifnode_module_is_a_drop_in_with_surrogate_gradient():
+    """spike2former_b200.Q_IFNode: forward == the reference neuron (values in {0, 1/8, .., 1}), membrane carried until
+    reset() (MemoryModule semantics), backward == quant.backward / 8 (STE), all through the C ABI."""
+    import spike2former_b200 as s2f
+
+    g = gen(41)
+    x = (torch.rand(4, 33, 64, generator=g) * 12 - 2)
+    x.view(-1)[:9] = torch.tensor([0.5, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5])
+    node = s2f.Q_IFNode()
+    xc = x.cuda().requires_grad_(True)
+    y = node(xc)
+    lv, v = port.nilif_reference(torch.stack([x, x]), T=2)               # oracle: two steps with the membrane carried
+    assert torch.equal(y.detach().cpu(), lv[0].float() / 8)
+    gy = torch.randn(x.shape, generator=g)
+    y.backward(gy.cuda())
+    want = gy / 8
+    want[(x < 0) | (x > 8)] = 0
+    assert torch.equal(xc.grad.cpu(), want)
+    y2 = node(x.cuda())                                                  # second call: v from the first one
+    assert torch.equal(y2.cpu(), lv[1].float() / 8)
+    assert torch.equal(node.v.cpu(), v)
+    node.reset()
+    assert node.v == 0.0
+    assert torch.equal(node(x.cuda()).cpu(), lv[0].float() / 8)
+    with pytest.raises(RuntimeError):
+        node(x)                                                          # CPU tensor: no CPU path
+
+
 # --------------------------------------------------------------------------------------------- conv / linear
 def _levels(shape, g, hi=9):
     return torch.randint(0, hi, shape, generator=g, dtype=torch.int8)
