@@ -1,3 +1,5 @@
+"""Launches the fused uint8 stem (s2f_stem_u8) three times at batch 32, 512x512, CHW input -- the target of
+    ncu --set full -k regex:stem_u8 -s 2 -c 1 -o gpurun_out/stem python tools/prof_stem_u8.py      (GPU box only)"""
 import torch, sys
 sys.path.insert(0, ".")
 import spike2former_b200 as s2f
