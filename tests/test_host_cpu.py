@@ -95,3 +95,51 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_fused_stem_host_folding_reproduces_the_oracle_on_cpu():
+    """engine.StemU8 (host side of s2f_stem_u8): digit planes of W / std over the raw bytes + the border-tabulated shift.
+    The kernel's arithmetic is emulated here with exact integer matmuls; the result must equal reference preprocessing +
+    float64 convolution + BatchNorm (oracle) to 2e-5 of scale, for both memory orders, including every border class."""
+    import torch.nn.functional as F
+
+    from oracle import port, weights
+    from spike2former_b200 import configs, engine, fold
+
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    cfg = configs.tiny()
+    P = weights.calibrated_state(cfg, 64, 64)
+    sd = {k[len("backbone."):]: v for k, v in P.items() if k.startswith("backbone.downsample1_1.")}
+    g = torch.Generator().manual_seed(77)
+    H, W = 21, 18
+    imgs = [torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8) for _ in range(2)]
+    x = port.data_preprocess(imgs, mean=mean, std=std, bgr_to_rgb=True).double()
+    s_, t_ = fold.conv_bn(sd, "downsample1_1.encode_conv", "downsample1_1.encode_bn")
+    ref = F.conv2d(x, sd["downsample1_1.encode_conv.weight"].double(), stride=2, padding=3)
+    ref = ref * s_.view(1, -1, 1, 1) + t_.view(1, -1, 1, 1)                       # [n, Cout, Ho, Wo]
+    Ho, Wo = ref.shape[-2:]
+    for chw in (True, False):
+        stem = engine.StemU8(sd, mean, std, True, chw, torch.device("cpu"))
+        cout = stem.cout
+        dig = stem.packed.view(3, 64, 256)[:, :cout, :192].to(torch.int64)
+        wint = dig[0] * 16384 + dig[1] * 128 + dig[2]                             # exact integer weights [Cout, 192]
+        tab = stem.tab.view(4, 4, 4, 4, cout).double()
+        raw = torch.stack(imgs).to(torch.int64)                                  # [n, 3, H, W] stored (BGR) order
+        out = torch.zeros(2, cout, Ho, Wo, dtype=torch.float64)
+        for ho in range(Ho):
+            for wo in range(Wo):
+                a = torch.zeros(2, 192, dtype=torch.int64)
+                for kh in range(7):
+                    y = 2 * ho - 3 + kh
+                    for kw in range(7):
+                        xx = 2 * wo - 3 + kw
+                        if 0 <= y < H and 0 <= xx < W:
+                            for c in range(3):
+                                j = c * 7 + kw if chw else kw * 3 + c
+                                a[:, kh * 24 + j] = raw[:, c, y, xx]
+                top, bot = min(max(3 - 2 * ho, 0), 3), min(max(2 * ho + 4 - H, 0), 3)
+                lef, rig = min(max(3 - 2 * wo, 0), 3), min(max(2 * wo + 4 - W, 0), 3)
+                S = (a @ wint.t()).double()                                       # the int32 accumulators, exactly
+                out[:, :, ho, wo] = S * stem.scale.double()[None, :] + tab[top, bot, lef, rig][None, :]
+        scale = max(1.0, ref.abs().max().item())
+        assert (out - ref).abs().max().item() < 2e-5 * scale, chw
