@@ -38,6 +38,12 @@ def to_engine_layout(o: torch.Tensor, mine_shape, layout: str) -> torch.Tensor:
     """Oracle tensor -> the engine's layout (see engine.NullProbe).  The engine may carry zero-padded channels
     (last dim rounded up to 16 for TMA); the oracle tensor is zero-padded to match."""
     mine_shape = tuple(mine_shape)
+    if isinstance(layout, tuple):                       # ("cm_heads", heads, d, dp): per-head channel padding
+        _, heads, d, dp = layout
+        core = to_engine_layout(o, mine_shape[:-1] + (heads * d,), "cm")
+        out = torch.zeros(mine_shape[:-1] + (heads, dp), dtype=core.dtype)
+        out[..., :d] = core.reshape(mine_shape[:-1] + (heads, d))
+        return out.reshape(mine_shape)
     c_ref = o.shape[1] if layout == "cm" else o.shape[-1]
     if layout in ("cm", "same") and mine_shape[-1] > c_ref and (mine_shape[-1] - c_ref) < 16 and \
             o.numel() // c_ref * mine_shape[-1] == int(torch.tensor(mine_shape).prod()):
@@ -125,3 +131,59 @@ class TeacherProbe:
             unexplained=sum(e["unexplained"] for e in sp), maxdev=max([e["maxdev"] for e in sp] or [0]),
             reals=len(re_), worst_rel=max([e["rel"] for e in re_] or [0.0]),
             worst_real=max(re_, key=lambda e: e["rel"])["name"] if re_ else None, unknown=unk)
+
+
+class ObserverProbe:
+    """Free-running parity: taps every tensor the PRODUCTION path hands over (engine.NullProbe docstring) without
+    replacing anything or switching code paths; under CUDA-graph capture a tap is one extra copy node.
+    `compare(taps)` then counts, neuron by neuron, the levels that differ from the oracle's."""
+    active = False
+    observe = True
+
+    def __init__(self, prefix="", spikes=None, reals=None):
+        self.prefix = prefix
+        self.spikes = {} if spikes is None else spikes
+        self.reals = {} if reals is None else reals
+
+    def scoped(self, prefix):
+        return ObserverProbe(self.prefix + prefix, self.spikes, self.reals)
+
+    def spike(self, name, t, layout="cm"):
+        self.spikes[self.prefix + name] = (t.detach().clone(memory_format=torch.contiguous_format), layout)
+        return t
+
+    def real(self, name, t, layout="cm"):
+        self.reals[self.prefix + name] = (t.detach().clone(memory_format=torch.contiguous_format), layout)
+        return t
+
+    def compare(self, taps, marks=None):
+        """-> dict(neurons, spike_elems, flips, maxdev, per_neuron=[(name, flips, numel)] in the engine's call order,
+        missing=[oracle neurons the engine never showed], reals=[(name, rel err)])."""
+        per, total, flips, maxdev = [], 0, 0, 0
+        for name, (t, layout) in self.spikes.items():
+            if name not in taps:
+                continue
+            lv = taps[name][1]
+            got = t.cpu()
+            if layout == "same" and got.dim() == lv.dim() and got.shape[0] == 1 and lv.shape[0] > 1:
+                lv = lv[-1:]                                  # last-only SDME: the engine keeps decoder output [-1]
+            want = to_engine_layout(lv, got.shape, layout)
+            diff = got != want
+            f = int(diff.sum())
+            if f:
+                maxdev = max(maxdev, int((got.int() - want.int()).abs().max()))
+            per.append((name, f, lv.numel()))
+            total += lv.numel(); flips += f
+        reals = []
+        for name, (t, layout) in self.reals.items():
+            ref = taps[name][0] if name in taps else (marks or {}).get(name)
+            if ref is None:
+                continue
+            got = t.cpu()
+            if layout == "same" and got.dim() == ref.dim() and got.shape[0] == 1 and ref.shape[0] > 1:
+                ref = ref[-1:]
+            want = to_engine_layout(ref, got.shape, layout)
+            reals.append((name, float((got - want).abs().max() / want.abs().max().clamp(min=1e-6))))
+        seen = {n for n, _, _ in per}
+        return dict(neurons=len(per), spike_elems=total, flips=flips, maxdev=maxdev, per_neuron=per,
+                    missing=[n for n in taps if n not in seen], reals=reals)

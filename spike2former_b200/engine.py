@@ -330,8 +330,15 @@ def plan_of(model, kind):
 class NullProbe:
     """Production probe: does nothing.  Layout tags tell a test probe how the reference lays the tensor out:
     'cm'  reference is channel-major [n, C, *spatial], ours is channels-last [n, *spatial, C];
-    'same' identical flat order;  'reint_T' our buffer holds the reference's [C, nq] reinterpretation transposed."""
+    'same' identical flat order;  'reint_T' our buffer holds the reference's [C, nq] reinterpretation transposed;
+    ('cm_heads', heads, d, dp): channels-last with every head's d channels padded to dp (stage 4: 45 -> 48).
+
+    `active` probes (teacher forcing, census) may replace tensors and make the engine materialise what its fusions
+    hide; an `observe` probe (oracle/probe.py::ObserverProbe) only LOOKS: the engine takes exactly the production
+    code path (fused FPN merge, strided q|k|v, side stream, last-only SDME, CUDA-graph capture) and merely hands the
+    probe every tensor that path produces anyway."""
     active = False
+    observe = False
 
     def spike(self, name, t, layout="cm"):
         return t
@@ -423,6 +430,9 @@ def _ms_block(L, name, s, sp, n, H, W, heads, pr, C):
     else:
         q, k, v = qkv[..., :CA], qkv[..., CA:2 * CA], qkv[..., 2 * CA:]
         ld = 3 * CA
+        if pr.observe:
+            for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+                pr.spike(f"{name}.attn.{nm}_spike", t, ("cm_heads", heads, d, dp))
     out_w = CA if dp != d else CP
     att, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=dp, q_ld=ld, kv_ld=ld, out_ld=out_w,
                              out_scale=(d ** -0.5) * INV ** 3)
@@ -432,6 +442,8 @@ def _ms_block(L, name, s, sp, n, H, W, heads, pr, C):
             att = padded(pr.spike(f"{name}.attn.attn_spike", ref_layout(att)))
         else:
             att = pr.spike(f"{name}.attn.attn_spike", att)
+    elif pr.observe:
+        pr.spike(f"{name}.attn.attn_spike", att, ("cm_heads", heads, d, dp) if dp != d else "cm")
     s2, sp2 = L[name + ".proj"](att, n, H, W, residual=s, f32=True, spike=True)
     s2 = pr.real(f"{name}.mlp.fc1_spike", s2)
     sp2 = pr.spike(f"{name}.mlp.fc1_spike", sp2)
@@ -799,7 +811,10 @@ def head_predict(model, x, img_shape, probe=NOPROBE):
 class GraphedForward:
     """One captured CUDA graph of segmentor_logits for a fixed input shape (see EncoderDecoder._run)."""
 
-    def __init__(self, seg, example, labels):
+    def __init__(self, seg, example, labels, probe=NOPROBE):
+        """probe: an observing probe (tests) whose taps become extra copy nodes of the captured graph."""
+        if probe.active:
+            raise RuntimeError("an active probe changes the code path and cannot be captured; use an observer")
         self.static_in = torch.empty_like(example)
         self.static_in.copy_(example)
         side = torch.cuda.Stream(device=example.device)
@@ -812,7 +827,7 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         l0 = ops.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad():
-            self.static_out = segmentor_logits(seg, self.static_in, labels=labels)
+            self.static_out = segmentor_logits(seg, self.static_in, probe, labels=labels)
         self.launches = ops.launch_count() - l0    # kernels of this library inside one replay
 
     def __call__(self, x):
@@ -877,6 +892,7 @@ def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
             img_hw = tuple(img.shape[-2:])
         else:
             img_hw = (int(h_), int(w_))
-    feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if probe.active else probe, pre=pre)
-    pr = probe.scoped("decode_head.") if probe.active else probe
+    scoped = probe.active or probe.observe
+    feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if scoped else probe, pre=pre)
+    pr = probe.scoped("decode_head.") if scoped else probe
     return _predict_from(seg.decode_head, feats, img_hw, pr, labels)

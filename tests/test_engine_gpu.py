@@ -92,6 +92,33 @@ def test_cityscapes_config_teacher_forced_256x512():
     assert rel < 1e-2 and agree >= 0.999
 
 
+def test_cityscapes_config_teacher_forced_full_1024x2048():
+    """BASELINE config 4 at its full shape (batch 1): 1.53 G spike elements, 16384/65536/262144-key cross-attention
+    (the 64-bit accumulation path of the attention kernel), 8192-token SDSA, 512 x 1024 mask maps."""
+    from spike2former_b200 import engine, synth
+
+    cfg = s2f.configs.cityscapes()
+    P = synth.synthetic_checkpoint("cityscapes", cfg)            # calibrated at 1024 x 2048 (tools/make_calibration.py)
+    img = weights.test_image(cfg, 1024, 2048)
+    taps, marks, ref = probe.record_oracle(P, cfg, img)
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(P, strict=True)
+    seg = seg.cuda()
+    pr = probe.TeacherProbe(taps, marks, torch.device("cuda"))
+    with torch.no_grad():
+        logits = engine.segmentor_logits(seg, img.cuda(), pr).cpu()
+    s = _report(pr)
+    assert s["unknown"] == [] and s["neurons"] == 270 and s["spike_elems"] == 1526936576
+    assert s["unexplained"] == 0 and s["maxdev"] <= 1
+    assert s["flips"] <= 1e-5 * s["spike_elems"]
+    assert s["worst_rel"] < 1e-4, s["worst_real"]
+    rel = float((logits - ref).abs().max() / ref.abs().max())
+    agree = float((logits.argmax(1) == ref.argmax(1)).float().mean())
+    ncls = ref.argmax(1).unique().numel()
+    print(f"Cityscapes 1024x2048: logits rel err {rel:.3e}, argmax agreement {agree:.6f}, classes {ncls}")
+    assert rel < 1e-2 and agree >= 0.999 and ncls >= 10
+
+
 def test_free_running_report():
     """No forcing: reports how spike flips grow through the (chaotic, random-init) network."""
     cfg = s2f.configs.tiny()

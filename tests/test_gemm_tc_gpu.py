@@ -138,3 +138,33 @@ def test_gemm_tc_fused_fpn_merge_matches_separate_kernels(cin, H, W):
     assert int((flips & ((want_f - want_f.floor() - 0.5).abs() > 1e-4)).sum()) == 0      # only at rounding ties
     up = F.interpolate(prev.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
     assert (got_f - (cur + up)).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,k", [(256, 256, 1), (128, 512, 3), (1024, 256, 1)])
+def test_gemm_tc_heavy_tailed_rows(cin, cout, k):
+    """Rows with a few large weights over a background ~1000x smaller (BN-folded checkpoints, and the stable synthetic
+    init): the 21-bit fixed point is relative to the row maximum, so small weights keep only ~11 bits each -- the
+    OUTPUT error must still be bounded by 2^-21 x row maximum per term, i.e. as tight as for a flat row."""
+    g = torch.Generator().manual_seed(7)
+    n, H, W = 2, 16, 16
+    K = cin * k * k
+    a = torch.randint(0, 9, (n, H, W, cin), generator=g, dtype=torch.int8)
+    w2d = torch.randn(cout, K, generator=g) * (1e-3 / K ** 0.5)
+    idx = torch.stack([torch.randperm(K, generator=g)[:3] for _ in range(cout)])
+    w2d.scatter_add_(1, idx, torch.randn(cout, 3, generator=g))
+    w2d[0] = torch.randn(K, generator=g).abs() * 1e-6                  # a row of tiny weights only
+    w2d[1, 5] = 1000.0                                                 # one huge outlier
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    w4 = w2d.view(cout, k, k, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d((a.double() / 8).permute(0, 3, 1, 2), w4.double(), padding=(k - 1) // 2).permute(0, 2, 3, 1)
+    ref = ref * sc.double() + sh.double()
+    packed, rowscale = ops.pack_weights_i8(w2d, k * k, cin, 3)
+    of, os_ = ops.gemm_tc(a.cuda(), packed.cuda(), n=n, H=H, W=W, Cin=cin, Cout=cout,
+                          scale=(sc.double() * rowscale.double() / 8).float().cuda(), shift=sh.cuda(), k=k, pad=(k - 1) // 2,
+                          want_f32=True, want_spike=True)
+    rowmax = w2d.abs().amax(1).double()
+    # per output: K terms x level <= 1 x half a quantisation step (< 2^-20 rowmax), plus fp32 rounding of the result
+    bound = (K * 2.0 ** -20 * rowmax * sc.double()).view(1, 1, 1, -1) + 3e-7 * ref.abs().clamp(min=1.0)
+    err = (of.cpu().double() - ref).abs()
+    assert bool((err <= bound).all()), float((err / bound).max())
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))

@@ -36,6 +36,29 @@ def test_nilif_bit_exact(shape):
     assert int(cnt.item()) == port.count_ties(x)
 
 
+@pytest.mark.parametrize("d_max,norm", [(4.0, 4.0), (8.0, 8.0), (4.0, 8.0)])
+def test_nilif_d4_variant_end_to_end(d_max, norm):
+    """The D = 4 neuron of BASELINE.json config 2 (Quant4 / Multispike_norm: surrogate.py:541-557,
+    mmseg/models/utils/Qtrick.py:4-38: round(clamp(x, 0, 4)) / 4) through the same kernel: levels, normalised
+    output, tie count, membrane over T and the STE window [0, D]."""
+    g = gen(41)
+    x = torch.rand(64, 1024, 512 // 8, generator=g) * 7 - 1.5
+    tv = torch.tensor([k + 0.5 for k in range(5)] + [4.0, 4.25, 4.5, 3.9999998, -0.0])
+    x.view(-1)[: tv.numel()] = tv
+    want = torch.round(torch.clamp(x, 0, d_max))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    got, _, y = ops.nilif(x.cuda(), want_norm=True, d_max=d_max, norm=norm, ties=cnt)
+    assert torch.equal(got.cpu(), want.to(torch.int8)) and torch.equal(y.cpu(), want / norm)
+    assert int(cnt.item()) == port.count_ties(x, d_max) and int(got.max()) == int(d_max)
+    xs = (torch.rand(3, 4096, generator=g) - 0.3) * 5
+    lv, v = port.nilif_reference(xs, d_max=d_max, T=3)
+    got, vo, _ = ops.nilif(xs.cuda(), want_v_out=True, T=3, C_=64, d_max=d_max, norm=norm)
+    assert torch.equal(got.cpu(), lv) and torch.equal(vo.cpu(), v)
+    gy = torch.randn(4096, generator=g)
+    gx = ops.nilif_bwd(xs[0].contiguous().cuda(), gy.cuda(), C_=64, d_max=d_max, norm=norm).cpu()
+    assert torch.equal(gx, gy / norm * ((xs[0] >= 0) & (xs[0] <= d_max)).float())
+
+
 def test_nilif_known_answers():
     """SURVEY.md section 0.4 [probed]: Q_IFNode on [0.5,1.5,2.5,3.5,7.5] gives levels [0,2,2,4,8]."""
     x = torch.tensor([0.5, 1.5, 2.5, 3.5, 7.5] + [0.0] * 11)
@@ -245,7 +268,8 @@ def test_dwconv_spike_operands_bitwise_equal_to_fp32_operands(k, C, H, W):
     assert torch.equal(s_i, s_f)
 
 
-@pytest.mark.parametrize("n,Nq,Nk,heads,d", [(2, 64, 64, 4, 16), (1, 20, 300, 4, 16), (2, 100, 1024, 8, 32), (1, 64, 64, 8, 45)])
+@pytest.mark.parametrize("n,Nq,Nk,heads,d", [(2, 64, 64, 4, 16), (1, 20, 300, 4, 16), (2, 100, 1024, 8, 32), (1, 64, 64, 8, 45),
+                                             (2, 1024, 1024, 8, 64), (1, 100, 4096, 8, 64)])     # d = 64: BASELINE config 2
 def test_linear_attn_exact(n, Nq, Nk, heads, d):
     """(Q K^T) V == Q (K^T V) on integer levels; compared with the reference's op order in float64."""
     g = gen(9)
