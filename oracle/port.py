@@ -34,8 +34,9 @@ class Ctx:
     tap:       callable(name, pre_activation, spike_levels) called at every neuron.
     """
 
-    def __init__(self, P, calibrate=False, tap=None, d_max=8.0, norm=8.0):
+    def __init__(self, P, calibrate=False, tap=None, d_max=8.0, norm=8.0, mutate=None):
         self.P, self.calibrate, self.tap = P, calibrate, tap
+        self.mutate = mutate       # callable(name, levels) -> levels: fault injection for the stability experiments
         self.d_max, self.norm = d_max, norm
         self.ties = 0
         self.neurons = 0
@@ -54,6 +55,8 @@ def lif(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
     (fire = round(clamp(v,0,8)), round half to even), :133-153 (soft reset, unused after), :197 (/8)."""
     v = 0.0 + x
     s = torch.round(torch.clamp(v, min=0, max=cx.d_max))
+    if cx.mutate is not None:
+        s = cx.mutate(name, s)
     cx.neurons += 1
     cx.elems += x.numel()
     if cx.tap is not None:

@@ -18,7 +18,7 @@ from spike2former_b200.synth import random_state, skeleton_state  # noqa: F401  
 from . import port
 
 MASK_GAIN = 2.0
-MASK_GAIN_OF = {"default": 2.0, "stable": 5.0}    # sharper masks -> >= 20 classes in the oracle argmax
+MASK_GAIN_OF = {"default": 2.0, "stable": 10.0}    # sharper masks -> >= 20 classes in the oracle argmax
 
 
 def calibration_batch(cfg, h, w, batch=2, seed=4321):

@@ -13,14 +13,16 @@ import copy
 
 
 def _model(embed_dim4, feat, num_classes, num_queries, enc_ffn, dec_ffn, num_heads, group, img, enc_layers=6,
-           dec_layers=6):
+           dec_layers=6, crop=None, pre_test_cfg=None):
     norm_cfg = dict(type="SyncBN", requires_grad=True)
     ps_dim = feat // 2
     return dict(
         type="EncoderDecoder",
-        # cfg:13-20 (both the ADE20K and the Cityscapes config): ImageNet statistics, BGR -> RGB, no test-time padding
-        data_preprocessor=dict(type="SegDataPreProcessor", size=(img, img), mean=[123.675, 116.28, 103.53],
-                               std=[58.395, 57.12, 57.375], bgr_to_rgb=True, pad_val=0, seg_pad_val=255),
+        # cfg:13-20: ImageNet statistics, BGR -> RGB; ADE20K: crop 512 x 512, no test-time padding; Cityscapes
+        # (..._CityScapes.py:12-20): crop 512 x 1024 and test_cfg=dict(size_divisor=32)
+        data_preprocessor=dict(type="SegDataPreProcessor", size=crop or (img, img), mean=[123.675, 116.28, 103.53],
+                               std=[58.395, 57.12, 57.375], bgr_to_rgb=True, pad_val=0, seg_pad_val=255,
+                               **({"test_cfg": pre_test_cfg} if pre_test_cfg else {})),
         backbone=dict(
             type="Spiking_vit_MetaFormer", img_size_h=img, img_size_w=img, patch_size=16, embed_dim=list(embed_dim4),
             num_heads=num_heads, mlp_ratios=4, in_channels=3, num_classes=num_classes, qkv_bias=False, depths=8,
@@ -63,7 +65,8 @@ def ade20k():
 
 def cityscapes():
     """SDTv2 + DCN pixel decoder, Cityscapes (19 classes, encoder FFN 2048)."""
-    return _model([64, 128, 256, 360], 256, 19, 100, 2048, 2048, 8, 32, 512)
+    return _model([64, 128, 256, 360], 256, 19, 100, 2048, 2048, 8, 32, 512, crop=(512, 1024),
+                  pre_test_cfg=dict(size_divisor=32))
 
 
 def tiny():

@@ -213,8 +213,14 @@ __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* _
       const float lx = __fadd_rn(__fadd_rn(ref_x, grid.gx[pt]), __fdiv_rn(__fmul_rn(o2.x, os), Win));
       const float ly = __fadd_rn(__fadd_rn(ref_y, grid.gy[pt]), __fdiv_rn(__fmul_rn(o2.y, os), Hin));
       const float sgx = __fadd_rn(__fmul_rn(2.f, lx), -1.f), sgy = __fadd_rn(__fmul_rn(2.f, ly), -1.f);
-      const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgx, 1.f), Win), -1.f), 0.5f);
-      const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(sgy, 1.f), Hin), -1.f), 0.5f);
+      // grid_sample's un-normalisation, align_corners=False, exactly as the oracle's kernel rounds it: ATen's
+      // vectorised CPU kernel (cpu/GridSamplerKernel.cpp, ComputeLocationBase::unnormalize) evaluates
+      // (g + 1) * (size / 2) - 0.5 with ONE rounding (the compiler contracts it to an FMA; verified bit for bit
+      // against F.grid_sample on 4e5 random points, tools/check_grid_sample_order.py).  Rounding the product
+      // separately moves ix by an ulp (~2e-6 px at x ~ 20), which the subtraction of floor(ix) turns into a
+      // 1e-5 relative error of the bilinear weight -- the largest arithmetic difference of the whole path.
+      const float ix = __fmaf_rn(__fadd_rn(sgx, 1.f), Win * 0.5f, -0.5f);
+      const float iy = __fmaf_rn(__fadd_rn(sgy, 1.f), Hin * 0.5f, -0.5f);
       const float fx = floorf(ix), fy = floorf(iy);
       const int x0 = (int)fx - pad, y0 = (int)fy - pad;   // back to unpadded coordinates
       const float tx = ix - fx, ty = iy - fy;

@@ -318,12 +318,11 @@ class HeadPlan:
 
 
 def plan_of(model, kind):
-    if model._plan is None:
-        dev = next(model.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("spike2former_b200: move the model to a CUDA device first (no CPU path)")
-        model._plan = kind(model, dev)
-    return model._plan
+    """The model's device-side plan, rebuilt when its parameters changed since the plan was made (models._Engined)."""
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("spike2former_b200: move the model to a CUDA device first (no CPU path)")
+    return model.current_plan(kind, dev)
 
 
 # ------------------------------------------------------------------------------------------------ probing
@@ -610,6 +609,7 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True, s
     y = pr.real(pd + "y0", y)
     outs = [y]
     hp, wp = H, W
+    forked = False
     for i in range(model.num_inputs - 2, -1, -1):
         forked = side_stream is not None and i == 0 and not pr.active and not want_mask_feature
         if forked:
@@ -637,7 +637,8 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True, s
             hp, wp = h, w
     if pr.active:
         pr.real(pd + "mask_feature_spike", y)
-    ysp = pr.spike(pd + "mask_feature_spike", ysp)
+    with (torch.cuda.stream(side_stream) if forked else contextlib.nullcontext()):   # an observer's tap copies on the producing stream
+        ysp = pr.spike(pd + "mask_feature_spike", ysp)
     mf = None
     if want_mask_feature or pr.active:
         mf, _ = L["mask_feature"](ysp, n, hp, wp, f32=True)
@@ -786,12 +787,18 @@ def head_forward_public(model, x):
     return cls.view(Ls, T, B, nq, -1).mean(1), masks.view(Ls, T, B, nq, h, w).mean(1)
 
 
-def _predict_from(model, feats, img_shape, probe=NOPROBE, labels=False):
+def _predict_from(model, feats, img_shape, probe=NOPROBE, labels=False, T=1):
     cls, me, ysp = head_forward(model, feats, probe, last_only=True)
     n, h, w, _ = ysp.shape
     nq = model.num_queries
     mp = _mask_pred(model, me[-1], ysp, False)                              # [n, h, w, nq] pixel-major
     cl = cls[-1].contiguous()
+    if T > 1:
+        # `.mean(1)` over the time axis of the class scores and of the mask einsum (dense_heads/maskformer_head.py:
+        # 574-582); only the T = 4 cocostuff configs reach this -- two small torch reductions, not a hot loop
+        n //= T
+        mp = mp.view(T, n, h, w, nq).mean(0)
+        cl = cl.view(T, n, nq, -1).mean(0)
     mp = probe.real("mask_pred", mp)
     cl = probe.real("cls_score", cl, "same")
     logits, lab = ops.semantic_tail(mp.view(n, h * w, nq), cl, n=n, Q=nq, K=model.num_classes, h=h, w=w,
@@ -803,9 +810,7 @@ def head_predict(model, x, img_shape, probe=NOPROBE):
     """mmseg MaskFormerHead.predict (decode_heads/maskformer_head.py:138-180) -> [B, K, H, W]."""
     feats = _import_feats(x)
     T = x[0].shape[0] if x[0].dim() == 5 else 1
-    if T != 1:
-        raise NotImplementedError("predict with T > 1: every Spike2Former config uses T = 1 (SURVEY.md section 0.3)")
-    return _predict_from(model, feats, img_shape, probe)
+    return _predict_from(model, feats, img_shape, probe, T=T)
 
 
 class GraphedForward:
@@ -828,6 +833,8 @@ class GraphedForward:
         l0 = ops.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = segmentor_logits(seg, self.static_in, probe, labels=labels)
+        # the graph replays raw device pointers into these plans: keep them alive as long as the graph
+        self.plans = (seg.backbone._plan, seg.decode_head._plan, seg.decode_head.pixel_decoder._plan)
         self.launches = ops.launch_count() - l0    # kernels of this library inside one replay
 
     def __call__(self, x):
@@ -871,8 +878,6 @@ def profile_dominant(seg, img, steps=2):
 
 def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
     """EncoderDecoder.encode_decode (encoder_decoder.py:125-133): internal tensors go straight to the head."""
-    if seg.backbone.T != 1:
-        raise NotImplementedError("T > 1 end-to-end inference is not used by any Spike2Former config")
     pre = None
     img_hw = tuple(img.shape[-2:])
     if img.dtype == torch.uint8:
@@ -883,7 +888,8 @@ def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
         chw = img.shape[1] == 3 and img.shape[3] != 3
         h_, w_ = (img.shape[2], img.shape[3]) if chw else (img.shape[1], img.shape[2])
         cout0 = seg.backbone.embed_dim[0] // 2
-        fused = (FUSE_STEM_U8 and pre._enable_normalize and tc.get("size") is None and tc.get("size_divisor") is None and
+        no_pad = pre._padded_size(int(h_), int(w_), tc.get("size"), tc.get("size_divisor")) == (int(h_), int(w_))
+        fused = (FUSE_STEM_U8 and pre._enable_normalize and no_pad and
                  seg.backbone.T == 1 and min(h_, w_) >= 8 and cout0 % 16 == 0 and cout0 <= 64 and img.is_contiguous())
         if not fused:
             # separate preprocessing kernel (padding requested, or a stem width the fused kernel does not cover)
@@ -895,4 +901,4 @@ def segmentor_logits(seg, img, probe=NOPROBE, labels=False):
     scoped = probe.active or probe.observe
     feats = backbone_forward(seg.backbone, img, probe.scoped("backbone.") if scoped else probe, pre=pre)
     pr = probe.scoped("decode_head.") if scoped else probe
-    return _predict_from(seg.decode_head, feats, img_hw, pr, labels)
+    return _predict_from(seg.decode_head, feats, img_hw, pr, labels, T=seg.backbone.T)

@@ -15,6 +15,8 @@ sm_100a kernels.  There is no CPU path: calling forward on CPU tensors raises.
 """
 from __future__ import annotations
 
+import collections
+
 import torch
 import torch.nn as nn
 
@@ -28,22 +30,41 @@ def _require_cuda(x: torch.Tensor, who: str):
 
 
 class _Engined(nn.Module):
-    """Shared plumbing: lazily built, invalidated whenever parameters are (re)loaded."""
+    """Shared plumbing: the folded / packed device copy of the parameters (`_plan`) is built lazily and dropped
+    whenever the parameters change: state_dict loads, `.to()` / `.cuda()`, `invalidate()`, and in-place edits of any
+    parameter or buffer (detected through the tensors' version counters, see `weights_version`)."""
 
     def __init__(self):
         super().__init__()
         self._plan = None
+        self._plan_version = None
+        self._epoch = 0            # bumped by every explicit invalidation
 
     def invalidate(self):
         self._plan = None
+        self._epoch += 1
 
     def _load_from_state_dict(self, *a, **k):
-        self._plan = None
+        self.invalidate()
         return super()._load_from_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
-        self._plan = None
+        self.invalidate()
         return super()._apply(fn, *a, **k)
+
+    def weights_version(self):
+        """Changes whenever a parameter / buffer of this module (children included) is replaced or edited in place."""
+        ts = self.__dict__.get("_tensors")
+        if ts is None or ts[0] != self._epoch:
+            ts = (self._epoch, [t for t in list(self.parameters()) + list(self.buffers())])
+            self.__dict__["_tensors"] = ts
+        return (self._epoch, sum(t._version for t in ts[1]), sum(m._epoch for m in self.modules() if isinstance(m, _Engined)))
+
+    def current_plan(self, kind, device):
+        v = self.weights_version()
+        if self._plan is None or self._plan_version != v:
+            self._plan, self._plan_version = kind(self, device), v
+        return self._plan
 
     def reset(self):
         """ResetModelHook protocol (resetmodel_hook.py:17-37): neurons are stateless here."""
@@ -225,15 +246,25 @@ class SegDataPreProcessor(nn.Module):
             ((self.test_cfg.get("size", None), self.test_cfg.get("size_divisor", None)) if self.test_cfg else (None, None))
         if training:
             assert data_samples is not None, "During training, `data_samples` must be define."
+        if training or self.test_cfg:
+            assert (size is not None) ^ (div is not None), "only one of size and size_divisor should be valid"   # misc.py:63-64
         x = self.normalized(inputs, size, div)
-        if data_samples is not None and (size is not None or div is not None):
-            ph, pw = x.shape[1] - int(img_h(inputs)), x.shape[2] - int(img_w(inputs))
-            for ds in data_samples:                                 # label maps: right/bottom pad with seg_pad_val (misc.py:94-105)
-                if hasattr(ds, "gt_sem_seg"):
-                    ds.gt_sem_seg.data = nn.functional.pad(ds.gt_sem_seg.data, (0, pw, 0, ph), value=self.seg_pad_val)
-                if hasattr(ds, "set_metainfo"):
-                    ds.set_metainfo({"img_shape": tuple(ds.gt_sem_seg.data.shape[-2:]) if hasattr(ds, "gt_sem_seg") else None,
-                                     "pad_shape": (int(x.shape[1]), int(x.shape[2])), "padding_size": (0, pw, 0, ph)})
+        H0, W0 = int(img_h(inputs)), int(img_w(inputs))
+        padding_size = (0, int(x.shape[2]) - W0, 0, int(x.shape[1]) - H0)    # (left, right, top, bottom): misc.py:78-86
+        if training:
+            # stack_batch with data_samples (misc.py:94-111): pad the label maps right / bottom with seg_pad_val and record
+            # the UNPADDED image shape, the padded label shape and the padding
+            for ds in data_samples:
+                for field in ("gt_sem_seg", "gt_edge_map"):
+                    if field in ds if hasattr(ds, "__contains__") else hasattr(ds, field):
+                        f_ = getattr(ds, field)
+                        f_.data = nn.functional.pad(f_.data, padding_size, value=self.seg_pad_val)
+                ds.set_metainfo({"img_shape": torch.Size((H0, W0)), "pad_shape": ds.gt_sem_seg.shape,
+                                 "padding_size": padding_size})
+        elif self.test_cfg and data_samples is not None:
+            # test-time padding (data_preprocessor.py:140-150, misc.py:112-116): only these two keys; img_shape is untouched
+            for ds in data_samples:
+                ds.set_metainfo({"img_padding_size": padding_size, "pad_shape": torch.Size((int(x.shape[1]), int(x.shape[2])))})
         return dict(inputs=x.permute(0, 3, 1, 2), data_samples=data_samples)
 
 
@@ -259,40 +290,55 @@ class EncoderDecoder(_Engined):
         self.align_corners = self.decode_head.align_corners
         self.num_classes = self.decode_head.num_classes
         self.out_channels = self.decode_head.out_channels
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()
+        self._shape_hits = collections.OrderedDict()
         self.use_cuda_graph = True       # replay one captured CUDA graph per (input shape, output kind)
+        self.graph_cache_size = 4        # LRU bound: every cached graph owns a private activation pool (GBs at batch 32)
+        self.graph_min_hits = 2          # a shape is captured the second time it is seen; one-off shapes run eagerly
+        self.alias_graph_output = False  # True: return the graph's static output buffer (overwritten by the next call
+                                         # with the same shape) instead of a fresh copy -- for serving loops that consume
+                                         # the result before the next call
 
     def invalidate(self):
         super().invalidate()
-        self._graphs = {}
+        self._graphs.clear()
         for m in (self.backbone, self.decode_head, self.decode_head.pixel_decoder):
             m.invalidate()
 
-    def _load_from_state_dict(self, *a, **k):
-        self._graphs = {}
-        return super()._load_from_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._graphs = {}
-        return super()._apply(fn, *a, **k)
-
     def _run(self, inputs, labels):
-        """The whole forward is ~300 kernel launches of 5-50 us each: it is captured once per input shape into a
-        CUDA graph (all launches go to torch's current stream through the C ABI, workspaces come from the graph's
-        private pool) and replayed.  The returned tensor is the graph's output buffer: it is overwritten by the next
-        call with the same shape, exactly like a CUDA-graphed module in any serving stack."""
+        """The whole forward is ~300 kernel launches of 5-50 us each: a shape that recurs is captured into a CUDA
+        graph (all launches go to torch's current stream through the C ABI, workspaces come from the graph's private
+        pool) and replayed.  A graph holds raw device pointers of the plans it was captured with, so it is keyed on
+        the weights version of the whole model and holds references to those plans: any parameter change (child
+        `load_state_dict`, `.to()`, in-place edits) makes the next call re-capture instead of replaying stale or
+        freed memory.  The cache is a small LRU, since evaluation over variable-size images would otherwise keep one
+        multi-GB activation pool per shape."""
         from . import engine
 
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
             return engine.segmentor_logits(self, inputs, labels=labels)
-        if torch.cuda.is_current_stream_capturing():
-            return engine.segmentor_logits(self, inputs, labels=labels)
+        version = self.weights_version()
         key = (tuple(inputs.shape), inputs.device.index, bool(labels), inputs.dtype)
         g = self._graphs.get(key)
+        if g is not None and g.version != version:
+            del self._graphs[key]
+            g = None
         if g is None:
+            hits = self._shape_hits.pop(key, 0) + 1
+            self._shape_hits[key] = hits
+            while len(self._shape_hits) > 64:
+                self._shape_hits.popitem(last=False)
+            if hits < self.graph_min_hits:
+                return engine.segmentor_logits(self, inputs, labels=labels)
+            while len(self._graphs) >= max(1, self.graph_cache_size):
+                self._graphs.popitem(last=False)             # frees the evicted graph and its pool
             g = engine.GraphedForward(self, inputs, labels)
+            g.version = self.weights_version()               # the capture built the plans: same version afterwards
             self._graphs[key] = g
-        return g(inputs)
+        else:
+            self._graphs.move_to_end(key)
+        out = g(inputs)
+        return out if self.alias_graph_output else out.clone()
 
     def extract_feat(self, inputs):
         return self.backbone(inputs)

@@ -47,6 +47,8 @@ def skeleton_state(cfg):
 #     (a sum over all keys, no softmax) lands at ATTN_TARGET levels instead of saturating at 8.
 K_STRONG, WEAK, DW_WEAK = 2, 0.01, 0.05
 GAIN, GAIN_FINAL, ATTN_TARGET = (0.25, 0.5), (0.002, 0.004), 0.6
+CLS_GAIN, ME_AMP = 8.0, 6.0      # smooth class scores (one flipped query spike must not switch a whole mask's class)
+DAMPED, GAIN_DAMPED = (".output_convs.", ".encoder_out_proj.1."), (0.03, 0.06)   # top-down FPN path: a coarse flip fans out x4 per level
 BRANCH_FINAL = (".Conv.bn2.", ".bn2.", ".proj_conv.1.", ".fc2_bn.", ".pwconv2.1.", ".out_conv.1.", ".ffn.bn2.")
 
 
@@ -84,8 +86,9 @@ def stable_state(cfg, seed=1234, hw=(512, 512)):
         elif t.dim() == 1 and (k[: -len(leaf)] + "running_mean") in P:     # BN affine
             final = any(p in k for p in BRANCH_FINAL) and ".dcn.input_proj.pwconv2.1." not in k
             qkv = any(f".attn.{nm}_conv.1." in k for nm in "qkv")
+            damped = any(p in k for p in DAMPED)
             if leaf == "weight":
-                lo, hi = GAIN_FINAL if final else GAIN
+                lo, hi = GAIN_FINAL if final else GAIN_DAMPED if damped else GAIN
                 t.copy_(lo + (hi - lo) * torch.rand(t.shape, generator=g))
             elif qkv:
                 if k.startswith("backbone."):
@@ -114,13 +117,15 @@ def stable_state(cfg, seed=1234, hw=(512, 512)):
                 idx = torch.randint(0, kk * kk, (rows,), generator=g)
                 w[torch.arange(rows), idx] += 0.7 * rnd((rows,))
                 t.copy_(w.reshape(t.shape))
-            elif fan_in >= 16 and not any(s in k for s in ("cls_embed", "mask_embed", "mask_feature", "shortcut")):
+            elif fan_in >= 16 and not any(s in k for s in ("cls_embed", "mask_embed.fc_out", "mask_feature", "shortcut")):
+                # mask_embed.fc1 / fc2 have no BatchNorm behind them: the strong taps themselves set the firing level
+                amp = ME_AMP if "mask_embed" in k else 1.0 / math.sqrt(K_STRONG)
                 flat = (WEAK / math.sqrt(fan_in)) * dense.reshape(rows, -1)
                 idx = torch.stack([torch.randperm(fan_in, generator=g)[:K_STRONG] for _ in range(rows)])
-                flat.scatter_add_(1, idx, rnd((rows, K_STRONG)) / math.sqrt(K_STRONG))
+                flat.scatter_add_(1, idx, rnd((rows, K_STRONG)) * amp)
                 t.copy_(flat.reshape(t.shape))
             else:
-                gain = 6.0 if ("mask_embed.fc1" in k or "mask_embed.fc2" in k) else 48.0 if "cls_embed" in k else 1.0
+                gain = CLS_GAIN if "cls_embed" in k else 1.0
                 t.copy_(dense * gain / math.sqrt(fan_in))
         elif leaf == "bias":
             t.copy_(rnd(t.shape) / math.sqrt(P[k[: -len("bias")] + "weight"][0].numel()))

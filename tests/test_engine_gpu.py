@@ -8,9 +8,9 @@ from oracle import port, probe, weights
 pytestmark = pytest.mark.gpu
 
 
-def _run(cfg, H, W, force=True, batch=1):
+def _run(cfg, H, W, force=True, batch=1, style="default"):
     torch.manual_seed(0)
-    P = weights.calibrated_state(cfg, H, W)
+    P = weights.calibrated_state(cfg, H, W, style=style)
     img = weights.test_image(cfg, H, W, batch)
     taps, marks, ref_logits = probe.record_oracle(P, cfg, img)
     seg = s2f.build_segmentor(cfg)
@@ -57,6 +57,18 @@ def test_tiny_teacher_forced():
     agree = float((logits.argmax(1) == ref.argmax(1)).float().mean())
     print("argmax agreement", agree, "classes", ref.argmax(1).unique().numel())
     assert agree >= 0.999
+
+
+def test_tiny_T2_teacher_forced():
+    """T > 1 (the T = 4 cocostuff configs of the reference): T folds into the batch, the head averages over it."""
+    cfg = s2f.configs.tiny()
+    cfg["backbone"]["T"] = 2
+    pr, logits, ref, taps = _run(cfg, 64, 64, batch=2)
+    s = _report(pr)
+    assert s["unknown"] == [] and s["unexplained"] == 0 and s["maxdev"] <= 1
+    assert logits.shape == ref.shape == (2, 11, 64, 64)
+    assert float((logits - ref).abs().max() / ref.abs().max()) < 1e-2
+    assert float((logits.argmax(1) == ref.argmax(1)).float().mean()) >= 0.999
 
 
 def test_ade20k_teacher_forced_512():
@@ -140,6 +152,7 @@ def test_cuda_graph_replay_matches_eager_launches():
     seg = s2f.build_segmentor(cfg)
     seg.load_state_dict(synth.synthetic_checkpoint("tiny", cfg), strict=True)
     seg = seg.cuda()
+    seg.graph_min_hits = 1
     g = torch.Generator().manual_seed(3)
     x1, x2 = (torch.randn(2, 3, 64, 64, generator=g).cuda() for _ in range(2))
     with torch.no_grad():
@@ -179,3 +192,47 @@ def test_public_api_shapes_and_batches(B, H, W):
     assert torch.equal(labels.long(), logits.argmax(1))
     assert torch.equal(single[0], logits[0])                 # batch-sharding invariant: an image does not see its batch
     assert logits.argmax(1).unique().numel() >= 2                 # not a constant map (small random-weight images show few classes)
+
+
+def test_graph_cache_follows_weight_changes_and_is_bounded():
+    """a captured graph holds raw pointers into the plans; any parameter change -- through a CHILD's
+    load_state_dict or an in-place edit -- must re-capture, never replay stale memory; one-off shapes run eagerly;
+    the cache is an LRU; results are fresh tensors unless aliasing is requested."""
+    from spike2former_b200 import engine, synth
+
+    cfg = s2f.configs.tiny()
+    seg = s2f.build_segmentor(cfg)
+    P = synth.synthetic_checkpoint("tiny", cfg)
+    seg.load_state_dict(P, strict=True)
+    seg = seg.cuda()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 3, 64, 64, generator=g).cuda()
+    with torch.no_grad():
+        a0 = seg.encode_decode(x)                      # first sighting of the shape: eager
+        assert len(seg._graphs) == 0
+        a1 = seg.encode_decode(x)                      # second: captured + replayed
+        assert len(seg._graphs) == 1 and torch.equal(a0, a1)
+        a2 = seg.encode_decode(x)
+        assert a2.data_ptr() != a1.data_ptr() and torch.equal(a1, a2)          # fresh result tensors
+        # (1) child load_state_dict with different weights
+        P2 = synth.random_state(cfg, seed=99)
+        for k, v in P.items():
+            if "running_" in k:
+                P2[k] = v
+        seg.backbone.load_state_dict({k[9:]: v for k, v in P2.items() if k.startswith("backbone.")})
+        b = seg.encode_decode(x)
+        want = engine.segmentor_logits(seg, x)
+        assert torch.equal(b, want) and not torch.equal(b, a1)
+        # (2) in-place edit of one parameter (class 0 becomes every query's favourite)
+        seg.decode_head.cls_embed.bias.data[0] += 5.0
+        c = seg.encode_decode(x)
+        assert torch.equal(c, engine.segmentor_logits(seg, x)) and not torch.equal(c, b)
+        # (3) LRU bound
+        seg.graph_cache_size, seg.graph_min_hits = 2, 1
+        for hw in (32, 64, 96, 128):
+            seg.encode_decode(torch.randn(1, 3, hw, hw, generator=g).cuda())
+        assert len(seg._graphs) == 2
+        # (4) aliasing on request
+        seg.alias_graph_output = True
+        y = torch.randn(1, 3, 128, 128, generator=g).cuda()
+        assert seg.encode_decode(y).data_ptr() == seg.encode_decode(y).data_ptr()

@@ -49,7 +49,7 @@ def test_nilif_d4_variant_end_to_end(d_max, norm):
     cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
     got, _, y = ops.nilif(x.cuda(), want_norm=True, d_max=d_max, norm=norm, ties=cnt)
     assert torch.equal(got.cpu(), want.to(torch.int8)) and torch.equal(y.cpu(), want / norm)
-    assert int(cnt.item()) == port.count_ties(x, d_max) and int(got.max()) == int(d_max)
+    assert int(cnt.item()) == port.count_ties(x, d_max) and int(got.max()) == int(min(d_max, 5))
     xs = (torch.rand(3, 4096, generator=g) - 0.3) * 5
     lv, v = port.nilif_reference(xs, d_max=d_max, T=3)
     got, vo, _ = ops.nilif(xs.cuda(), want_v_out=True, T=3, C_=64, d_max=d_max, norm=norm)

@@ -62,6 +62,7 @@ def _tiny_segmentor():
     cfg = s2f.configs.tiny()
     seg = s2f.build_segmentor(cfg)
     seg.load_state_dict(weights.calibrated_state(cfg, 64, 64), strict=True)
+    seg.graph_min_hits = 1            # capture at the first sighting of a shape: these tests are about graph replay
     return seg.cuda()
 
 
