@@ -32,7 +32,8 @@ def _require_cuda(x: torch.Tensor, who: str):
 class _Engined(nn.Module):
     """Shared plumbing: the folded / packed device copy of the parameters (`_plan`) is built lazily and dropped
     whenever the parameters change: state_dict loads, `.to()` / `.cuda()`, `invalidate()`, and in-place edits of any
-    parameter or buffer (detected through the tensors' version counters, see `weights_version`)."""
+    parameter or buffer (detected through the tensors' version counters, see `weights_version`; writes through
+    `param.data` bypass those counters by PyTorch's design -- call `invalidate()` after such an edit)."""
 
     def __init__(self):
         super().__init__()

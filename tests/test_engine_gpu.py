@@ -224,7 +224,7 @@ def test_graph_cache_follows_weight_changes_and_is_bounded():
         want = engine.segmentor_logits(seg, x)
         assert torch.equal(b, want) and not torch.equal(b, a1)
         # (2) in-place edit of one parameter (class 0 becomes every query's favourite)
-        seg.decode_head.cls_embed.bias.data[0] += 5.0
+        seg.decode_head.cls_embed.bias[0] += 5.0          # (no_grad) bumps the tensor's version counter
         c = seg.encode_decode(x)
         assert torch.equal(c, engine.segmentor_logits(seg, x)) and not torch.equal(c, b)
         # (3) LRU bound
