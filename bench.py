@@ -9,7 +9,12 @@ head -> seg logits [B,150,512,512]) over one batch of B synthetic 512x512 images
   e2e   : the same through the public API with HOST buffers: pinned uint8 images (the dataset format the reference's
           SegDataPreProcessor receives) -> H2D -> normalise + forward -> argmax label map (uint8) -> D2H, every step,
           inside the timed region
-  roofline : the dominant kernel class (spike GEMM / conv) timed live with CUDA events on the launch stream
+  roofline : the dominant kernel class (spike GEMM / conv) timed live with CUDA events on the launch stream, on the
+          reference layers' ALGORITHMIC FLOPs (executed FLOPs beside it), plus a per-class table
+  tensor_peaks : tcgen05 issue-rate ceilings of kind::i8 and kind::f16(bf16) measured in this run (csrc/peak.cu)
+  kernels : BASELINE.json config 2 micro-benchmarks (NI-LIF D=8 / D=4, spike GEMM, spike-driven attention C=512 d=64)
+  batches : the same model at 1 and 8 images per GPU (the reference's own timing protocol is batch 1)
+  cityscapes_1024x2048 : BASELINE.json config 4 with its own value / e2e / per-class roofline
   cpu_baseline : the oracle port (CPU restatement of the reference, pinned bit-exact to it) on this box's host
           cores over a bounded sample, rank 0, N=1 only
 `--impl reference` times that CPU path alone with the same JSON contract.
@@ -33,7 +38,18 @@ import torch  # noqa: E402
 H = W = 512
 WORKLOAD = "Spike2Former SDTv2 + DCN pixel decoder, ADE20K-shape 512x512 inference (150 classes, 100 queries)"
 ALG_GFLOP_PER_IMG = 131.0      # 142 GFLOP minus the six discarded mask einsums (inference uses [-1])
-CITY_H, CITY_W = 1024, 2048    # BASELINE.json config 4: Cityscapes shape (19 classes), reported as a secondary number
+CITY_H, CITY_W = 1024, 2048    # BASELINE.json config 4: Cityscapes shape (19 classes)
+NBUF = 4                       # rotating input batches
+
+
+def workload_config(B, world):
+    """The `config` object of the JSON line -- the same for the CUDA arm and the reference arm."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
+            "weights": "seeded random init + shipped calibration statistics (spike2former_b200/synth.py)",
+            "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2",
+            "value_input": "fp32 [B,3,512,512] resident in HBM (encode_decode -> fp32 logits [B,150,512,512])",
+            "e2e_input": "uint8 [B,3,512,512] pinned host memory -> SegDataPreProcessor + predict -> uint8 labels -> host",
+            "alg_gflop_per_image": ALG_GFLOP_PER_IMG}
 
 
 def peaks():
@@ -88,7 +104,8 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_reference_run(steps, warmup):
-    """The reference's CPU implementation of the path: oracle/port.py (bit-exact restatement, see tests/golden)."""
+    """The reference's CPU implementation of the path: oracle/port.py (bit-exact restatement, see tests/golden).
+    One step = preprocess + forward + argmax of ONE 512x512 image (a bounded sample of the batch-32 workload)."""
     from oracle import port
     from spike2former_b200 import configs, synth
 
@@ -116,18 +133,17 @@ def cpu_reference_run(steps, warmup):
                        f"{cores} threads, after {warmup} warm-up"), dt / steps * 1e3
 
 
-def kernel_microbench(dev):
-    """BASELINE.json config 2 on one GPU: fused NI-LIF (B=64, N=1024, C=512, T=1) and the MLP spike GEMM 512->2048."""
-    from spike2former_b200 import ops
+# ----------------------------------------------------------------------------------------------- micro-benchmarks
+class KernelTimer:
+    def __init__(self, dev):
+        self.flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
 
-    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
-
-    def timed(fn, iters=10):
+    def __call__(self, fn, iters=10):
         for _ in range(3):
             fn()
         ts = []
         for _ in range(iters):
-            flush.view(torch.int64).sum()                  # evict the working set, leave clean lines in L2
+            self.flush.view(torch.int64).sum()             # evict the working set, leave clean lines in L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda._sleep(400000)                      # the launch is queued before the GPU reaches e0
             e0.record(); fn(); e1.record()
@@ -135,15 +151,73 @@ def kernel_microbench(dev):
             ts.append(e0.elapsed_time(e1))
         return statistics.median(ts) * 1e-3
 
+
+def tensor_peaks(dev):
+    """Tensor-pipe ceilings measured in this run, the way MEASURED_PEAKS.json measures bf16 (best of 10 = burst, back to
+    back for ~3 s = sustained): (i) tcgen05 issue rate of kind::i8 and kind::f16 (csrc/peak.cu: operands resident in
+    shared memory, nothing but the tensor pipe can limit it), (ii) cuBLASLt int8 GEMM 8192^3 through torch._int_mm."""
+    from spike2former_b200 import ops
+
+    out = {}
+    for kind in ("i8", "bf16"):
+        iters = 4096 if kind == "i8" else 8192               # ~5e12 ops per launch (five 8192^3 GEMMs' worth)
+        for _ in range(3):
+            n_ops = ops.peak_mma(kind, iters)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); n_ops = ops.peak_mma(kind, iters); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(3000.0 / best))
+        e0.record()
+        for _ in range(reps):
+            ops.peak_mma(kind, iters)
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"tcgen05_{kind}_issue_rate"] = dict(burst_tops=n_ops / best / 1e9, sustained_tops=n_ops * reps / e0.elapsed_time(e1) / 1e9,
+                                                 ops_per_launch=n_ops)
+    try:
+        a = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev).t()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out["cublaslt_int8_8192^3"] = dict(burst_tops=2.0 * 8192 ** 3 / best / 1e9)
+    except Exception as e:  # pragma: no cover
+        out["cublaslt_int8_8192^3"] = dict(unavailable=str(e)[:120])
+    return out
+
+
+def kernel_microbench(dev, pk, tp):
+    """BASELINE.json config 2 on one GPU (B=64, N=1024 tokens, C=512, 8 heads, d=64, T=1): fused NI-LIF (D=8 and D=4),
+    the MLP spike GEMM 512->2048 and the spike-driven attention Q(K^T V)."""
+    from spike2former_b200 import ops
+
+    timed = KernelTimer(dev)
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(64, 1024, 512, generator=g) * 12 - 2).to(dev)
     lv = torch.empty(x.shape, dtype=torch.int8, device=dev)
-    t = timed(lambda: ops.nilif(x, out=lv))
-    nilif = dict(workload="NI-LIF B=64 N=1024 C=512 T=1 D=8", us=t * 1e6, gbs=x.numel() * 5 / t / 1e9,
-                 algorithmic_bytes=x.numel() * 5)
+    nb = x.numel() * 5
+
+    def lif_entry(t, label):
+        return dict(workload=label, us=t * 1e6, gbs=nb / t / 1e9, algorithmic_bytes=nb, frac_of_measured_hbm=nb / t / 1e9 / pk["hbm"],
+                    frac_of_8tbs_nominal=nb / t / 1e9 / 8000.0)
+
+    nilif = lif_entry(timed(lambda: ops.nilif(x, out=lv)), "NI-LIF B=64 N=1024 C=512 T=1 D=8 (Q_IFNode / Quant, /8)")
     bn_s, bn_b = (torch.rand(512, generator=g) + 0.5).to(dev), torch.randn(512, generator=g).to(dev)
     t = timed(lambda: ops.nilif(x, scale=bn_s, shift=bn_b, out=lv))
-    nilif["with_folded_bn_affine"] = dict(us=t * 1e6, gbs=x.numel() * 5 / t / 1e9)
+    nilif["with_folded_bn_affine"] = dict(us=t * 1e6, gbs=nb / t / 1e9, frac_of_measured_hbm=nb / t / 1e9 / pk["hbm"])
+    nilif_d4 = lif_entry(timed(lambda: ops.nilif(x, out=lv, d_max=4.0, norm=4.0)),
+                         "NI-LIF B=64 N=1024 C=512 T=1 D=4 (Quant4 / Multispike_norm, /4): BASELINE config 2 as written")
     n, Hh, Ww, cin, cout = 64, 32, 32, 512, 2048
     a = torch.randint(0, 9, (n, Hh, Ww, cin), generator=g, dtype=torch.int8).to(dev)
     w = torch.randn(cout, cin, generator=g) / cin ** 0.5
@@ -151,44 +225,109 @@ def kernel_microbench(dev):
     packed, sc, sh = packed.to(dev), (rowscale / 8).to(dev), torch.zeros(cout, device=dev)
     t = timed(lambda: ops.gemm_tc(a, packed, n=n, H=Hh, W=Ww, Cin=cin, Cout=cout, scale=sc, shift=sh, pieces=3,
                                   want_spike=True))
+    alg = 2.0 * n * Hh * Ww * cin * cout / t / 1e12
+    i8 = tp["tcgen05_i8_issue_rate"]["burst_tops"]
     gemm = dict(workload="spike GEMM fc1 512->2048, 65536 tokens, int8 spikes x 3 int8 weight planes, NI-LIF epilogue",
-                us=t * 1e6, tflops_algorithmic=2.0 * n * Hh * Ww * cin * cout / t / 1e12)
-    return dict(nilif_cfg2=nilif, gemm_cfg2=gemm)
+                us=t * 1e6, tflops_algorithmic=alg, algorithmic_vs_measured_bf16_burst=alg / pk["bf16"],
+                int8_tops_executed=3.0 * alg, executed_vs_measured_i8_issue_rate=3.0 * alg / i8)
+    # spike-driven attention of one MS_Block at config 2: q, k, v int8 levels [64, 1024, 512], 8 heads x 64
+    heads, d, N = 8, 64, 1024
+    q, k, v = (torch.randint(0, 3, (64, N, heads * d), generator=g, dtype=torch.int8).to(dev) for _ in range(3))
+    t = timed(lambda: ops.linear_attn(q, k, v, n=64, Nq=N, Nk=N, heads=heads, d=d, out_scale=d ** -0.5 / 512))
+    fl = 2.0 * 64 * heads * d * d * 2 * N                    # K^T V and Q (K^T V): SURVEY.md section 8d, 8.6 GFLOP
+    byts = 4.0 * 64 * N * heads * d                          # q, k, v read + levels written, 1 B each
+    sdsa = dict(workload="SDSA Q(K^T V) + NI-LIF, B=64 N=1024 C=512 8 heads d=64 (sdtv2.py:335-336)", us=t * 1e6,
+                tflops=fl / t / 1e12, gbs=byts / t / 1e9, frac_of_measured_hbm=byts / t / 1e9 / pk["hbm"],
+                bound="hbm: 268 MB of int8 operands against 8.6 GFLOP (32 FLOP/B)")
+    return dict(nilif_cfg2=nilif, nilif_cfg2_d4=nilif_d4, gemm_cfg2=gemm, sdsa_cfg2=sdsa)
 
 
-def cityscapes_throughput(dev, world, dist, B, steps=4):
-    """Secondary number (BASELINE.json config 4): Cityscapes config at 1024x2048, batch-sharded, inputs resident."""
-    import spike2former_b200 as s2f
-    from spike2former_b200 import synth
+# ----------------------------------------------------------------------------------------------- model timing
+class Harness:
+    """value / e2e timing of one segmentor at one (batch, shape), on this rank."""
 
-    cfg = s2f.configs.cityscapes()
-    seg = s2f.build_segmentor(cfg)
-    seg.load_state_dict(synth.synthetic_checkpoint("cityscapes", cfg), strict=True)
-    seg = seg.to(dev)
-    g = torch.Generator().manual_seed(7)
-    xs = [torch.randn(B, 3, CITY_H, CITY_W, generator=g).to(dev) for _ in range(2)]
-    with torch.no_grad():
-        for i in range(3):
-            seg.predict_labels(xs[i & 1])
-        if dist is not None:
-            dist.barrier()
+    def __init__(self, seg, B, h, w, dev, dist, seed):
+        self.seg, self.B, self.h, self.w, self.dev, self.dist = seg, B, h, w, dev, dist
+        g = torch.Generator().manual_seed(seed)
+        self.devin = [torch.randn(B, 3, h, w, generator=g).to(dev) for _ in range(NBUF)]
+        self.host = [torch.randint(0, 256, (B, 3, h, w), generator=g, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
+        # end-to-end: pinned uint8 host batch -> H2D (copy stream, double buffered so the copy of step i+1 overlaps the
+        # forward of step i) -> fused preprocessor + forward with fused argmax (one CUDA graph) -> D2H of the uint8 label
+        # map; all of it inside the timed region
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [torch.empty(B, 3, h, w, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.ev_ready = [torch.cuda.Event() for _ in range(2)]
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]
+        self.host_outs = [torch.empty(B, h, w, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
         torch.cuda.synchronize()
+
+    def step_resident(self, i, labels=False):
+        with torch.no_grad():
+            x = self.devin[i % NBUF]
+            return self.seg.predict_labels(x) if labels else self.seg.encode_decode(x)
+
+    def step_e2e(self, i):
+        j = i & 1
+        main = torch.cuda.current_stream()
+        with torch.no_grad():
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.ev_free[j])
+                self.stage[j].copy_(self.host[i % NBUF], non_blocking=True)
+                self.ev_ready[j].record(self.copy_stream)
+            main.wait_event(self.ev_ready[j])
+            labels = self.seg.predict_labels(self.stage[j])
+            self.ev_free[j].record(main)
+            self.host_outs[j].copy_(labels, non_blocking=True)
+        return self.host_outs[j]
+
+    def timed(self, fn, steps, warmup):
+        """W warm-up steps, then exactly K steps between barriers; CUDA events; max over ranks -> ms for the K steps."""
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            seg.predict_labels(xs[i & 1])
+            fn(i)
         e1.record()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    del seg, xs
-    torch.cuda.empty_cache()
-    return dict(workload="Spike2Former SDTv2 + DCN pixel decoder, Cityscapes-shape 1024x2048 (19 classes), fused argmax",
-                batch_per_gpu=B, images_per_second=world * B / (ms / 1e3), ms_per_step=ms)
+        self.barrier()
+        from spike2former_b200 import dist as s2f_dist
+
+        return s2f_dist.max_over_ranks(e0.elapsed_time(e1), self.dev)
+
+
+def build(name, dev):
+    import spike2former_b200 as s2f
+    from spike2former_b200 import synth
+
+    cfg = getattr(s2f.configs, name)()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint(name, cfg), strict=True)
+    seg = seg.to(dev)
+    seg.alias_graph_output = True        # serving loop: the result is consumed (copied out / dropped) before the next call,
+    return seg                           # so the graph's static output buffer is handed out without a 5 GB copy per step
+
+
+def class_rooflines(roof, pk, tp):
+    """Per kernel class: share of the step and the fraction of the roof that bounds it."""
+    from spike2former_b200 import engine
+
+    out = {}
+    for k, c in roof["classes"].items():
+        e = dict(ms=c["ms"], launches=c["launches"])
+        if k.startswith("gemm") or k in ("semantic_tail", "stem_u8"):
+            e.update(tflops_algorithmic=c["tflops_algorithmic"], tflops_executed=c["tflops_executed"],
+                     frac_of_bf16_sustained=round(c["tflops_algorithmic"] / pk["bf16_sustained"], 3))
+            if k == "gemm_tc":
+                e["int8_executed_frac_of_i8_issue_rate"] = round(3 * c["tflops_executed"] / tp["tcgen05_i8_issue_rate"]["sustained_tops"], 3) if tp else None
+        if k in engine.HBM_CLASSES or k in ("semantic_tail", "stem_u8"):
+            e.update(gbs=c["gbs"], frac_of_hbm=round(c["gbs"] / pk["hbm"], 3))
+        out[k] = e
+    return out
 
 
 def main():
@@ -199,22 +338,23 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--city-batch", type=int, default=4, help="images per GPU for the 1024x2048 secondary number (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip micro-benchmarks, peaks, batch 1 / 8 and the CPU baseline")
+    ap.add_argument("--city-batch", type=int, default=4, help="images per GPU for the 1024x2048 config (0 = skip)")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from spike2former_b200 import dist as s2f_dist
+
+    rank, world, local = s2f_dist.env_world()
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+        steps, warm = max(1, args.steps), max(0, args.warmup)
         cb, ms = cpu_reference_run(steps, warm)
         print(json.dumps({
             "impl": "reference", "metric": "images_per_second", "value": cb["value"], "unit": "images/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_step": 1, "device": "host CPU"},
+            "config": workload_config(args.batch, max(1, args.gpus)),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -229,110 +369,83 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
-    import spike2former_b200 as s2f
-    from spike2former_b200 import engine, ops, synth
+    from spike2former_b200 import engine, ops
 
-    cfg = s2f.configs.ade20k()
-    seg = s2f.build_segmentor(cfg)
-    seg.load_state_dict(synth.synthetic_checkpoint("ade20k", cfg), strict=True)
-    seg = seg.to(dev)
+    warm = max(args.warmup, 3)                 # >= 3 warm-ups: the second sighting of a shape captures its CUDA graph
+    seg = build("ade20k", dev)
     B = args.batch
-    NBUF = 4                                   # rotate input batches: 4 x B x 3 MB > L2 for B >= 12; the per-step
-    g = torch.Generator().manual_seed(1000 + rank)   # working set (GBs of activations) thrashes L2 anyway
-    devin = [torch.randn(B, 3, H, W, generator=g).to(dev) for _ in range(NBUF)]      # resident fp32 batches (`value`)
-    host = [torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
+    hs = Harness(seg, B, H, W, dev, dist, 1000 + rank)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_resident(i):
-        with torch.no_grad():
-            return seg.encode_decode(devin[i % NBUF])
-
-    # end-to-end: pinned uint8 host batch -> H2D (copy stream, double buffered so the copy of step i+1 overlaps the
-    # forward of step i) -> SegDataPreProcessor kernel + forward with fused argmax (one CUDA graph) -> D2H of the uint8
-    # label map; all of it inside the timed region
-    copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty(B, 3, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]
-    ev_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-    host_outs = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
-
-    def step_e2e(i):
-        j = i & 1
-        main = torch.cuda.current_stream()
-        with torch.no_grad():
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_free[j])
-                stage[j].copy_(host[i % NBUF], non_blocking=True)
-                ev_ready[j].record(copy_stream)
-            main.wait_event(ev_ready[j])
-            labels = seg.predict_labels(stage[j])
-            ev_free[j].record(main)
-            host_outs[j].copy_(labels, non_blocking=True)
-        return host_outs[j]
-
-    # ------------------------------------------------------------------ device-resident timing
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
+    # ------------------------------------------------------------------ device-resident timing (the headline `value`)
+    for i in range(warm):
+        hs.step_resident(i)
+    hs.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step_resident(i)
-    e1.record()
-    barrier()
-    launches = ops.launch_count() - l0
-    if launches == 0:      # CUDA-graph replay: the library's counter only sees the capture; one replay = that many kernels
-        launches = args.steps * sum(g.launches for k, g in seg._graphs.items() if not k[2])
-    ms = e0.elapsed_time(e1)
+    ms_max = hs.timed(hs.step_resident, args.steps, 0)
     clocks = sampler.stop()
-    t = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    launches = args.steps * sum(g.launches for k, g in seg._graphs.items() if not k[2])
     value = world * B * args.steps / (ms_max / 1e3)
 
     # ------------------------------------------------------------------ end-to-end (host buffers) timing
-    for i in range(4):
-        step_e2e(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
-    e1.record()
-    barrier()                                  # every H2D, forward and D2H of the timed steps has completed here
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+    e2e_ms = hs.timed(hs.step_e2e, args.steps, 4)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
+    extras = rank == 0 and world == 1 and not args.no_extras
+    pk = peaks()
     # ------------------------------------------------------------------ roofline of the dominant kernel class
-    roof = engine.profile_dominant(seg, devin[0], steps=min(args.steps, 3)) if rank == 0 else None
+    roof = engine.profile_dominant(seg, hs.devin[0], steps=min(args.steps, 3)) if rank == 0 else None
+    tp = tensor_peaks(dev) if extras else None
+    micro = kernel_microbench(dev, pk, tp) if extras else None
 
-    micro = kernel_microbench(dev) if rank == 0 else None
-    city = cityscapes_throughput(dev, world, dist, args.city_batch) if args.city_batch > 0 else None
+    batches = None
+    if extras:        # the reference's own protocol is batch 1 (tools/analysis_tools/benchmark.py:57-110); SURVEY 8d asks for 1 / 8 / 32
+        batches = {}
+        for b in (1, 8):
+            seg._graphs.clear()
+            h2 = Harness(seg, b, H, W, dev, None, 2000 + b)
+            ms_b = h2.timed(h2.step_resident, 20, 4)
+            ms_e = h2.timed(h2.step_e2e, 20, 4)
+            batches[f"batch_{b}"] = dict(images_per_second=b * 20 / (ms_b / 1e3), ms_per_step=ms_b / 20,
+                                         e2e_images_per_second=b * 20 / (ms_e / 1e3), e2e_ms_per_step=ms_e / 20,
+                                         launches_per_step=next(g.launches for k, g in seg._graphs.items() if not k[2]))
+            del h2
+    del hs
+    seg._graphs.clear()
+    torch.cuda.empty_cache()
+
+    city = None
+    if args.city_batch > 0:       # BASELINE.json config 4, batch-sharded like the headline
+        cseg = build("cityscapes", dev)
+        cb_ = args.city_batch
+        hc = Harness(cseg, cb_, CITY_H, CITY_W, dev, dist, 3000 + rank)
+        csteps = max(4, args.steps // 2)
+        ms_v = hc.timed(lambda i: hc.step_resident(i, labels=True), csteps, 3)
+        ms_e = hc.timed(hc.step_e2e, csteps, 3)
+        city = dict(workload="Spike2Former SDTv2 + DCN pixel decoder, Cityscapes-shape 1024x2048 (19 classes), fused argmax labels",
+                    batch_per_gpu=cb_, steps=csteps, images_per_second=world * cb_ * csteps / (ms_v / 1e3), ms_per_step=ms_v / csteps,
+                    e2e={"value": world * cb_ * csteps / (ms_e / 1e3), "unit": "images/s",
+                         "h2d_bytes_per_step": cb_ * 3 * CITY_H * CITY_W, "d2h_bytes_per_step": cb_ * CITY_H * CITY_W})
+        if rank == 0:
+            croof = engine.profile_dominant(cseg, hc.devin[0], steps=2, labels=True)
+            cpeak = pk["bf16_sustained"] if croof["bound"] == "tensor" else pk["hbm"]
+            city["roofline"] = {"bound": croof["bound"], "kernel": croof["kernel"], "achieved": croof["achieved"],
+                                "achieved_executed": croof["achieved_executed"], "peak": cpeak, "unit": croof["unit"],
+                                "frac": croof["achieved"] / cpeak, "share_of_step": croof["share"],
+                                "classes": class_rooflines(croof, pk, tp)}
+        del hc, cseg
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    pk = peaks()
+    cfg_out = workload_config(B, world)
     out = {
         "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": roof["dtype"] if roof else "int8xf32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
-                   "weights": "seeded random init + shipped calibration statistics (spike2former_b200/synth.py)",
-                   "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2",
-                   "value_input": "fp32 [B,3,512,512] resident in HBM (encode_decode -> fp32 logits [B,150,512,512])",
-                   "e2e_input": "uint8 [B,3,512,512] pinned host memory -> SegDataPreProcessor + predict -> uint8 labels -> host",
-                   "alg_gflop_per_image": ALG_GFLOP_PER_IMG},
+        "config": cfg_out,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W,
                 "d2h_bytes_per_step": B * H * W},
@@ -343,31 +456,30 @@ def main():
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if roof and roof["kernel"] == "gemm_tc" and os.path.exists(tj):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list (mean over the
-        # 179 GEMM launches of one forward), scaled from the profiled batch to this run's batch
+        # GEMM launches of one forward), scaled from the profiled batch to this run's batch
         t = json.load(open(tj))["gemm_i8_tc_kernel<3>"]
         traffic = t["dram_bytes_per_launch"] * B / t["batch"]
     if roof:
         peak = pk["bf16_sustained"] if roof["bound"] == "tensor" else pk["hbm"]
         out["roofline"] = {"bound": roof["bound"], "achieved": roof["achieved"], "peak": peak, "unit": roof["unit"],
                            "frac": roof["achieved"] / peak, "traffic": traffic, "kernel": roof["kernel"],
+                           "flops_counted": "algorithmic: the reference layers' MACs (RepConv = 2*C*C + 9*C per pixel, unpadded channels)",
+                           "achieved_executed": roof["achieved_executed"],
                            "share_of_step": roof["share"], "launches_per_step": roof["launches"],
                            "peak_source": pk["src"] + (" bf16 sustained (inside a long step)" if roof["bound"] == "tensor" else " copy"),
-                           "per_class_ms": roof["per_class_ms"]}
+                           "per_class_ms": roof["per_class_ms"], "classes": class_rooflines(roof, pk, tp),
+                           "whole_step": {"ms_under_events": roof["step_ms"],
+                                          "model_tflops_algorithmic": value * ALG_GFLOP_PER_IMG / 1e3,
+                                          "frac_of_bf16_sustained": value * ALG_GFLOP_PER_IMG / 1e3 / pk["bf16_sustained"]}}
+    if tp:
+        out["tensor_peaks"] = tp
     if city:
         out["cityscapes_1024x2048"] = city
+    if batches:
+        out["batches"] = batches
     if micro:
-        micro["nilif_cfg2"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["gbs"] / pk["hbm"]
-        micro["nilif_cfg2"]["frac_of_8tbs_nominal"] = micro["nilif_cfg2"]["gbs"] / 8000.0
-        micro["nilif_cfg2"]["with_folded_bn_affine"]["frac_of_measured_hbm"] = micro["nilif_cfg2"]["with_folded_bn_affine"]["gbs"] / pk["hbm"]
-        # the kernel executes 3 int8 MACs (digit planes) per algorithmic MAC; int8 dense peak: nominal 4.5 POP/s (2x the
-        # nominal 2.25 PFLOP/s bf16), no int8 figure is in MEASURED_PEAKS.json.  The measured tensor-pipe activity of the
-        # same launch is in the committed ncu capture.
-        micro["gemm_cfg2"]["int8_ops_executed_per_s"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] * 1e12
-        micro["gemm_cfg2"]["frac_of_nominal_int8_4500T"] = 3.0 * micro["gemm_cfg2"]["tflops_algorithmic"] / 4500.0
-        micro["gemm_cfg2"]["algorithmic_vs_measured_bf16_burst"] = micro["gemm_cfg2"]["tflops_algorithmic"] / pk["bf16"]
-        micro["gemm_cfg2"]["ncu_tensor_pipe_active"] = "77.4 % (profiles/r1z_gemm_cfg2fc1_full.md)"
         out["kernels"] = micro
-    if world == 1 and not args.no_cpu_baseline:
+    if extras and not args.no_cpu_baseline:
         cb, _ = cpu_reference_run(6, 1)
         out["cpu_baseline"] = cb
     print(json.dumps(out))

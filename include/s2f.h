@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 6 */
+S2F_API int s2f_abi_version(void);   /* currently 7 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -239,6 +239,13 @@ S2F_API int s2f_semantic_tail(const float* mask_pred, const float* cls, float* l
 S2F_API int64_t s2f_semantic_tail_ws_bytes(int n, int K);
 S2F_API int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, float* logits, uint8_t* labels, void* ws,
                          int n, int Q, int K, int h, int w, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement aid ("int8 peak not measured yet -> measure it before quoting utilisation").
+ * Issues `iters` x 4 back-to-back tcgen05.mma (M=128, N=256; kind 0 = kind::i8, K=32; kind 1 = kind::f16 on bf16,
+ * K=16) per SM on operands resident in shared memory: the tensor-pipe ceiling for that MMA kind.
+ * Returns the operations (2 x MACs) one launch performs, or -1. */
+S2F_API int64_t s2f_peak_mma(int kind, int iters, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S2F_LIB") or os.path.join(_HERE, "libs2f.so")      # S2F_LIB: experiment builds only
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class ConvArgs(C.Structure):
@@ -62,6 +62,7 @@ SIGNATURES = {
     "s2f_semantic_tail": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "s2f_semantic_tail_ws_bytes": (_L, [_I, _I]),
     "s2f_semantic_tail_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "s2f_peak_mma": (_L, [_I, _I, _P]),
 }
 
 _lib = None

@@ -37,6 +37,10 @@ class Gemm:
         self.cout, self.cin, self.k, self.stride, self.pad = int(w2d.shape[0]), int(cin), k, stride, pad
         self.w = ops.pad_rows4(fold.f32(w2d, device))
         self.scale, self.shift = fold.f32(scale, device), fold.f32(shift, device)
+        # MACs per output row the REFERENCE's layer(s) perform for what this launch computes (bench.py's roofline counts
+        # algorithmic work: a re-parameterised RepConv executes 9*C*C here but is 2*C*C + 9*C there; zero-padded
+        # channels are not work either).  None: the executed count is the algorithmic one.
+        self.alg_macs = None
         # tensor-core form: int8 digit planes + scale with the packer's power-of-two row scale folded in
         self.tc = None
         if spike_in and USE_TC and ops.tc_eligible(self.cin, k, stride) and pad == (k - 1) // 2:
@@ -48,7 +52,8 @@ class Gemm:
             sc = self.tc[1] if a_scale == 1.0 else self._scaled(a_scale)
             return ops.gemm_tc(a, self.tc[0], n=n, H=H, W=W, Cin=self.cin, Cout=self.cout, scale=sc, shift=self.shift,
                                k=self.k, stride=self.stride, pad=self.pad, pieces=TC_PIECES, residual=residual,
-                               want_f32=f32, want_spike=spike, transposed=transposed, up_prev=up_prev)
+                               want_f32=f32, want_spike=spike, transposed=transposed, up_prev=up_prev,
+                               alg_macs=self.alg_macs)
         if up_prev is not None:
             raise RuntimeError("fused FPN merge needs the tensor-core path")
         return self._simt(a, n, H, W, residual, f32, spike, transposed, a_scale, **kw)
@@ -146,7 +151,9 @@ def _conv_gemm(sd, conv_key, bn_key, device, k=1, stride=1, pad=0, extra_scale=N
     w = sd[conv_key + ".weight"]
     s, t = fold.conv_bn(sd, conv_key, bn_key, extra_scale)
     w2d, s, t, cin = _pad_channels(fold.w_khwc(w), s, t, k * k, cin_pad, cout_pad)
-    return Gemm(w2d, s, t, cin, k, stride, pad, device)
+    gm = Gemm(w2d, s, t, cin, k, stride, pad, device)
+    gm.alg_macs = int(w.shape[0]) * int(w[0].numel())          # the reference's (unpadded) Cout * Cin * k * k
+    return gm
 
 
 def head_pad(d):
@@ -183,7 +190,11 @@ def _rep_gemm(sd, keys, device, cin_pad=None, cout_pad=None, out_heads=None, in_
         w4[:, :, idx] = w3
         w = w4.reshape(w.shape[0], -1)
     w, s, b, cin = _pad_channels(w, torch.ones_like(b), b, 9, cin_pad, cout_pad)
-    return Gemm(w, s, b, cin, 3, 1, 1, device)
+    gm = Gemm(w, s, b, cin, 3, 1, 1, device)
+    # RepConv (sdtv2.py:111-132): 1x1 (C*C) + depthwise 3x3 (9*C) + 1x1 (C*C) MACs per pixel and branch
+    gm.alg_macs = sum(2 * int(sd[k + ".0.body.0.weight"].shape[0]) * int(sd[k + ".0.body.0.weight"].shape[1]) +
+                      9 * int(sd[k + ".0.body.2.0.weight"].shape[0]) for k in keys)
+    return gm
 
 
 def _dw(sd, conv_key, bn_key, device):
@@ -770,8 +781,10 @@ def _mask_pred(model, me_rows, ysp, transposed):
     wb, _ = pdl["mask_fold"](me_rows.contiguous(), 1, n * R, 1, f32=True, a_scale=model.alpha * INV)   # [1, n*R, 1, cin+1]
     packed, sc, sh = ops.pack_rows_i8_device(wb.view(n * R, cin + 1), n_img=n, rows_per_img=R, K=cin, pieces=TC_PIECES,
                                              post_scale=INV, bias_col=cin)
+    # the reference computes mask_feature (C_in x C_out per pixel, pixel_decoder.py:467-470) and then the einsum
+    # (R x C_out per pixel, maskformer_head.py:581); folded, only R x C_in per pixel is executed
     out, _ = ops.gemm_tc(ysp, packed, n=n, H=h, W=w, Cin=cin, Cout=R, scale=sc, shift=sh, pieces=TC_PIECES,
-                         want_f32=True, transposed=transposed, per_image=True)
+                         want_f32=True, transposed=transposed, per_image=True, alg_macs=cin * dim + R * dim)
     return out
 
 
@@ -847,12 +860,13 @@ class GraphedForward:
 HBM_CLASSES = ("nilif", "dwconv", "dcn_gather", "upsample_add_lif", "elementwise", "linear_attn")
 
 
-def profile_dominant(seg, img, steps=2):
+def profile_dominant(seg, img, steps=2, labels=False):
     """Time every launch of `steps` forwards with CUDA events on the launch stream and report the kernel
-    class that takes the largest share of the step (bench.py's `roofline` object)."""
+    class that takes the largest share of the step (bench.py's `roofline` object) plus a per-class table:
+    ms, launches, ALGORITHMIC TFLOP/s (the reference layers' work), executed TFLOP/s, GB/s."""
     prof = ops.Profiler()
     with torch.no_grad():
-        segmentor_logits(seg, img)                      # warm
+        segmentor_logits(seg, img, labels=labels)       # warm
         torch.cuda.synchronize()
         for _ in range(steps):
             # park the GPU behind a ~0.3 s spin kernel while the host enqueues the whole forward: the events then
@@ -860,7 +874,7 @@ def profile_dominant(seg, img, steps=2):
             torch.cuda._sleep(int(6e8))
             ops.set_profiler(prof)
             try:
-                segmentor_logits(seg, img)
+                segmentor_logits(seg, img, labels=labels)
             finally:
                 ops.set_profiler(None)
             torch.cuda.synchronize()
@@ -869,11 +883,18 @@ def profile_dominant(seg, img, steps=2):
     name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     tensor = name.startswith("gemm") or name == "semantic_tail"
     sec = top["ms"] / 1e3
+    classes = {}
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        t = v["ms"] / 1e3
+        classes[k] = dict(ms=round(v["ms"] / steps, 3), launches=v["launches"] // steps,
+                          tflops_algorithmic=round(v["flops"] / t / 1e12, 1), tflops_executed=round(v["exec_flops"] / t / 1e12, 1),
+                          gbs=round(v["bytes"] / t / 1e9, 0))
     return dict(kernel=name, bound="tensor" if tensor else "hbm",
                 achieved=(top["flops"] / sec / 1e12) if tensor else (top["bytes"] / sec / 1e9),
+                achieved_executed=(top["exec_flops"] / sec / 1e12) if tensor else None,
                 unit="TFLOP/s" if tensor else "GB/s", share=top["ms"] / total, launches=top["launches"] // steps,
                 dtype="f32 (int8 spikes x fp32 weights)" if name == "gemm_simt" else "int8 spikes x int8 weight digits",
-                per_class_ms={k: round(v["ms"] / steps, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])})
+                per_class_ms={k: v["ms"] for k, v in classes.items()}, classes=classes, step_ms=total / steps)
 
 
 def segmentor_logits(seg, img, probe=NOPROBE, labels=False):

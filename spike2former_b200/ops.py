@@ -46,9 +46,9 @@ class Profiler:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for cls, e0, e1, fl, by, _ in self.records:
-            a = agg.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            a["ms"] += e0.elapsed_time(e1); a["flops"] += fl; a["bytes"] += by; a["launches"] += 1
+        for cls, e0, e1, fl, by, _, ex in self.records:
+            a = agg.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, exec_flops=0.0))
+            a["ms"] += e0.elapsed_time(e1); a["flops"] += fl; a["bytes"] += by; a["launches"] += 1; a["exec_flops"] += ex
         return agg
 
 
@@ -68,12 +68,13 @@ def _p0():
     return e
 
 
-def _p1(e0, cls, flops=0.0, nbytes=0.0, detail=""):
+def _p1(e0, cls, flops=0.0, nbytes=0.0, detail="", exec_flops=None):
+    """flops: ALGORITHMIC work of the reference layer(s) this launch stands for; exec_flops: what the kernel executes."""
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    _PROF.records.append((cls, e0, e1, float(flops), float(nbytes), detail))
+    _PROF.records.append((cls, e0, e1, float(flops), float(nbytes), detail, float(flops if exec_flops is None else exec_flops)))
 
 
 def _nb(*ts):
@@ -227,7 +228,7 @@ def pack_rows_i8_device(w, *, n_img, rows_per_img, K, pieces=3, post_scale=1.0, 
 
 
 def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad=0, pieces=3, residual=None,
-            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX, per_image=False, up_prev=None):
+            want_f32=False, want_spike=False, transposed=False, d_max=D_MAX, per_image=False, up_prev=None, alg_macs=None):
     """tcgen05 spike GEMM.  a: int8 levels channels-last; `scale` already contains rowscale * 1/8."""
     if a.dtype != torch.int8:
         raise S2FError("gemm_tc: a must be int8 levels")
@@ -251,8 +252,11 @@ def gemm_tc(a, w_packed, *, n, H, W, Cin, Cout, scale, shift, k=1, stride=1, pad
         args.up_prev, args.up_H, args.up_W = _ptr(up_prev, torch.float32, "up_prev"), int(up_prev.shape[1]), int(up_prev.shape[2])
     e0 = _p0()
     check(_lib.lib().s2f_gemm_i8_tc(C.byref(args), _stream()), "s2f_gemm_i8_tc")
-    _p1(e0, "gemm_tc", 2.0 * n * Ho * Wo * Cout * k * k * Cin, _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces,
-        f"{n}x{H}x{W} {Cin}->{Cout} k{k}s{stride} f32={int(want_f32)} sp={int(want_spike)} res={int(residual is not None)} tr={int(transposed)}")
+    executed = 2.0 * n * Ho * Wo * Cout * k * k * Cin
+    _p1(e0, "gemm_tc", executed if alg_macs is None else 2.0 * n * Ho * Wo * alg_macs,
+        _nb(a, residual, out_f32, out_spike) + Cout * k * k * Cin * pieces,
+        f"{n}x{H}x{W} {Cin}->{Cout} k{k}s{stride} f32={int(want_f32)} sp={int(want_spike)} res={int(residual is not None)} tr={int(transposed)}",
+        exec_flops=executed)
     return out_f32, out_spike
 
 
@@ -374,6 +378,14 @@ def stem_u8(img, w_packed, scale, shift_tab, *, Cout, want_f32=True, want_spike=
                                  float(d_max), _stream()), "s2f_stem_u8")
     _p1(e0, "stem_u8", 2.0 * n * Ho * Wo * Cout * 147, _nb(img, of, os_), f"{n}x{H}x{W} uint8 3->{Cout} k7s2")
     return of, os_
+
+
+def peak_mma(kind="i8", iters=4096):
+    """One launch of the tensor-pipe issue-rate kernel (csrc/peak.cu) on the current stream -> operations performed."""
+    n = int(_lib.lib().s2f_peak_mma({"i8": 0, "bf16": 1}[kind], int(iters), _stream()))
+    if n < 0:
+        check(1, "s2f_peak_mma")
+    return n
 
 
 def level_hist(levels, hist=None):

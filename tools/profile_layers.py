@@ -28,7 +28,7 @@ with torch.no_grad():
     ops.set_profiler(None)
 torch.cuda.synchronize()
 agg = {}
-for cls, e0, e1, fl, by, detail in prof.records:
+for cls, e0, e1, fl, by, detail, _ex in prof.records:
     a = agg.setdefault((cls, detail), [0.0, 0.0, 0.0, 0])
     a[0] += e0.elapsed_time(e1); a[1] += fl; a[2] += by; a[3] += 1
 tot = sum(a[0] for a in agg.values())
