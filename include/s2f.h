@@ -241,6 +241,16 @@ S2F_API int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, float
                          int n, int Q, int K, int h, int w, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Masked decoder attention in the reference's association order ({Cross,}MultiHeadAttentionBlock.forward,
+ * mmcv_spike/transformer.py:262-270 and 345-353): scores = Q K^T * (out_scale folds 1/sqrt(embed_dim) and the spike
+ * normalisers); scores.masked_fill(mask, 0); out = scores V; levels = NI-LIF(out).  mask: uint8 [n*heads, Nq, Nk],
+ * non-zero = masked (the reference's bool attn_mask reshaped at :266-267 / :350-351), or NULL.  q [n,Nq,q_ld],
+ * k / v [n,Nk,kv_ld] int8 levels with head h at columns h*d..h*d+d-1; exact int64 accumulation over the keys. */
+S2F_API int s2f_dec_attn(const int8_t* q, const int8_t* k, const int8_t* v, const uint8_t* mask, int8_t* out_spike,
+                 float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld, int out_ld,
+                 float out_scale, float d_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement aid ("int8 peak not measured yet -> measure it before quoting utilisation").
  * Issues `iters` x 4 back-to-back tcgen05.mma (M=128, N=256; kind 0 = kind::i8, K=32; kind 1 = kind::f16 on bf16,
  * K=16) per SM on operands resident in shared memory: the tensor-pipe ceiling for that MMA kind.

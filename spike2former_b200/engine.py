@@ -669,9 +669,11 @@ def pixel_decoder_forward_public(model, x):
 
 
 # ------------------------------------------------------------------------------------------------ decoder + SDME
-def _attention(L, key, pfx, q_sp, k_sp, v_sp, n, nq, nk, heads, dim, residual, pr, kv_cache=None):
+def _attention(L, key, pfx, q_sp, k_sp, v_sp, n, nq, nk, heads, dim, residual, pr, kv_cache=None, attn_mask=None):
     """{Cross,}MultiHeadAttentionBlock (mmcv_spike/transformer.py:237-278, 318-361) from the LIF levels of
-    its three inputs.  Linear form: NI-LIF(Q (K^T V) / sqrt(dim)); out_conv epilogue adds the residual."""
+    its three inputs.  Linear form: NI-LIF(Q (K^T V) / sqrt(dim)); out_conv epilogue adds the residual.
+    attn_mask (bool [n*heads, nq, nk], True = masked_fill(0), :265-269 / :349-353) switches to the key-walking kernel
+    s2f_dec_attn, because a mask does not commute with the Q (K^T V) re-association."""
     q_sp = pr.spike(key + ".q_conv_spike", q_sp, "same")
     _, q = L[pfx + ".q"](q_sp, n, nq, 1, spike=True)
     q = pr.spike(key + ".q_spike", q.view(n, nq, dim), "same")
@@ -681,16 +683,23 @@ def _attention(L, key, pfx, q_sp, k_sp, v_sp, n, nq, nk, heads, dim, residual, p
     v_sp = pr.spike(key + ".v_conv_spike", v_sp, "same")
     _, v = L[pfx + ".v"](v_sp, n, nk, 1, spike=True)
     v = pr.spike(key + ".v_spike", v.view(n, nk, dim), "same")
-    att, _ = ops.linear_attn(q, k, v, n=n, Nq=nq, Nk=nk, heads=heads, d=dim // heads,
-                             out_scale=INV ** 3 / (dim ** 0.5))
+    if attn_mask is None:
+        att, _ = ops.linear_attn(q, k, v, n=n, Nq=nq, Nk=nk, heads=heads, d=dim // heads,
+                                 out_scale=INV ** 3 / (dim ** 0.5))
+    else:
+        att, _ = ops.dec_attn(q, k, v, n=n, Nq=nq, Nk=nk, heads=heads, d=dim // heads, mask=attn_mask,
+                              out_scale=INV ** 3 / (dim ** 0.5))
     att = pr.spike(key + ".attn_spike", att, "same")
     out, _ = L[pfx + ".out"](att, n, nq, 1, residual=residual, f32=True)
     return out.view(n, nq, dim)
 
 
-def head_forward(model, feats, probe=NOPROBE, last_only=False):
+def head_forward(model, feats, probe=NOPROBE, last_only=False, cross_attn_masks=None):
     """mmdet MaskFormerHead.forward (dense_heads/maskformer_head.py:498-586).
-    Returns (cls [L,n,nq,K+1], mask levels int8 [L,n,nq,C], mask_feature [n,h,w,C]); L = 1 when last_only."""
+    Returns (cls [L,n,nq,K+1], mask levels int8 [L,n,nq,C], mask_feature [n,h,w,C]); L = 1 when last_only.
+    cross_attn_masks: optional list (one entry per decoder layer, None or bool [n*heads, nq, nk_level]) -- the
+    `cross_attn_mask` argument of DetrTransformerDecoderLayer.forward (detr_layers.py:491-559); the Spike2Former configs
+    pass None (maskformer_head.py:563)."""
     pd_model = model.pixel_decoder
     pr = probe
     side = None
@@ -727,7 +736,7 @@ def head_forward(model, feats, probe=NOPROBE, last_only=False):
         k = f"transformer_decoder.layers.{i}"
         q_sp, _, _ = ops.nilif(qf, residual=qe, residual_period=qe.numel())
         qf = _attention(L, k + ".cross_attn.attn", f"{i}.cross_attn", q_sp, lvl_k[lv], lvl_v[lv], n, nq, lvl_n[lv], heads,
-                        dim, qf, pr)
+                        dim, qf, pr, attn_mask=cross_attn_masks[i] if cross_attn_masks is not None else None)
         qf = pr.real(k + ".self_attn.attn.v_conv_spike", qf, "same")
         qk_sp, _, _ = ops.nilif(qf, residual=qe, residual_period=qe.numel())
         v_sp, _, _ = ops.nilif(qf)

@@ -299,6 +299,31 @@ def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=Non
     return out_s, out_f
 
 
+def dec_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, mask=None, q_ld=None, kv_ld=None, out_ld=None, want_f32=False,
+             d_max=D_MAX):
+    """Masked spike attention in the reference's order: NI-LIF(((Q K^T) masked_fill(mask, 0)) V * out_scale).
+    mask: bool / uint8 [n*heads, Nq, Nk] (True = masked, mmcv_spike/transformer.py:265-269, 349-353) or None."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if not isinstance(t, torch.Tensor) or t.dtype != torch.int8 or not t.is_cuda:
+            raise S2FError(f"dec_attn: {nm} must be CUDA int8 levels (no CPU path)")
+    Cc = heads * d
+    if mask is not None:
+        if not mask.is_cuda or mask.numel() != n * heads * Nq * Nk:
+            raise S2FError("dec_attn: mask must be a CUDA tensor of n*heads*Nq*Nk elements")
+        mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        mask = _ptr(mask.contiguous(), torch.uint8, "mask")
+    out_ld = int(out_ld or Cc)
+    out_s = torch.zeros((n, Nq, out_ld), dtype=torch.int8, device=q.device) if out_ld != Cc else \
+        torch.empty((n, Nq, out_ld), dtype=torch.int8, device=q.device)
+    out_f = torch.zeros((n, Nq, out_ld), dtype=torch.float32, device=q.device) if want_f32 else None
+    e0 = _p0()
+    check(_lib.lib().s2f_dec_attn(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), mask,
+                                  _ptr(out_s), _ptr(out_f), n, Nq, Nk, heads, d, int(q_ld or Cc), int(kv_ld or Cc), out_ld,
+                                  float(out_scale), float(d_max), _stream()), "s2f_dec_attn")
+    _p1(e0, "linear_attn", 4.0 * n * heads * d * Nq * Nk, n * (Nq + 2 * Nk) * Cc + _nb(out_s, out_f), f"{n} x Nq{Nq} Nk{Nk} masked")
+    return out_s, out_f
+
+
 def dcnv3_gather(x, offset, mask, *, n, H, W, G, Cg, K=3, offset_scale=1.0, mask_scale=1.0 / NORM):
     """DCNv3 sampling core (dcnv3_core_pytorch, dcnv3_func.py:147-189)."""
     out = torch.empty((n, H, W, G * Cg), dtype=torch.float32, device=x.device)

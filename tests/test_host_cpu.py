@@ -143,3 +143,88 @@ def test_fused_stem_host_folding_reproduces_the_oracle_on_cpu():
                 out[:, :, ho, wo] = S * stem.scale.double()[None, :] + tab[top, bot, lef, rig][None, :]
         scale = max(1.0, ref.abs().max().item())
         assert (out - ref).abs().max().item() < 2e-5 * scale, chw
+
+
+REF_CFG = "/root/reference/Segmentation/configs/Spike2Former"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("fname,params,classes,T", [
+    ("SDTv2_maskformer_DCNpixelDecoder_ade20k.py", 34361112, 150, 1),
+    ("SDTv2_maskformer_DCNPixelDecoder_CityScapes.py", 37491605, 19, 1),
+    ("SDTv2_maskformer_cocostuff10k_512x512.py", None, 171, 4),
+])
+def test_reference_config_files_drop_in_unchanged(fname, params, classes, T):
+    """The reference's own config files (exec'd as plain Python: `_base_` is just a list literal) -> their `model=`
+    dict -> MODELS.build: the registry surface of BASELINE.json's north star ("the existing configs under
+    Segmentation/configs drop in unchanged")."""
+    ns = {}
+    exec(compile(open(os.path.join(REF_CFG, fname)).read(), fname, "exec"), ns)
+    seg = s2f.MODELS.build(ns["model"])
+    assert type(seg).__name__ == "EncoderDecoder" and type(seg.backbone).__name__ == "Spiking_vit_MetaFormer"
+    assert type(seg.decode_head.pixel_decoder).__name__ == "DCNTransformerEncoderPixelDecoder"
+    assert seg.num_classes == classes and seg.backbone.T == T
+    assert seg.backbone.init_cfg["checkpoint"] == ns["checkpoint_file"]           # kept for init_weights (sdtv2.py:577-612)
+    if params is not None:
+        assert sum(p.numel() for p in seg.parameters()) == params
+    dp = seg.data_preprocessor
+    assert dp.channel_conversion and dp.size == tuple(ns["crop_size"]) or list(dp.size) == list(ns["crop_size"])
+    if "CityScapes" in fname:
+        assert dp.test_cfg == dict(size_divisor=32)
+        mine = s2f.configs.cityscapes()["data_preprocessor"]
+        assert tuple(mine["size"]) == tuple(ns["crop_size"]) and mine["test_cfg"] == dict(size_divisor=32)
+
+
+def test_preprocessor_metainfo_follows_stack_batch():
+    """SegDataPreProcessor.forward must write the metainfo keys of mmseg's stack_batch
+    (data_preprocessor.py:127-150, utils/misc.py:94-116): training -> img_shape (UNPADDED), pad_shape, padding_size;
+    test-time padding -> img_padding_size and pad_shape only, img_shape untouched.  CPU part: the bookkeeping is
+    checked with the normalisation kernel stubbed out (no GPU here)."""
+    from spike2former_b200 import models
+
+    class Field:
+        def __init__(self, data):
+            self.data = data
+
+        @property
+        def shape(self):
+            return self.data.shape
+
+    class Sample:
+        def __init__(self, h, w):
+            self.gt_sem_seg = Field(torch.zeros(1, h, w, dtype=torch.long))
+            self.meta = {"img_shape": (h, w), "ori_shape": (h, w)}
+
+        def __contains__(self, k):
+            return hasattr(self, k)
+
+        def set_metainfo(self, d):
+            self.meta.update(d)
+
+    def fake_normalized(self, batch, size=None, size_divisor=None, out=None):
+        hp, wp = self._padded_size(batch.shape[2], batch.shape[3], size, size_divisor)
+        return torch.zeros(batch.shape[0], hp, wp, 3)
+
+    pre = models.SegDataPreProcessor(mean=[1, 2, 3], std=[1, 1, 1], size=(64, 96), bgr_to_rgb=True, seg_pad_val=255,
+                                     test_cfg=dict(size_divisor=32))
+    orig_norm, orig_cuda = models.SegDataPreProcessor.normalized, torch.Tensor.cuda
+    models.SegDataPreProcessor.normalized = fake_normalized
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        imgs = [torch.zeros(3, 50, 70, dtype=torch.uint8) for _ in range(2)]
+        tr = [Sample(50, 70) for _ in range(2)]
+        out = pre({"inputs": imgs, "data_samples": tr}, training=True)
+        assert tuple(out["inputs"].shape) == (2, 3, 64, 96)
+        for s in tr:
+            assert tuple(s.meta["img_shape"]) == (50, 70) and tuple(s.meta["pad_shape"]) == (1, 64, 96)
+            assert tuple(s.meta["padding_size"]) == (0, 26, 0, 14) and "img_padding_size" not in s.meta
+            assert tuple(s.gt_sem_seg.data.shape) == (1, 64, 96) and int(s.gt_sem_seg.data[0, -1, -1]) == 255
+        te = [Sample(50, 70) for _ in range(2)]
+        out = pre({"inputs": imgs, "data_samples": te}, training=False)
+        assert tuple(out["inputs"].shape) == (2, 3, 64, 96)             # size_divisor 32: 50 x 70 -> 64 x 96
+        for s in te:
+            assert tuple(s.meta["img_padding_size"]) == (0, 26, 0, 14) and tuple(s.meta["pad_shape"]) == (64, 96)
+            assert tuple(s.meta["img_shape"]) == (50, 70) and "padding_size" not in s.meta       # untouched
+            assert tuple(s.gt_sem_seg.data.shape) == (1, 50, 70)                                  # labels are not padded at test time
+    finally:
+        models.SegDataPreProcessor.normalized, torch.Tensor.cuda = orig_norm, orig_cuda

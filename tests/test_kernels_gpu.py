@@ -285,6 +285,96 @@ def test_linear_attn_exact(n, Nq, Nk, heads, d):
     assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
 
 
+@pytest.mark.parametrize("n,Nq,Nk,heads,d,masked", [(2, 100, 1024, 8, 32, True), (1, 37, 300, 4, 45, True), (2, 20, 64, 2, 64, True),
+                                                    (1, 100, 4096, 8, 32, False)])
+def test_dec_attn_masked_matches_reference_order(n, Nq, Nk, heads, d, masked):
+    """s2f_dec_attn: scores = Q K^T / sqrt(dim); masked_fill(mask, 0); out = scores V; NI-LIF
+    (mmcv_spike/transformer.py:262-270, 345-353) -- against the same expression in float64, and against the linear
+    kernel when there is no mask."""
+    g = gen(17)
+    C = heads * d
+    q, k, v = _levels((n, Nq, C), g), _levels((n, Nk, C), g), _levels((n, Nk, C), g)
+    mask = (torch.rand(n * heads, Nq, Nk, generator=g) < 0.3) if masked else None
+    scale = 1.0 / (C ** 0.5) / 512
+    hs = lambda t, N: t.double().view(n, N, heads, d).permute(0, 2, 1, 3)
+    scores = hs(q, Nq) @ hs(k, Nk).transpose(-2, -1)
+    if masked:
+        scores = scores.masked_fill(mask.view(n, heads, Nq, Nk), 0)
+    ref = (scores @ hs(v, Nk)).permute(0, 2, 1, 3).reshape(n, Nq, C) * scale
+    os_, of = ops.dec_attn(q.cuda(), k.cuda(), v.cuda(), n=n, Nq=Nq, Nk=Nk, heads=heads, d=d, out_scale=scale,
+                           mask=mask.cuda() if masked else None, want_f32=True)
+    assert (of.cpu().double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+    if not masked:
+        ls, lf = ops.linear_attn(q.cuda(), k.cuda(), v.cuda(), n=n, Nq=Nq, Nk=Nk, heads=heads, d=d, out_scale=scale, want_f32=True)
+        assert torch.equal(ls, os_) and torch.equal(lf, of)
+
+
+def test_decoder_layer_with_cross_attention_mask_vs_oracle():
+    """engine.head_forward(cross_attn_masks=...) against the oracle's decoder with the same masks
+    (detr_layers.py:491-559 `cross_attn_mask`): query states after every layer."""
+    import spike2former_b200 as s2f
+    from oracle import port, weights
+    from spike2former_b200 import engine
+
+    cfg = s2f.configs.tiny()
+    P = weights.calibrated_state(cfg, 64, 64)
+    img = weights.test_image(cfg, 64, 64, batch=2)
+    heads = cfg["decode_head"]["transformer_decoder"]["layer_cfg"]["self_attn_cfg"]["num_heads"]
+    nq = cfg["decode_head"]["num_queries"]
+    g = gen(23)
+    masks = [torch.rand(2 * heads, nq, (64 // 16) ** 2 * 4 ** (i % 3), generator=g) < 0.4 for i in range(6)]
+    # oracle: the port's decoder_layer takes cross_mask
+    cx = port.Ctx(P)
+    cx.marks = {}
+    with torch.no_grad():
+        feats = port.backbone_forward(cx, cfg["backbone"], img)
+        orig = port.decoder_layer
+        calls = []
+
+        def with_mask(cx_, key, query, kv, qpos, kpos, heads_, cross_mask=None):
+            i = int(key.rsplit(".", 1)[1])
+            calls.append(i)
+            return orig(cx_, key, query, kv, qpos, kpos, heads_, masks[i])
+
+        port.decoder_layer = with_mask
+        try:
+            port.head_forward(cx, cfg["decode_head"], feats, 1)
+        finally:
+            port.decoder_layer = orig
+    assert calls == list(range(6))
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(P, strict=True)
+    seg = seg.cuda()
+
+    class Rec(engine.NullProbe):
+        observe = True
+
+        def __init__(self, prefix="", store=None):
+            self.prefix, self.store = prefix, ({} if store is None else store)
+
+        def scoped(self, p):
+            return Rec(self.prefix + p, self.store)
+
+        def real(self, name, t, layout="cm"):
+            self.store[self.prefix + name] = t.detach().clone()
+            return t
+
+    rec = Rec("decode_head.")
+    with torch.no_grad():
+        f2 = engine.backbone_forward(seg.backbone, img.cuda())
+        engine.head_forward(seg.decode_head, f2, rec, cross_attn_masks=[m.cuda() for m in masks])
+    for i in range(6):
+        key = f"decode_head.transformer_decoder.layers.{i}.out"
+        want, got = cx.marks[key], rec.store[key].cpu()
+        assert (got - want).abs().max() <= 1e-3 * want.abs().max(), (i, float((got - want).abs().max()))
+    # and the masks matter
+    rec2 = Rec("decode_head.")
+    with torch.no_grad():
+        engine.head_forward(seg.decode_head, f2, rec2)
+    assert not torch.equal(rec2.store["decode_head.transformer_decoder.layers.5.out"], rec.store["decode_head.transformer_decoder.layers.5.out"])
+
+
 def test_linear_attn_strided_operands_and_padded_output():
     """q|k|v as column slices of one fused [n, N, 3C] projection (engine._ms_block) and a 16-byte padded output row."""
     g = gen(12)
