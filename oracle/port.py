@@ -34,8 +34,9 @@ class Ctx:
     tap:       callable(name, pre_activation, spike_levels) called at every neuron.
     """
 
-    def __init__(self, P, calibrate=False, tap=None, d_max=8.0, norm=8.0, mutate=None):
+    def __init__(self, P, calibrate=False, tap=None, d_max=8.0, norm=8.0, mutate=None, train=False):
         self.P, self.calibrate, self.tap = P, calibrate, tap
+        self.train = train         # training mode: batch-statistics BatchNorm (momentum 0.1) + surrogate-gradient neurons
         self.mutate = mutate       # callable(name, levels) -> levels: fault injection for the stability experiments
         self.d_max, self.norm = d_max, norm
         self.ties = 0
@@ -50,24 +51,42 @@ class Ctx:
 
 
 # ----------------------------------------------------------------------------- primitives
+class QuantSTE(torch.autograd.Function):
+    """`quant` (surrogate.py:522-538): forward round(clamp(i, 0, 8)); backward grad * 1[0 <= i <= 8]."""
+
+    @staticmethod
+    def forward(ctx, i, d_max):
+        ctx.save_for_backward(i)
+        ctx.d_max = d_max
+        return torch.round(torch.clamp(i, min=0, max=d_max))
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (i,) = ctx.saved_tensors
+        g = grad_output.clone()
+        g[i < 0] = 0
+        g[i > ctx.d_max] = 0
+        return g, None
+
+
 def lif(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
     """Q_IFNode(Quant()) after reset: neuron.py:459-460 (charge), :115-131 + surrogate.py:522-529
     (fire = round(clamp(v,0,8)), round half to even), :133-153 (soft reset, unused after), :197 (/8)."""
     v = 0.0 + x
-    s = torch.round(torch.clamp(v, min=0, max=cx.d_max))
+    s = QuantSTE.apply(v, cx.d_max) if cx.train else torch.round(torch.clamp(v, min=0, max=cx.d_max))
     if cx.mutate is not None:
         s = cx.mutate(name, s)
     cx.neurons += 1
     cx.elems += x.numel()
     if cx.tap is not None:
-        cx.tap(name, x, s)
+        cx.tap(name, x.detach(), s.detach())
     return s / cx.norm
 
 
 def bn(cx: Ctx, key: str, x: torch.Tensor) -> torch.Tensor:
     P = cx.P
     return F.batch_norm(x, P[key + ".running_mean"], P[key + ".running_var"], P[key + ".weight"], P[key + ".bias"],
-                        training=cx.calibrate, momentum=1.0 if cx.calibrate else 0.1, eps=BN_EPS)
+                        training=cx.calibrate or cx.train, momentum=1.0 if cx.calibrate else 0.1, eps=BN_EPS)
 
 
 def conv(cx: Ctx, key: str, x, stride=1, pad=0, groups=1):
@@ -86,7 +105,8 @@ def rep_conv(cx, key, x):
     y = conv(cx, key + ".0.body.0", x)
     k = key + ".0.body.1.bn"
     y = bn(cx, k, y)
-    pad_val = P[k + ".bias"] - P[k + ".running_mean"] * P[k + ".weight"] / torch.sqrt(P[k + ".running_var"] + BN_EPS)
+    pad_val = P[k + ".bias"].detach() - P[k + ".running_mean"] * P[k + ".weight"].detach() / \
+        torch.sqrt(P[k + ".running_var"] + BN_EPS)                                    # sdtv2.py:68-74 (detached)
     y = F.pad(y, [1, 1, 1, 1])
     pv = pad_val.view(1, -1, 1, 1)
     y[:, :, 0:1, :] = pv

@@ -298,3 +298,118 @@ def load_data_preprocessor():
     sys.modules["mmseg.utils"].stack_batch = misc.stack_batch
     mod = _exec("mmseg.models.data_preprocessor_ref", "mmseg/models/data_preprocessor.py")
     return mod.SegDataPreProcessor
+
+
+# --------------------------------------------------------------------------- training glue
+class _InstanceData:
+    """mmengine.structures.InstanceData stand-in: attribute bag whose len() is the length of its first field."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def __len__(self):
+        for v in self.__dict__.values():
+            return len(v)
+        return 0
+
+
+class _Field:
+    def __init__(self, data):
+        self.data = data
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+
+class TrainSample:
+    """SegDataSample stand-in for the loss path: `.gt_sem_seg.data`, `.metainfo`, `.set_metainfo`."""
+
+    def __init__(self, gt_sem_seg, img_shape):
+        self.gt_sem_seg = _Field(gt_sem_seg)
+        self.metainfo = dict(img_shape=tuple(img_shape), ori_shape=tuple(img_shape), pad_shape=tuple(img_shape))
+
+    def set_metainfo(self, d):
+        self.metainfo.update(d)
+
+
+def _multi_apply(func, *args, **kwargs):
+    from functools import partial
+
+    pfunc = partial(func, **kwargs) if kwargs else func
+    return tuple(map(list, zip(*map(pfunc, *args))))
+
+
+_TRAIN = None
+
+
+def load_training():
+    """Execute the reference's OWN loss / matching code: mmdet/models/losses/{utils,cross_entropy_loss,focal_loss,
+    dice_loss}.py, task_modules/assigners/{assign_result,base_assigner,match_cost,hungarian_assigner}.py and
+    task_modules/samplers/{sampling_result,mask_sampling_result,base_sampler,mask_pseudo_sampler}.py, and point the
+    already loaded heads at the real InstanceData / multi_apply / reduce_mean semantics."""
+    global _TRAIN
+    if _TRAIN is not None:
+        return _TRAIN
+    ns = load()
+    models = ns.MODELS
+    task_utils = sys.modules["mmdet.registry"].TASK_UTILS
+
+    class NiceRepr:
+        pass
+
+    _shell("mmdet.utils.util_mixins", NiceRepr=NiceRepr)
+    sys.modules["mmdet.utils"].util_mixins = sys.modules["mmdet.utils.util_mixins"]
+    _shell("mmdet.utils.util_random", ensure_rng=lambda rng=None: rng)
+    _shell("mmdet.structures.bbox", bbox_overlaps=None, bbox_xyxy_to_cxcywh=None, BaseBoxes=type("BaseBoxes", (), {}),
+           cat_boxes=None)
+    sys.modules["mmengine.structures"].InstanceData = _InstanceData
+    sys.modules["mmcv.ops"].sigmoid_focal_loss = None                     # CUDA-only op; the CPU path never calls it
+    _shell("mmdet.models.losses")
+    _exec("mmdet.models.losses.utils", "mmdet/models/losses/utils.py")
+    for f in ("cross_entropy_loss", "focal_loss", "dice_loss"):            # register the REAL losses over the null ones
+        _exec("mmdet.models.losses." + f, f"mmdet/models/losses/{f}.py")
+    _shell("mmdet.models.task_modules")
+    ap = "mmdet.models.task_modules.assigners"
+    _shell(ap)
+    ar = _exec(ap + ".assign_result", "mmdet/models/task_modules/assigners/assign_result.py")
+    sys.modules[ap].AssignResult = ar.AssignResult
+    _exec(ap + ".base_assigner", "mmdet/models/task_modules/assigners/base_assigner.py")
+    _exec(ap + ".match_cost", "mmdet/models/task_modules/assigners/match_cost.py")
+    _exec(ap + ".hungarian_assigner", "mmdet/models/task_modules/assigners/hungarian_assigner.py")
+    sp = "mmdet.models.task_modules.samplers"
+    _shell(sp)
+    _exec(sp + ".sampling_result", "mmdet/models/task_modules/samplers/sampling_result.py")
+    _exec(sp + ".mask_sampling_result", "mmdet/models/task_modules/samplers/mask_sampling_result.py")
+    _exec(sp + ".base_sampler", "mmdet/models/task_modules/samplers/base_sampler.py")
+    _exec(sp + ".mask_pseudo_sampler", "mmdet/models/task_modules/samplers/mask_pseudo_sampler.py")
+    # names the head modules bound at import time
+    for mod in (ns.det_head, ns.seg_head):
+        mod.InstanceData = _InstanceData
+    ns.det_head.multi_apply = _multi_apply
+    ns.det_head.reduce_mean = lambda t: t                                  # single process (dist_utils.py:59-62)
+    ns.task_utils = task_utils
+    assert "HungarianAssigner" in task_utils.table and "FocalLoss" in models.table
+    _TRAIN = ns
+    return ns
+
+
+def build_reference_for_training(cfg, train_cfg):
+    """(backbone, head) with the reference's real losses, HungarianAssigner and MaskPseudoSampler, in train mode."""
+    import copy
+
+    ns = load_training()
+    cfg = copy.deepcopy(cfg)
+    bb_cfg = dict(cfg["backbone"]); bb_cfg.pop("type"); bb_cfg.pop("init_cfg", None)
+    backbone = ns.sdtv2.Spiking_vit_MetaFormer(**bb_cfg)
+    head_cfg = dict(cfg["decode_head"]); head_cfg["train_cfg"] = copy.deepcopy(train_cfg)
+    head = ns.MODELS.build(head_cfg)
+    backbone.train(); head.train()
+    return backbone, head
+
+
+def reference_train_loss(backbone, head, img, gt_sem_seg):
+    """EncoderDecoder.loss (encoder_decoder.py:163-188) after ResetModelHook: dict of the reference's loss terms."""
+    reset_neurons(backbone, head)
+    samples = [TrainSample(gt_sem_seg[i], img.shape[-2:]) for i in range(img.shape[0])]      # [1, H, W] each, as PackSegInputs
+    return head.loss(backbone(img), samples, None)
