@@ -215,6 +215,13 @@ S2F_API int s2f_stem_u8(const uint8_t* img, int chw, const int8_t* w_packed, int
                 const float* shift_tab, float* out_f32, int8_t* out_spike, int n, int H, int W, int Cout, float d_max,
                 void* stream);
 
+/* Training-mode neuron (T = 1, v0 = 0): forward writes the normalised spikes y = rint(clamp(x,0,d_max)) / norm (fp32) and
+ * ONE tag byte per neuron = level | 0x80 when x lies outside [0, d_max]; backward is `quant.backward`
+ * (surrogate.py:531-538) followed by the "/ norm": gx = gy / norm where the range bit is clear, else 0.  The saved state of
+ * a neuron is 1 B instead of the 4 B pre-activation.  All pointers 16-byte aligned. */
+S2F_API int s2f_nilif_train_fwd(const float* x, float* y_norm, uint8_t* tag, int64_t N, float d_max, float norm, void* stream);
+S2F_API int s2f_nilif_train_bwd(const uint8_t* tag, const float* gy, float* gx, int64_t N, float norm, void* stream);
+
 /* Histogram of spike levels: hist16[l] += #{i : levels[i] == l}, l = 0..15 (uint64, accumulated: zero it first).
  * The firing-rate census of tools/cal_firing_num.py:140-171 (firing rate = 1 - hist[0]/N, mean level = sum l*hist[l]/N)
  * taken from the int8 levels the kernels emit.  levels must be 16-byte aligned. */

@@ -63,6 +63,8 @@ SIGNATURES = {
     "s2f_semantic_tail_ws_bytes": (_L, [_I, _I]),
     "s2f_semantic_tail_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "s2f_peak_mma": (_L, [_I, _I, _P]),
+    "s2f_nilif_train_fwd": (_I, [_P, _P, _P, _L, _F, _F, _P]),
+    "s2f_nilif_train_bwd": (_I, [_P, _P, _P, _L, _F, _P]),
     "s2f_dec_attn": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
 }
 

@@ -181,7 +181,18 @@ class MaskFormerHead(_Engined):
         return engine.head_predict(self, x, img_shape)
 
     def loss(self, x, batch_data_samples, train_cfg=None):
-        raise NotImplementedError("training glue (Hungarian matching + losses) is outside the hot path (SURVEY.md section 8f-3)")
+        """-> dict of the 21 loss terms (decode_heads/maskformer_head.py:108-136, dense_heads/maskformer_head.py:367-496).
+        x: the backbone's four maps ([T,B,C,H,W] or [T*B,C,H,W]) with autograd history; see spike2former_b200/train.py."""
+        from . import train
+
+        _require_cuda(x[0], type(self).__name__)
+        owner = getattr(self, "_segmentor", None)
+        if owner is None:
+            raise RuntimeError("MaskFormerHead.loss needs the EncoderDecoder that owns this head (parameter names are rooted there)")
+        net = owner()._training_net()
+        feats = [t.flatten(0, 1) if t.dim() == 5 else t for t in x]
+        gt = torch.stack([ds.gt_sem_seg.data for ds in batch_data_samples]).to(feats[0].device)
+        return train.head_losses(net, feats, gt, self.ignore_index)
 
 
 @register_everywhere
@@ -288,6 +299,10 @@ class EncoderDecoder(_Engined):
         self.decode_head = MODELS.build(decode_head)
         self.data_preprocessor = MODELS.build(data_preprocessor) if isinstance(data_preprocessor, dict) else data_preprocessor
         self.test_cfg = test_cfg
+        import weakref
+
+        self.decode_head._segmentor = weakref.ref(self)
+        self._train_net = None
         self.align_corners = self.decode_head.align_corners
         self.num_classes = self.decode_head.num_classes
         self.out_channels = self.decode_head.out_channels
@@ -343,6 +358,25 @@ class EncoderDecoder(_Engined):
 
     def extract_feat(self, inputs):
         return self.backbone(inputs)
+
+    def _training_net(self):
+        from . import train
+
+        if self._train_net is None or self._train_net[0] != self._epoch:
+            self._train_net = (self._epoch, train.Net(self))
+        return self._train_net[1]
+
+    def loss(self, inputs, data_samples):
+        """EncoderDecoder.loss (encoder_decoder.py:163-188): fp32 [B,3,H,W] + SegDataSamples (`gt_sem_seg.data` [1,H,W])
+        -> dict of loss terms prefixed 'decode.' (add_prefix, :156-161), with autograd history on the parameters.
+        Surrogate-gradient training mode: batch-statistics BatchNorm, see spike2former_b200/train.py."""
+        from . import train
+
+        _require_cuda(inputs, type(self).__name__)
+        net = self._training_net()
+        gt = torch.stack([ds.gt_sem_seg.data for ds in data_samples]).to(inputs.device)
+        losses = train.head_losses(net, net.backbone(inputs), gt, self.decode_head.ignore_index)
+        return {"decode." + k: v for k, v in losses.items()}
 
     def encode_decode(self, inputs, batch_img_metas=None):
         """fp32 [B,3,H,W] -> seg logits [B,K,H,W] (encoder_decoder.py:125-133), whole-image mode.

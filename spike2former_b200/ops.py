@@ -133,6 +133,25 @@ def nilif_bwd(x, gy, scale=None, shift=None, residual=None, C_=None, d_max=D_MAX
     return gx
 
 
+def nilif_train_fwd(x, d_max=D_MAX, norm=NORM):
+    """Training-mode neuron forward: (y = level / norm fp32, tag uint8 = level | 0x80 where x is outside [0, d_max])."""
+    _ptr(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    tag = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(_lib.lib().s2f_nilif_train_fwd(_ptr(x), _ptr(y), _ptr(tag), x.numel(), float(d_max), float(norm), _stream()),
+          "s2f_nilif_train_fwd")
+    return y, tag
+
+
+def nilif_train_bwd(tag, gy, norm=NORM):
+    """Surrogate gradient from the saved tag byte: gx = gy / norm where the neuron's input was inside [0, d_max]."""
+    _ptr(tag, torch.uint8, "tag")
+    _ptr(gy, torch.float32, "gy")
+    gx = torch.empty_like(gy)
+    check(_lib.lib().s2f_nilif_train_bwd(_ptr(tag), _ptr(gy), _ptr(gx), gy.numel(), float(norm), _stream()), "s2f_nilif_train_bwd")
+    return gx
+
+
 def affine_add_lif(x, scale=None, residual=None, want_f32=True, want_spike=True, d_max=D_MAX):
     out_f = torch.empty_like(x) if want_f32 else None
     out_s = torch.empty(x.shape, dtype=torch.int8, device=x.device) if want_spike else None

@@ -62,3 +62,51 @@ def test_shard_range_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.nn as nn
+
+    from spike2former_b200 import train
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = nn.Sequential(nn.Linear(64, 300), nn.ReLU(), nn.Linear(300, 300), nn.ReLU(), nn.Linear(300, 5))
+        unused = nn.Parameter(torch.zeros(7))                       # a parameter that never receives a gradient
+        params = list(model.parameters()) + [unused]
+        buckets = train.GradBuckets(params, bucket_mb=0.2)           # several buckets
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(8, 64, generator=g), torch.randn(8, 5, generator=g)
+        b, e = s2f_dist.shard_range(8, world, rank)
+        for _ in range(2):                                           # hooks re-arm every step
+            model.zero_grad()
+            buckets.start()
+            ((model(x[b:e]) - y[b:e]) ** 2).mean().backward()
+            buckets.finish()
+        got = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        model.zero_grad()
+        ((model(x) - y) ** 2).mean().backward()                      # the full batch on one process
+        want = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        q.put((rank, len(buckets.buckets), float((got - want).abs().max()), buckets.bytes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_buckets_average_like_one_big_batch():
+    """train.GradBuckets (the training step's NCCL all-reduce, here over gloo): two ranks with half the batch each end up
+    with the gradient of the whole batch; buckets are launched from autograd hooks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=60) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, nb, err, nbytes in out:
+        assert nb >= 2 and err < 1e-6 and nbytes == 4 * (64 * 300 + 300 + 300 * 300 + 300 + 300 * 5 + 5 + 7)
