@@ -312,6 +312,50 @@ def build(name, dev):
     return seg                           # so the graph's static output buffer is handed out without a 5 GB copy per step
 
 
+def training_step_bench(dev, world, rank, dist, B, precision, steps=5, warmup=2):
+    """BASELINE.json config 5: one surrogate-gradient training step of the ADE20K model (batch 6 per GPU as in the
+    reference config :181-182, 512x512 crops, synthetic labels), forward + 21 losses + backward + gradient all-reduce over
+    NCCL (N > 1) + clip + AdamW, timed with CUDA events between barriers, max over ranks."""
+    import spike2former_b200 as s2f
+    from spike2former_b200 import dist as s2f_dist, synth, train
+
+    cfg = s2f.configs.ade20k()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint("ade20k", cfg), strict=True)
+    seg = seg.to(dev)
+    step = train.TrainStep(seg, precision=precision)
+    g = torch.Generator().manual_seed(500 + rank)
+    imgs = [torch.randn(B, 3, H, W, generator=g).to(dev) for _ in range(2)]
+    gts = [torch.randint(0, 150, (B, 1, H // 16, W // 16), generator=g).repeat_interleave(16, 2).repeat_interleave(16, 3).to(dev)
+           for _ in range(2)]
+    for i in range(warmup):
+        step(imgs[i & 1], gts[i & 1])
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    timing = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        losses = step(imgs[i & 1], gts[i & 1], timing=timing)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = s2f_dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    out = dict(workload="Spike2Former ADE20K training step (surrogate-gradient NI-LIF backward, 21 loss terms, AdamW, clip 0.01)",
+               batch_per_gpu=B, n_gpus=world, precision=precision, steps=steps, ms_per_step=ms, images_per_second=world * B / (ms / 1e3),
+               phases_ms={k: v / steps for k, v in timing.items()}, total_loss=float(sum(losses.values())),
+               params=sum(p.numel() for p in seg.parameters()),
+               allreduce_bytes_per_step=step.buckets.bytes if step.buckets is not None else 0,
+               allreduce_buckets=len(step.buckets.buckets) if step.buckets is not None else 0,
+               host_syncs_per_step="1 D2H of all 7 x B cost matrices + 1 H2D of the assignments (reference: 7 x B)",
+               peak_memory_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    del step, seg
+    torch.cuda.empty_cache()
+    return out
+
+
 def class_rooflines(roof, pk, tp):
     """Per kernel class: share of the step and the fraction of the roof that bounds it."""
     from spike2former_b200 import engine
@@ -340,6 +384,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip micro-benchmarks, peaks, batch 1 / 8 and the CPU baseline")
     ap.add_argument("--city-batch", type=int, default=4, help="images per GPU for the 1024x2048 config (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=6, help="images per GPU of the training-step measurement (config 5; 0 = skip)")
+    ap.add_argument("--train-precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     args = ap.parse_args()
     from spike2former_b200 import dist as s2f_dist
 
@@ -436,6 +482,8 @@ def main():
         del hc, cseg
         torch.cuda.empty_cache()
 
+    training = training_step_bench(dev, world, rank, dist, args.train_batch, args.train_precision) if args.train_batch > 0 else None
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -477,6 +525,8 @@ def main():
         out["cityscapes_1024x2048"] = city
     if batches:
         out["batches"] = batches
+    if training:
+        out["training_step"] = training
     if micro:
         out["kernels"] = micro
     if extras and not args.no_cpu_baseline:

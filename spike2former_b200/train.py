@@ -529,16 +529,29 @@ class TrainStep:
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
-    def __call__(self, img, gt_sem_seg):
+    def __call__(self, img, gt_sem_seg, timing=None):
+        """timing: optional dict that receives CUDA-event milliseconds of the phases of this step
+        (forward_loss, backward, allreduce_exposed = time spent waiting for NCCL after the backward pass, optimizer)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timing is not None else None
+        mark = (lambda i: ev[i].record()) if ev else (lambda i: None)
         self.opt.zero_grad(set_to_none=False)
         if self.buckets is not None:
             self.buckets.start()
+        mark(0)
         losses = self.losses(img, gt_sem_seg)
         total = sum(v for k, v in losses.items() if "loss" in k)         # mmengine parse_losses
+        mark(1)
         total.backward()
+        mark(2)
         if self.buckets is not None:
             self.buckets.finish()
+        mark(3)
         torch.nn.utils.clip_grad_norm_(self.seg.parameters(), self.max_norm, norm_type=2)     # cfg:153
         self.opt.step()
+        mark(4)
         self.seg.invalidate()                                            # inference plans / graphs hold the old weights
+        if ev:
+            torch.cuda.synchronize()
+            for name, i in (("forward_loss", 0), ("backward", 1), ("allreduce_exposed", 2), ("optimizer", 3)):
+                timing[name] = timing.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
         return losses
