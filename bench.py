@@ -47,7 +47,7 @@ def workload_config(B, world):
     return {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
             "weights": "seeded random init + shipped calibration statistics (spike2former_b200/synth.py)",
             "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2",
-            "value_input": "fp32 [B,3,512,512] resident in HBM (encode_decode -> fp32 logits [B,150,512,512])",
+            "value_input": "uint8 [B,3,512,512] resident in HBM (SegDataPreProcessor + encode_decode -> fp32 logits [B,150,512,512])",
             "e2e_input": "uint8 [B,3,512,512] pinned host memory -> SegDataPreProcessor + predict -> uint8 labels -> host",
             "alg_gflop_per_image": ALG_GFLOP_PER_IMG}
 
@@ -249,8 +249,10 @@ class Harness:
     def __init__(self, seg, B, h, w, dev, dist, seed):
         self.seg, self.B, self.h, self.w, self.dev, self.dist = seg, B, h, w, dev, dist
         g = torch.Generator().manual_seed(seed)
-        self.devin = [torch.randn(B, 3, h, w, generator=g).to(dev) for _ in range(NBUF)]
         self.host = [torch.randint(0, 256, (B, 3, h, w), generator=g, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
+        # `value`: the same uint8 images (the format the reference's SegDataPreProcessor receives from the dataset) already
+        # resident in HBM; the preprocessor is folded into the tensor-core stem, so no fp32 image is ever materialised
+        self.devin = [x.to(dev) for x in self.host]
         # end-to-end: pinned uint8 host batch -> H2D (copy stream, double buffered so the copy of step i+1 overlaps the
         # forward of step i) -> fused preprocessor + forward with fused argmax (one CUDA graph) -> D2H of the uint8 label
         # map; all of it inside the timed region
@@ -312,7 +314,7 @@ def build(name, dev):
     return seg                           # so the graph's static output buffer is handed out without a 5 GB copy per step
 
 
-def training_step_bench(dev, world, rank, dist, B, precision, steps=5, warmup=2):
+def training_step_bench(dev, world, rank, dist, B, precision, steps=5, warmup=2, graph=True):
     """BASELINE.json config 5: one surrogate-gradient training step of the ADE20K model (batch 6 per GPU as in the
     reference config :181-182, 512x512 crops, synthetic labels), forward + 21 losses + backward + gradient all-reduce over
     NCCL (N > 1) + clip + AdamW, timed with CUDA events between barriers, max over ranks."""
@@ -323,7 +325,7 @@ def training_step_bench(dev, world, rank, dist, B, precision, steps=5, warmup=2)
     seg = s2f.build_segmentor(cfg)
     seg.load_state_dict(synth.synthetic_checkpoint("ade20k", cfg), strict=True)
     seg = seg.to(dev)
-    step = train.TrainStep(seg, precision=precision)
+    step = train.TrainStep(seg, precision=precision, graph=graph)
     g = torch.Generator().manual_seed(500 + rank)
     imgs = [torch.randn(B, 3, H, W, generator=g).to(dev) for _ in range(2)]
     gts = [torch.randint(0, 150, (B, 1, H // 16, W // 16), generator=g).repeat_interleave(16, 2).repeat_interleave(16, 3).to(dev)
@@ -344,7 +346,7 @@ def training_step_bench(dev, world, rank, dist, B, precision, steps=5, warmup=2)
     torch.cuda.synchronize()
     ms = s2f_dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     out = dict(workload="Spike2Former ADE20K training step (surrogate-gradient NI-LIF backward, 21 loss terms, AdamW, clip 0.01)",
-               batch_per_gpu=B, n_gpus=world, precision=precision, steps=steps, ms_per_step=ms, images_per_second=world * B / (ms / 1e3),
+               batch_per_gpu=B, n_gpus=world, precision=precision, cuda_graph_forward_backward=graph, steps=steps, ms_per_step=ms, images_per_second=world * B / (ms / 1e3),
                phases_ms={k: v / steps for k, v in timing.items()}, total_loss=float(sum(losses.values())),
                params=sum(p.numel() for p in seg.parameters()),
                allreduce_bytes_per_step=step.buckets.bytes if step.buckets is not None else 0,

@@ -159,24 +159,32 @@ class Net:
         x = self.bn(key + ".pwconv2.1", self.conv(key + ".pwconv2.0", lif(x)))
         return x.permute(0, 2, 3, 1)
 
-    @staticmethod
-    def dcnv3_core(x, offset, mask, ksz, pad, group, gch, offset_scale):
-        """dcnv3_core_pytorch (dcnv3_func.py:91-189), stride 1, dilation 1."""
+    def dcn_constants(self, hin, win, hout, wout, ksz, group, offset_scale, dev):
+        """_get_reference_points + _generate_dilation_grids (dcnv3_func.py:91-144): depend on the shape only, so they
+        are built once (on the host, as the reference does) and kept on the device -- nothing inside the forward copies
+        from host memory, which keeps the whole forward CUDA-graph capturable."""
+        key = (hin, win, hout, wout, ksz, group, offset_scale, str(dev))
+        if key not in self.pe:
+            half = (ksz - 1) // 2
+            ry = torch.linspace(half + 0.5, half + 0.5 + (hout - 1), hout, dtype=torch.float32)
+            rx = torch.linspace(half + 0.5, half + 0.5 + (wout - 1), wout, dtype=torch.float32)
+            ref_y, ref_x = torch.meshgrid(ry, rx, indexing="ij")
+            ref = torch.stack((ref_x.reshape(-1)[None] / win, ref_y.reshape(-1)[None] / hin), -1).reshape(1, hout, wout, 1, 2)
+            lin = torch.linspace(-half, -half + (ksz - 1), ksz, dtype=torch.float32)
+            gx, gy = torch.meshgrid(lin, lin, indexing="ij")
+            grid = torch.stack([gx / win, gy / hin], -1).reshape(-1, 1, 2).repeat(1, group, 1).permute(1, 0, 2)
+            grid = grid.reshape(1, 1, 1, group * ksz * ksz, 2)
+            norm = torch.tensor([win, hin]).reshape(1, 1, 1, 2).repeat(1, 1, 1, group * ksz * ksz)
+            self.pe[key] = ((ref + grid * offset_scale).to(dev), norm.to(dev))
+        return self.pe[key]
+
+    def dcnv3_core(self, x, offset, mask, ksz, pad, group, gch, offset_scale):
+        """dcnv3_core_pytorch (dcnv3_func.py:147-189), stride 1, dilation 1."""
         x = F.pad(x, [0, 0, pad, pad, pad, pad])
         n, hin, win, _ = x.shape
         _, hout, wout, _ = offset.shape
-        dev = x.device
-        half = (ksz - 1) // 2
-        ry = torch.linspace(half + 0.5, half + 0.5 + (hout - 1), hout, dtype=torch.float32, device=dev)
-        rx = torch.linspace(half + 0.5, half + 0.5 + (wout - 1), wout, dtype=torch.float32, device=dev)
-        ref_y, ref_x = torch.meshgrid(ry, rx, indexing="ij")
-        ref = torch.stack((ref_x.reshape(-1)[None] / win, ref_y.reshape(-1)[None] / hin), -1).reshape(1, hout, wout, 1, 2)
-        lin = torch.linspace(-half, -half + (ksz - 1), ksz, dtype=torch.float32, device=dev)
-        gx, gy = torch.meshgrid(lin, lin, indexing="ij")
-        grid = torch.stack([gx / win, gy / hin], -1).reshape(-1, 1, 2).repeat(1, group, 1).permute(1, 0, 2)
-        grid = grid.reshape(1, 1, 1, group * ksz * ksz, 2)
-        norm = torch.tensor([win, hin], device=dev).reshape(1, 1, 1, 2).repeat(1, 1, 1, group * ksz * ksz)
-        loc = (ref + grid * offset_scale).repeat(n, 1, 1, 1, 1).flatten(3, 4) + offset * offset_scale / norm
+        base, norm = self.dcn_constants(hin, win, hout, wout, ksz, group, offset_scale, x.device)
+        loc = base.repeat(n, 1, 1, 1, 1).flatten(3, 4) + offset * offset_scale / norm
         pts = ksz * ksz
         xin = x.view(n, hin * win, group * gch).transpose(1, 2).reshape(n * group, gch, hin, win)
         sg = (2 * loc - 1).view(n, hout * wout, group, pts, 2).transpose(1, 2).flatten(0, 1)
@@ -409,6 +417,11 @@ def losses_from_matching(all_cls, all_masks, labels_list, masks_list, match, num
 def head_losses(net, feats, gt_sem_seg, ignore_index=255):
     """mmseg MaskFormerHead.loss: forward of all 7 decoder outputs + loss_by_feat -> dict of 21 loss terms."""
     all_cls, all_masks = net.head(feats)
+    return losses_from_outputs(net, all_cls, all_masks, gt_sem_seg, ignore_index)
+
+
+def losses_from_outputs(net, all_cls, all_masks, gt_sem_seg, ignore_index=255):
+    """loss_by_feat (maskformer_head.py:367-408) on top of the mmseg label conversion."""
     inst = [seg_to_instances(g, ignore_index) for g in gt_sem_seg]
     ll, ml = [a for a, _ in inst], [b for _, b in inst]
     match, counts = batched_match(all_cls.detach(), all_masks.detach(), ll, ml)
@@ -497,17 +510,33 @@ def param_groups(seg, lr=1e-3, weight_decay=0.005):
     return [dict(params=ps, lr=lr * lm, weight_decay=weight_decay * wm) for (lm, wm), ps in groups.items()]
 
 
+class _NetModule(torch.nn.Module):
+    """The network part of the step (image -> 7 class-score / mask-logit maps) as a module over the segmentor's
+    parameters, so that torch.cuda.make_graphed_callables can capture its forward and backward passes."""
+
+    def __init__(self, seg, net):
+        super().__init__()
+        self.seg, self.net = seg, net
+
+    def forward(self, img):
+        return self.net.head(self.net.backbone(img))
+
+
 class TrainStep:
     """One optimisation step of config 5: forward, 21 losses, backward, bucketed NCCL all-reduce, clip 0.01, AdamW.
 
     precision: "fp32" (exact library arithmetic: the parity setting), "tf32" (cuDNN / cuBLAS TF32 tensor cores) or
-    "bf16" (autocast of the convolutions / matmuls; neurons, BatchNorm statistics and the loss stay fp32)."""
+    "bf16" (autocast of the convolutions / matmuls; neurons, BatchNorm statistics and the loss stay fp32).
+    graph: capture the network's forward and backward passes (~20 000 + ~30 000 small launches at batch 6, launch-bound
+    when issued one by one) into two CUDA graphs per input shape; matching and the losses stay eager (their shapes
+    depend on the labels).  With a graph the gradient buckets are launched when the backward graph has finished."""
 
-    def __init__(self, seg, lr=1e-3, weight_decay=0.005, max_norm=0.01, precision="fp32", bucket_mb=25):
+    def __init__(self, seg, lr=1e-3, weight_decay=0.005, max_norm=0.01, precision="fp32", bucket_mb=25, graph=False):
         if next(seg.parameters()).device.type != "cuda":
             raise RuntimeError("TrainStep: move the model to a CUDA device first (no CPU path)")
         self.seg, self.max_norm, self.precision = seg, max_norm, precision
         self.net = Net(seg)
+        self.graph, self._graphed = graph, {}
         self.opt = torch.optim.AdamW(param_groups(seg, lr, weight_decay), betas=(0.9, 0.999), fused=True)
         dist = torch.distributed
         self.buckets = GradBuckets(list(seg.parameters()), bucket_mb) if dist.is_available() and dist.is_initialized() \
@@ -521,11 +550,16 @@ class TrainStep:
         old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32, tf32
         try:
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.precision == "bf16"):
-                feats = self.net.backbone(img)
-                feats = [f.float() for f in feats]
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.precision == "bf16"):
-                return head_losses(self.net, feats, gt_sem_seg, self.seg.decode_head.ignore_index)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.precision == "bf16", cache_enabled=not self.graph):
+                if self.graph:
+                    key = (tuple(img.shape), img.device.index)
+                    if key not in self._graphed:
+                        self._graphed[key] = torch.cuda.make_graphed_callables(_NetModule(self.seg, self.net), (img.clone(),),
+                                                                               allow_unused_input=True)
+                    all_cls, all_masks = self._graphed[key](img)
+                else:
+                    all_cls, all_masks = self.net.head(self.net.backbone(img))
+            return losses_from_outputs(self.net, all_cls.float(), all_masks.float(), gt_sem_seg, self.seg.decode_head.ignore_index)
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
