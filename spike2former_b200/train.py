@@ -554,8 +554,14 @@ class TrainStep:
                 if self.graph:
                     key = (tuple(img.shape), img.device.index)
                     if key not in self._graphed:
+                        # capture runs the forward a few times: put the BatchNorm running statistics back afterwards
+                        # (RepConv's border value reads them, sdtv2.py:68-74, so they are part of the forward's input)
+                        saved = {k: b.clone() for k, b in self.seg.named_buffers()}
                         self._graphed[key] = torch.cuda.make_graphed_callables(_NetModule(self.seg, self.net), (img.clone(),),
                                                                                allow_unused_input=True)
+                        with torch.no_grad():
+                            for k, b in self.seg.named_buffers():
+                                b.copy_(saved[k])
                     all_cls, all_masks = self._graphed[key](img)
                 else:
                     all_cls, all_masks = self.net.head(self.net.backbone(img))
