@@ -326,11 +326,12 @@ def dec_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, mask=None, q_ld=None, k
         if not isinstance(t, torch.Tensor) or t.dtype != torch.int8 or not t.is_cuda:
             raise S2FError(f"dec_attn: {nm} must be CUDA int8 levels (no CPU path)")
     Cc = heads * d
+    mask_t = None                        # keeps the (possibly temporary) mask storage alive until the kernel is enqueued
     if mask is not None:
         if not mask.is_cuda or mask.numel() != n * heads * Nq * Nk:
             raise S2FError("dec_attn: mask must be a CUDA tensor of n*heads*Nq*Nk elements")
-        mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
-        mask = _ptr(mask.contiguous(), torch.uint8, "mask")
+        mask_t = (mask.view(torch.uint8) if mask.dtype == torch.bool else mask).contiguous()
+        mask = _ptr(mask_t, torch.uint8, "mask")
     out_ld = int(out_ld or Cc)
     out_s = torch.zeros((n, Nq, out_ld), dtype=torch.int8, device=q.device) if out_ld != Cc else \
         torch.empty((n, Nq, out_ld), dtype=torch.int8, device=q.device)
@@ -340,6 +341,8 @@ def dec_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, mask=None, q_ld=None, k
                                   _ptr(out_s), _ptr(out_f), n, Nq, Nk, heads, d, int(q_ld or Cc), int(kv_ld or Cc), out_ld,
                                   float(out_scale), float(d_max), _stream()), "s2f_dec_attn")
     _p1(e0, "linear_attn", 4.0 * n * heads * d * Nq * Nk, n * (Nq + 2 * Nk) * Cc + _nb(out_s, out_f), f"{n} x Nq{Nq} Nk{Nk} masked")
+    if mask_t is not None:
+        mask_t.record_stream(torch.cuda.current_stream())
     return out_s, out_f
 
 
