@@ -34,6 +34,28 @@ inline int check_launch(const char* what) {
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute and the SM count are PER DEVICE: a process that runs the model on a second GPU must set the
+// kernels' shared-memory attribute there too.  `once` is a per-call-site bit mask indexed by the ordinal.
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+inline bool first_use_on_this_device(std::atomic<uint64_t>& once) {
+  const uint64_t bit = 1ull << (current_device() & 63);
+  return (once.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+inline int sm_count() {
+  static std::atomic<int> cached[64];
+  const int dev = current_device();
+  int n = cached[dev & 63].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev & 63].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 // round-half-to-even of clamp(v, 0, d): torch.round(torch.clamp(v, 0, d)) -- surrogate.py:529
 __device__ __forceinline__ float spike_level(float v, float d_max) { return rintf(fminf(fmaxf(v, 0.f), d_max)); }
 

@@ -966,12 +966,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (p.stages < 2) p.stages = 2;
   size_t smem = (p.b_resident ? b_all : 0) + (size_t)p.stages * stage_bytes + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;          // never two CTAs on one SM: each allocates all 512 TMEM columns
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_count();
   // CTAs per channel tile: fill the SMs, never more than there are row tiles
   int per_n = num_sms / tiles_n;
   if (per_n < 1) per_n = 1;
@@ -981,11 +976,9 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   cudaError_t attr_err = cudaSuccess;
 #define S2F_TC_LAUNCH(P, E, W)                                                                                            \
   do {                                                                                                                  \
-    static bool attr_set = false;                                                                                       \
-    if (!attr_set) {                                                                                                    \
+    static std::atomic<uint64_t> attr_set{0};                                                                           \
+    if (first_use_on_this_device(attr_set))                                                                             \
       attr_err = cudaFuncSetAttribute(gemm_i8_tc_kernel<P, E, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-      attr_set = attr_err == cudaSuccess;                                                                               \
-    }                                                                                                                   \
     if (attr_err == cudaSuccess) gemm_i8_tc_kernel<P, E, W><<<grid, tc_threads(W), smem, (cudaStream_t)stream>>>(map_a, map_b, map_up, p); \
   } while (0)
 #define S2F_TC_EPI(P)                                               \

@@ -319,14 +319,13 @@ extern "C" int s2f_stem_u8(const uint8_t* img, int chw, const int8_t* w_packed, 
   const int64_t tiles = (int64_t)n * p.tiles_w * p.tiles_h;
   S2F_REQUIRE(tiles < (1ll << 31), "stem_u8: too many tiles");
   p.tiles = (int)tiles;
-  p.ctas = (int)(tiles < 148 ? tiles : 148);
+  p.ctas = (int)(tiles < sm_count() ? tiles : sm_count());
   p.d_max = d_max > 0.f ? d_max : 8.f;
   const size_t smem = 1024 + stem::B_BYTES + 2 * stem::A_STAGE + 128 + 64 * 4 + (size_t)256 * Cout * 4 + 64 + 2 * stem::PATCH_BYTES;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};
+  if (first_use_on_this_device(attr)) {
     cudaError_t e = cudaFuncSetAttribute(stem::stem_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "stem_u8: smem attribute: %s", cudaGetErrorString(e));
-    attr = true;
   }
   // one CTA per SM: each allocates all 512 TMEM columns
   stem::stem_u8_kernel<<<p.ctas, stem::THREADS, smem < 120 * 1024 ? 120 * 1024 : smem, (cudaStream_t)stream>>>(p);

@@ -626,11 +626,10 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
   const int Np = (K + 15) / 16 * 16;
   const size_t prep_sm = sizeof(float) * (size_t)Q * K;
   S2F_REQUIRE(prep_sm <= 160 * 1024, "semantic_tail_tc: Q*K too large");
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};
+  if (first_use_on_this_device(attr)) {
     cudaFuncSetAttribute(tail_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr = true;
   }
   tail_prep_kernel<<<n, 256, prep_sm, st>>>(cls, reinterpret_cast<uint8_t*>(ws), Q, K, Np);
   int rc = check_launch("tail_prep_kernel");
@@ -657,12 +656,11 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
     }
     q.ctas_per_img = per_img;
     { const char* dbg = getenv("S2F_TAIL_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
-    static bool attr2 = false;
-    if (!attr2) {
+    static std::atomic<uint64_t> attr2{0};
+    if (first_use_on_this_device(attr2)) {
       cudaError_t e = cudaFuncSetAttribute(tail_x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_x2_kernel<512 * 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return fail(S2F_ERR_CUDA, "semantic_tail_tc: smem attribute: %s", cudaGetErrorString(e));
-      attr2 = true;
     }
     if ((int64_t)H * W == 512 * 512) tail_x2_kernel<512 * 512><<<dim3(per_img, n), T2_THREADS, smem2, st>>>(q);
     else tail_x2_kernel<0><<<dim3(per_img, n), T2_THREADS, smem2, st>>>(q);

@@ -1,0 +1,58 @@
+"""GPU tool for ncu: one forward of the benchmarked path inside a cudaProfilerStart/Stop bracket.
+
+    ncu --profile-from-start off ... python tools/profile_forward.py [ade20k|cityscapes] [batch] [logits|labels] [micro]
+
+The model takes the same uint8 batch bench.py feeds it; `micro` profiles the BASELINE config 2 kernels instead
+(NI-LIF D=8 / D=4 / folded BN, spike GEMM fc1 512->2048, SDSA C=512 d=64)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import spike2former_b200 as s2f  # noqa: E402
+from spike2former_b200 import engine, ops, synth  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "ade20k"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+labels = (sys.argv[3] if len(sys.argv) > 3 else "logits") == "labels"
+micro = len(sys.argv) > 4 and sys.argv[4] == "micro"
+g = torch.Generator().manual_seed(0)
+if micro:
+    x = (torch.rand(64, 1024, 512, generator=g) * 12 - 2).cuda()
+    lv = torch.empty(x.shape, dtype=torch.int8, device="cuda")
+    sc, sh = (torch.rand(512, generator=g) + 0.5).cuda(), torch.randn(512, generator=g).cuda()
+    a = torch.randint(0, 9, (64, 32, 32, 512), generator=g, dtype=torch.int8).cuda()
+    w = torch.randn(2048, 512, generator=g) / 512 ** 0.5
+    packed, rowscale = ops.pack_weights_i8(w, 1, 512, 3)
+    packed, gsc, gsh = packed.cuda(), (rowscale / 8).cuda(), torch.zeros(2048).cuda()
+    q, k, v = (torch.randint(0, 3, (64, 1024, 512), generator=g, dtype=torch.int8).cuda() for _ in range(3))
+
+    def run():
+        ops.nilif(x, out=lv)
+        ops.nilif(x, out=lv, d_max=4.0, norm=4.0)
+        ops.nilif(x, scale=sc, shift=sh, out=lv)
+        ops.gemm_tc(a, packed, n=64, H=32, W=32, Cin=512, Cout=2048, scale=gsc, shift=gsh, pieces=3, want_spike=True)
+        ops.linear_attn(q, k, v, n=64, Nq=1024, Nk=1024, heads=8, d=64, out_scale=64 ** -0.5 / 512)
+        ops.peak_mma("i8", 1024)
+else:
+    cfg = getattr(s2f.configs, name)()
+    seg = s2f.build_segmentor(cfg)
+    seg.load_state_dict(synth.synthetic_checkpoint(name, cfg), strict=True)
+    seg = seg.cuda()
+    H, W = (512, 512) if name == "ade20k" else (1024, 2048)
+    u8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).cuda()
+
+    def run():
+        with torch.no_grad():
+            engine.segmentor_logits(seg, u8, labels=labels)
+
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+run()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("launches through the library so far:", ops.launch_count())

@@ -16,7 +16,7 @@ cfg = s2f.configs.ade20k()
 seg = s2f.build_segmentor(cfg)
 seg.load_state_dict(synth.synthetic_checkpoint("ade20k", cfg), strict=True)
 seg = seg.cuda()
-x = torch.randn(B, 3, 512, 512, device="cuda")
+x = torch.randint(0, 256, (B, 3, 512, 512), dtype=torch.uint8, device="cuda")          # the uint8 batch bench.py feeds
 with torch.no_grad():
     for _ in range(2):
         engine.segmentor_logits(seg, x)
