@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 7 */
+S2F_API int s2f_abi_version(void);   /* currently 8 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -151,6 +151,21 @@ S2F_API int s2f_pack_rows_i8_device(const float* w, int ld, int n_img, int rows_
 S2F_API int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const float* w, const float* scale, const float* shift,
                const float* pad_value, float* out_f32, int8_t* out_spike, int n, int H, int W, int C, int k,
                int no_pad, float d_max, void* stream);
+
+/* SepConv tail in one launch (sdtv2.py:176-179: `x = self.dwconv(x); x = self.bn2(self.pwconv2(x))`; the stencil output
+ * is real-valued, so the 1x1 is a real x real product): depthwise k x k (pad (k-1)/2) over int8 levels a [n,H,W,Cm]
+ * (value = level * a_scale), tap-major fp32 weights w_dw [k*k, Cm]; then
+ *   y = (W_pw x2) * scale[co] + shift[co] + residual ; out_f32 = y ; out_spike = rint(clamp(y, 0, d_max)).
+ * The stencil runs on CUDA cores in the reference tap order (bit-identical to s2f_dwconv), its output stays in shared
+ * memory as fp16 hi + lo (scaled by the power of two a_pre; choose it so that |x2| * a_pre < 32768) and the 1x1 runs on
+ * tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).  w_pw_packed: the K-major SWIZZLE_128B fp16
+ * hi / lo image of W_pw [Cout, Cm] with one power-of-two scale per row (spike2former_b200/ops.py::pack_pw_f16,
+ * s2f_sepconv_bpack_bytes bytes); `scale` must contain rowscale[co] / a_pre besides the folded BatchNorm scale.
+ * Cm % 64 == 0, 16 <= Cout <= 128, Cout % 4 == 0. */
+S2F_API int64_t s2f_sepconv_bpack_bytes(int Cm, int Cout);
+S2F_API int s2f_sepconv_dwpw(const int8_t* a, float a_scale, const float* w_dw, const void* w_pw_packed, float a_pre,
+                     const float* scale, const float* shift, const float* residual, float* out_f32, int8_t* out_spike,
+                     int n, int H, int W, int Cm, int Cout, int k, float d_max, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Spike-driven (linear) attention.  q,k,v: int8 levels [n, Ntok, heads*d] (value = level/norm).

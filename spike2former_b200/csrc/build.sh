@@ -11,7 +11,7 @@ objs=()
 mkdir -p "$bdir"
 for src in "$here"/*.cu; do
   obj="$bdir/$(basename "${src%.cu}").o"
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$here/common.cuh" -nt "$obj" || "$here/conv_direct.cuh" -nt "$obj" || "$here/conv_tf32.cuh" -nt "$obj" || "$here/../../include/s2f.h" -nt "$obj" ]]; then
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$here/common.cuh" -nt "$obj" || "$here/conv_direct.cuh" -nt "$obj" || "$here/conv_tf32.cuh" -nt "$obj" || "$here/dw_tile.cuh" -nt "$obj" || "$here/../../include/s2f.h" -nt "$obj" ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" 2> "$obj.log" || { cat "$obj.log"; exit 1; }
   fi
   objs+=("$obj")

@@ -1,6 +1,9 @@
 // Channels-last spatial kernels: depthwise stencil, DCNv3 bilinear gather, FPN upsample-add-LIF.
 // All HBM/L2-bound; threads run over channels fastest so every warp access is a coalesced row.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "dw_tile.cuh"
 
 // kernel sizes >= S2F_DW_ROLL_MIN keep the loop over kernel rows rolled: the fully unrolled 7x7 body (~60 KB of SASS)
 // thrashes the instruction cache (stall_no_instruction was the top stall; 0.62 -> 0.49 ms at 256^2 x 64 ch, batch 32)
@@ -27,10 +30,6 @@ namespace s2f {
 // contiguous row segment.  Weights are tap-major [k*k, C].  fp32 accumulation in the reference's tap order (kh, kw).
 // One input pixel x 4 channels as raw bits (int8: one 32-bit word; fp32: a float4), loaded unconditionally from a clamped
 // address so that the compiler can issue all loads of a row back to back.
-struct Raw8 { uint32_t w; };
-struct Raw32 { float4 v; };
-__device__ __forceinline__ Raw8 load_raw(const int8_t* p) { return Raw8{__ldg(reinterpret_cast<const uint32_t*>(p))}; }
-__device__ __forceinline__ Raw32 load_raw(const float* p) { return Raw32{__ldg(reinterpret_cast<const float4*>(p))}; }
 // int8 levels enter the FFMAs as fp32 *denormals*: the isolated byte b, reinterpreted as a float, is b * 2^-149, and
 // FFMA takes denormal operands at full rate (no -ftz in this build).  With the weights pre-multiplied by 2^DW_WEXP every
 // product and partial sum is the reference's value times 2^(DW_WEXP-149) -- a power of two, so each rounding is the
@@ -44,15 +43,9 @@ __device__ __forceinline__ void unpack4(Raw8 r, bool ok, float& x0, float& x1, f
   x2 = __uint_as_float(__byte_perm(raw, 0u, 0x4442));
   x3 = __uint_as_float(__byte_perm(raw, 0u, 0x4443));
 }
-template <typename AT> struct DwScale;
-template <> struct DwScale<int8_t> { static constexpr float w_pre = 0x1p100f, post = 0x1p49f; };   // 2^DW_WEXP, 2^(149-DW_WEXP)
-template <> struct DwScale<float> { static constexpr float w_pre = 1.f, post = 1.f; };
 __device__ __forceinline__ void unpack4(Raw32 r, bool ok, float& x0, float& x1, float& x2, float& x3) {
   x0 = ok ? r.v.x : 0.f; x1 = ok ? r.v.y : 0.f; x2 = ok ? r.v.z : 0.f; x3 = ok ? r.v.w : 0.f;
 }
-template <typename AT> struct RawOf;
-template <> struct RawOf<int8_t> { using type = Raw8; };
-template <> struct RawOf<float> { using type = Raw32; };
 
 template <typename AT, int KS, int TW, int CT>      // CT: compile-time channel count (0 = use the runtime C)
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a, float a_scale,
@@ -162,6 +155,67 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const AT* __restrict__ a
       if (out_spike) {
         const uint32_t pk = pack_levels4(y[0], y[1], y[2], y[3], d_max);
         *reinterpret_cast<uint32_t*>(out_spike + o) = pk;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise k x k, register-tiled over TWO output rows with the kernel in shared memory (the production stencil; the
+// arithmetic core is dw_tile.cuh).  A block of 128 threads = 128 consecutive (column strip, channel quad) pairs, walking
+// down a chunk of RH output rows so that six of the eight input rows of a k = 7 step are L1 hits.  Same bits as
+// dwconv_kernel (tests/test_kernels_gpu.py).
+constexpr int DWT_THREADS = 128;
+
+template <typename AT, int KS, int CT>
+__global__ void __launch_bounds__(DWT_THREADS, 3) dwconv_tile_kernel(const AT* __restrict__ a, float a_scale,
+                                                                  const float* __restrict__ w_tap,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift,
+                                                                  float* __restrict__ out_f32, int8_t* __restrict__ out_spike,
+                                                                  int n, int H, int W, int C_rt, int Ho, int Wo, int pad,
+                                                                  float d_max, int RH) {
+  constexpr int TW = DW_TW;
+  extern __shared__ float4 dw_wsm[];                 // [KS*KS][C/4], pre-scaled
+  const int C = CT ? CT : C_rt;
+  const int c4n = C >> 2;
+  dw_stage_weights<AT>(dw_wsm, w_tap, KS * KS * c4n, threadIdx.x, DWT_THREADS);
+  __syncthreads();
+  const int strips = (Wo + TW - 1) / TW;
+  const int row_tiles = strips * c4n;                // (strip, channel quad) pairs of one output row pair
+  const int groups = (row_tiles + DWT_THREADS - 1) / DWT_THREADS;
+  const int hchunks = (Ho + RH - 1) / RH;
+  const int tasks = n * hchunks * groups;
+  const float asc = a_scale * DwScale<AT>::post;     // powers of two: exact
+  for (int task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int flat = (task % groups) * DWT_THREADS + (int)threadIdx.x;
+    if (flat >= row_tiles) continue;
+    const int hc = (task / groups) % hchunks, img = task / (groups * hchunks);
+    const int cq = flat % c4n, wo0 = (flat / c4n) * TW, c = cq * 4;
+    const AT* base = a + (int64_t)img * H * W * C + c;
+    float4 sc = make_float4(asc, asc, asc, asc), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c));
+      sc = make_float4(s4.x * asc, s4.y * asc, s4.z * asc, s4.w * asc);
+      sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+    }
+    const int h_end = min(Ho, (hc + 1) * RH);
+    for (int ho0 = hc * RH; ho0 < h_end; ho0 += 2) {
+      float2 acc[2][TW][2];
+      dw_tile_8x2<AT, KS, CT>(base, H, W, C, ho0, wo0, pad, (uint32_t)__cvta_generic_to_shared(dw_wsm + cq), (uint32_t)c4n * 16u, acc);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (ho0 + t >= Ho) break;
+        const int64_t o0 = (((int64_t)img * Ho + ho0 + t) * Wo + wo0) * C + c;
+#pragma unroll
+        for (int p = 0; p < TW; ++p) {
+          if (wo0 + p >= Wo) break;
+          const float y0 = fmaf(acc[t][p][0].x, sc.x, sh.x), y1 = fmaf(acc[t][p][0].y, sc.y, sh.y);
+          const float y2 = fmaf(acc[t][p][1].x, sc.z, sh.z), y3 = fmaf(acc[t][p][1].y, sc.w, sh.w);
+          const int64_t o = o0 + (int64_t)p * C;
+          if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y0, y1, y2, y3);
+          if (out_spike) *reinterpret_cast<uint32_t*>(out_spike + o) = pack_levels4(y0, y1, y2, y3, d_max);
+        }
       }
     }
   }
@@ -340,12 +394,49 @@ extern "C" int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const fl
   const int pad = no_pad ? 0 : (k - 1) / 2;
   const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
   S2F_REQUIRE(Ho > 0 && Wo > 0, "dwconv: empty output");
-  constexpr int TW = 8;
-  const int64_t total = (int64_t)n * Ho * ((Wo + TW - 1) / TW) * (C / 4);
-  S2F_REQUIRE(total < (1ll << 31) && (int64_t)W * C < (1ll << 31), "dwconv: problem too large for 32-bit task indices");
-  const int g = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   const float asc = a_is_spike ? a_scale : 1.f;
+  S2F_REQUIRE((int64_t)W * C < (1ll << 31), "dwconv: row too large for 32-bit offsets");
+  // Production path: two-row register tiles with the kernel in shared memory.  3 resident blocks of 128 threads per SM.
+  const char* lg = getenv("S2F_DW_LEGACY");            // A/B switch for tools/bench_kernels.py (read per call)
+  const bool legacy = lg && lg[0] == '1';
+  const size_t wsm = (size_t)k * k * C * sizeof(float);
+  const int64_t row_tiles = (int64_t)((Wo + 7) / 8) * (C / 4), groups = ceil_div(row_tiles, DWT_THREADS);
+  if (!legacy && wsm <= 64 * 1024 && (int64_t)n * Ho * groups < (1ll << 30)) {
+    const int resident = sm_count() * 3;
+    int RH = 32;                                       // rows a block walks down: as long as >= 8 waves of tasks remain
+    while (RH > 2 && (int64_t)n * ceil_div(Ho, RH) * groups < 8ll * resident) RH >>= 1;
+    const int64_t tasks = (int64_t)n * ceil_div(Ho, RH) * groups;
+    const int g = (int)(tasks < resident ? tasks : resident);
+#define S2F_DWT_C(AT, KS, CT)                                                                                    \
+  do {                                                                                                           \
+    static std::atomic<uint64_t> once{0};                                                                        \
+    if (first_use_on_this_device(once))                                                                          \
+      cudaFuncSetAttribute(dwconv_tile_kernel<AT, KS, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+    dwconv_tile_kernel<AT, KS, CT><<<g, DWT_THREADS, wsm, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, \
+                                                                 out_f32, out_spike, n, H, W, C, Ho, Wo, pad, d_max, RH); \
+  } while (0)
+#define S2F_DWT(AT, KS)                                                       \
+  do {                                                                        \
+    if (C == 64) S2F_DWT_C(AT, KS, 64);                                       \
+    else if (C == 128) S2F_DWT_C(AT, KS, 128);                                \
+    else if (C == 256) S2F_DWT_C(AT, KS, 256);                                \
+    else if (C == 512) S2F_DWT_C(AT, KS, 512);                                \
+    else S2F_DWT_C(AT, KS, 0);                                                \
+  } while (0)
+    if (a_is_spike) {
+      if (k == 3) S2F_DWT(int8_t, 3); else if (k == 5) S2F_DWT(int8_t, 5); else S2F_DWT(int8_t, 7);
+    } else {
+      if (k == 3) S2F_DWT(float, 3); else if (k == 5) S2F_DWT(float, 5); else S2F_DWT(float, 7);
+    }
+#undef S2F_DWT_C
+#undef S2F_DWT
+    return check_launch("dwconv_tile_kernel");
+  }
+  constexpr int TW = 8;
+  const int64_t total = (int64_t)n * Ho * ((Wo + TW - 1) / TW) * (C / 4);
+  S2F_REQUIRE(total < (1ll << 31), "dwconv: problem too large for 32-bit task indices");
+  const int g = grid_for(total, 256);
 #define S2F_DW_C(AT, KS, CT)                                                                                               \
   dwconv_kernel<AT, KS, TW, CT><<<g, 256, 0, st>>>(reinterpret_cast<const AT*>(a), asc, w, scale, shift, out_f32, out_spike, \
                                                    n, H, W, C, Ho, Wo, pad, d_max)

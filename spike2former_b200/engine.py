@@ -25,6 +25,7 @@ INV = 1.0 / NORM
 USE_TC = True            # spike-operand layers run on the tcgen05 kernel (the CUDA-core kernel covers the rest)
 import os as _os
 TC_PIECES = int(_os.environ.get("S2F_TC_PIECES", "3"))   # int8 digit planes per weight: 3 = 21-bit fixed point (default), 2 = 14-bit fast mode
+FUSE_SEPCONV = _os.environ.get("S2F_FUSE_SEPCONV", "1") != "0"   # SepConv dw7x7 + pwconv2 as one launch (csrc/sepconv_tc.cu)
 TC_MIN_ROWS = 1          # every eligible layer runs on the tensor-core kernel whatever the batch: its integer accumulation
                          # is order-independent, so an image's result never depends on how many images share the launch
 
@@ -80,6 +81,35 @@ class Dw:
     def __call__(self, a, n, H, W, f32=False, spike=False):
         return ops.dwconv(a, self.w, n=n, H=H, W=W, C_=self.c, k=self.k, scale=self.scale, shift=self.shift,
                           want_f32=f32, want_spike=spike)
+
+
+class SepDwPw:
+    """SepConv's `dwconv` + `pwconv2` + `bn2` (sdtv2.py:176-179) as one launch (csrc/sepconv_tc.cu): the real-valued
+    stencil output stays in shared memory as fp16 hi + lo and the 1x1 runs on tcgen05 kind::f16."""
+
+    def __init__(self, sd, dw_key, pw_key, bn_key, device):
+        wd = sd[dw_key + ".weight"]
+        wp = fold.w_khwc(sd[pw_key + ".weight"])
+        self.k, self.cm, self.cout = int(wd.shape[-1]), int(wd.shape[0]), int(wp.shape[0])
+        s, t = fold.conv_bn(sd, pw_key, bn_key)
+        packed, rowscale = ops.pack_pw_f16(wp)
+        # |stencil output| <= sum |w_dw| (levels / 8 <= 1): the power of two that keeps the fp16 hi part below 2^15
+        bound = float(wd.double().abs().sum(dim=(1, 2, 3)).max().clamp_min(1e-30))
+        self.a_pre = float(2.0 ** max(-8, min(8, math.floor(math.log2(32000.0 / bound)))))
+        self.w_dw = fold.f32(fold.dw_taps(wd), device)
+        self.packed = packed.to(device)
+        self.scale = fold.f32(s * rowscale.double() / self.a_pre, device)
+        self.shift = fold.f32(t, device)
+
+    @staticmethod
+    def eligible(sd, dw_key, pw_key):
+        cm, cout = int(sd[dw_key + ".weight"].shape[0]), int(sd[pw_key + ".weight"].shape[0])
+        return USE_TC and FUSE_SEPCONV and cm % 64 == 0 and 16 <= cout <= 128 and cout % 4 == 0 and sd.get(dw_key + ".bias") is None
+
+    def __call__(self, a, n, H, W, residual=None, f32=True, spike=True):
+        return ops.sepconv_dwpw(a, self.w_dw, self.packed, n=n, H=H, W=W, Cm=self.cm, Cout=self.cout, k=self.k,
+                                scale=self.scale, shift=self.shift, a_pre=self.a_pre, residual=residual,
+                                want_f32=f32, want_spike=spike)
 
 
 class StemU8:
@@ -215,6 +245,8 @@ class BackbonePlan:
             L[name + ".pw1"] = _conv_gemm(sd, name + ".Conv.pwconv1", name + ".Conv.bn1", dev)
             L[name + ".dw"] = _dw(sd, name + ".Conv.dwconv", None, dev)
             L[name + ".pw2"] = _conv_gemm(sd, name + ".Conv.pwconv2", name + ".Conv.bn2", dev)
+            if SepDwPw.eligible(sd, name + ".Conv.dwconv", name + ".Conv.pwconv2"):
+                L[name + ".dwpw"] = SepDwPw(sd, name + ".Conv.dwconv", name + ".Conv.pwconv2", name + ".Conv.bn2", dev)
             L[name + ".conv1"] = _conv_gemm(sd, name + ".conv1", name + ".bn1", dev, 3, 1, 1)
             L[name + ".conv2"] = _conv_gemm(sd, name + ".conv2", name + ".bn2", dev, 3, 1, 1)
         # every stage width is kept at a multiple of 16 channels in HBM (stage 4: 360 -> 368, zero padded)
@@ -406,8 +438,11 @@ def _conv_block(L, name, s, sp, n, H, W, pr):
     sp = pr.spike(f"{name}.Conv.spike1", sp)
     _, a = L[name + ".pw1"](sp, n, H, W, spike=True, f32=False)
     a = pr.spike(f"{name}.Conv.spike2", a)
-    d, _ = L[name + ".dw"](a, n, H, W, f32=True)
-    s2, sp2 = L[name + ".pw2"](d, n, H, W, residual=s, f32=True, spike=True)
+    if name + ".dwpw" in L and a.dtype == torch.int8:
+        s2, sp2 = L[name + ".dwpw"](a, n, H, W, residual=s, f32=True, spike=True)
+    else:
+        d, _ = L[name + ".dw"](a, n, H, W, f32=True)
+        s2, sp2 = L[name + ".pw2"](d, n, H, W, residual=s, f32=True, spike=True)
     s2 = pr.real(f"{name}.spike1", s2)
     sp2 = pr.spike(f"{name}.spike1", sp2)
     _, a = L[name + ".conv1"](sp2, n, H, W, spike=True)

@@ -297,6 +297,55 @@ def dwconv(a, w_tap, *, n, H, W, C_, k, scale=None, shift=None, a_scale=1.0 / NO
     return out_f, out_s
 
 
+def pack_pw_f16(w2d: torch.Tensor):
+    """fp32 [Cout, Cm] 1x1 weights -> (uint8 image, rowscale) for s2f_sepconv_dwpw: every row is scaled by the power of
+    two that brings its largest magnitude into [1024, 2048) and split into fp16 hi + lo (22 significant bits of the row
+    maximum, like the 21-bit digit planes of the spike GEMM); image = [hi | lo][Cm / 64][Np rows][64 k] in the K-major
+    SWIZZLE_128B order of tl_off (csrc/tail_tc.cu).  True weight = (hi + lo) * rowscale."""
+    w = w2d.detach().double().cpu()
+    cout, cm = w.shape
+    if cm % 64:
+        raise S2FError("pack_pw_f16: Cm must be a multiple of 64")
+    npad = (cout + 15) // 16 * 16
+    amax = w.abs().amax(dim=1).clamp_min(1e-30)
+    e = torch.floor(torch.log2(amax))                       # amax in [2^e, 2^(e+1))
+    rowscale = torch.pow(torch.tensor(2.0, dtype=torch.float64), e - 10)
+    ws = w / rowscale[:, None]
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.double()).to(torch.float16)
+    img = torch.zeros(2, cm // 64, npad, 64, dtype=torch.float16)
+    r = torch.arange(cout)
+    for plane, src in enumerate((hi, lo)):
+        blocks = src.reshape(cout, cm // 64, 8, 8)           # [row, 128-byte atom, 16-byte chunk, element]
+        for chunk in range(8):
+            idx = ((chunk ^ (r & 7))[:, None] * 8 + torch.arange(8)[None, :])   # swizzle: chunk ^ (row % 8)
+            for a in range(cm // 64):
+                img[plane, a].index_put_((r[:, None].expand(-1, 8), idx), blocks[:, a, chunk, :])
+    return img.view(torch.uint8).reshape(-1).contiguous(), rowscale.to(torch.float32)
+
+
+def sepconv_dwpw(a, w_dw_tap, w_pw_packed, *, n, H, W, Cm, Cout, k, scale, shift, a_pre=16.0, residual=None,
+                 a_scale=1.0 / NORM, want_f32=True, want_spike=True, d_max=D_MAX, alg_macs=None):
+    """SepConv tail (sdtv2.py:176-179) in one launch: depthwise k x k over int8 levels, then pwconv2 + BN (+ residual).
+    `scale` must already hold rowscale / a_pre (see pack_pw_f16)."""
+    if a.dtype != torch.int8:
+        raise S2FError("sepconv_dwpw: a must be int8 levels")
+    out_f = torch.empty((n, H, W, Cout), dtype=torch.float32, device=a.device) if want_f32 else None
+    out_s = torch.empty((n, H, W, Cout), dtype=torch.int8, device=a.device) if want_spike else None
+    need = int(_lib.lib().s2f_sepconv_bpack_bytes(Cm, Cout))
+    if w_pw_packed.numel() * w_pw_packed.element_size() != need:
+        raise S2FError(f"sepconv_dwpw: packed weights hold {w_pw_packed.numel()} bytes, expected {need}")
+    e0 = _p0()
+    check(_lib.lib().s2f_sepconv_dwpw(_ptr(a, torch.int8, "a"), float(a_scale), _ptr(w_dw_tap, torch.float32, "w_dw"),
+                                      _ptr(w_pw_packed, torch.uint8, "w_pw_packed"), float(a_pre),
+                                      _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                      _ptr(residual, torch.float32, "residual"), _ptr(out_f), _ptr(out_s),
+                                      n, H, W, Cm, Cout, k, float(d_max), _stream()), "s2f_sepconv_dwpw")
+    macs = Cm * k * k + (Cm * Cout if alg_macs is None else alg_macs)
+    _p1(e0, "sepconv_dwpw", 2.0 * n * H * W * macs, _nb(a, residual, out_f, out_s), f"{n}x{H}x{W} dw{k} {Cm} -> pw {Cout}")
+    return out_f, out_s
+
+
 # ------------------------------------------------------------------------------------------ attention / DCN / tail
 def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=None, out_ld=None, want_f32=False,
                 d_max=D_MAX):

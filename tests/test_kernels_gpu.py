@@ -479,3 +479,40 @@ def test_semantic_tail_general_scale_falls_back_to_serial_kernel():
 def test_cpu_tensors_are_rejected():
     with pytest.raises(RuntimeError):
         ops.nilif(torch.zeros(16))
+
+
+@pytest.mark.parametrize("k,Cm,Cout,H,W,n", [(7, 64, 32, 40, 48, 2), (7, 128, 64, 19, 23, 2), (7, 256, 128, 16, 32, 3),
+                                             (3, 64, 16, 9, 17, 1)])
+def test_sepconv_dwpw_fused_vs_float64_and_two_kernel_path(k, Cm, Cout, H, W, n):
+    """SepConv tail (sdtv2.py:176-179) in one launch: depthwise stencil (reference tap order) + pwconv2 on
+    tcgen05 kind::f16 with fp16 hi/lo operands.  Against float64 and against s2f_dwconv + the fp32 1x1 kernel."""
+    g = gen(31)
+    a = _levels((n, H, W, Cm), g)
+    w_dw = torch.randn(Cm, 1, k, k, generator=g) / k
+    w_pw = torch.randn(Cout, Cm, generator=g) / Cm ** 0.5
+    w_pw[0, :] *= 1e-3                                            # a tiny row and a heavy-tailed row
+    w_pw[1, 3] = 20.0
+    sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    res = torch.randn(n, H, W, Cout, generator=g)
+    x2 = F.conv2d((a.double() / 8).permute(0, 3, 1, 2), w_dw.double(), padding=(k - 1) // 2, groups=Cm)
+    ref = torch.einsum("nchw,oc->nhwo", x2, w_pw.double()) * sc.double() + sh.double() + res.double()
+    w_tap = w_dw.reshape(Cm, k * k).t().contiguous().cuda()
+    packed, rowscale = ops.pack_pw_f16(w_pw)
+    a_pre = 16.0
+    scale = (sc.double() * rowscale.double() / a_pre).float().cuda()
+    of, os_ = ops.sepconv_dwpw(a.cuda(), w_tap, packed.cuda(), n=n, H=H, W=W, Cm=Cm, Cout=Cout, k=k, scale=scale,
+                               shift=sh.cuda(), a_pre=a_pre, residual=res.cuda(), want_f32=True, want_spike=True)
+    tol = 2e-5 * max(1.0, ref.abs().max().item())
+    err = (of.cpu().double() - ref).abs().max().item()
+    assert err < tol, (err, tol)
+    # levels: equal to the oracle's except where its pre-activation is within the tolerance of a rounding boundary
+    lv_ref = torch.round(torch.clamp(ref, 0, 8))
+    bad = os_.cpu().double() != lv_ref
+    frac = (torch.clamp(ref, 0, 8) - torch.floor(torch.clamp(ref, 0, 8)) - 0.5).abs()
+    assert bool((frac[bad] < 1e-4 * ref.abs().clamp_min(1.0)[bad]).all()), int(bad.sum())
+    assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+    # the two-kernel path it replaces
+    d, _ = ops.dwconv(a.cuda(), w_tap, n=n, H=H, W=W, C_=Cm, k=k, want_f32=True)
+    o2, _ = ops.conv_simt(d, ops.pad_rows4(w_pw.cuda()), n=n, H=H, W=W, Cin=Cm, Cout=Cout, scale=sc.cuda(), shift=sh.cuda(),
+                          residual=res.cuda(), want_f32=True, want_spike=True)
+    assert (of - o2).abs().max().item() < tol

@@ -112,6 +112,72 @@ def bench_nilif(out):
             print(f"{line['case']:50s} {t * 1e6:9.1f} us  {nbytes / t / 1e9:7.0f} GB/s (algorithmic 5 B/neuron-step)")
 
 
+DW_CASES = [
+    # name, n, H, W, C, k, f32 out, spike out
+    ("SepConv dw7 @256^2 x64", 32, 256, 256, 64, 7, True, False),
+    ("SepConv dw7 @128^2 x128", 32, 128, 128, 128, 7, True, False),
+    ("SepConv dw7 @64^2 x256", 32, 64, 64, 256, 7, True, False),
+    ("FPN dw3 @256^2 x256", 32, 256, 256, 256, 3, False, True),
+    ("FPN dw3 @128^2 x256 f32", 32, 128, 128, 256, 3, True, False),
+    ("DCN dw5 @32^2 x512", 32, 32, 32, 512, 5, False, True),
+    ("DCN dw5 @32^2 x256", 32, 32, 32, 256, 5, False, True),
+    ("Conv dw3 @32^2 x512", 32, 32, 32, 512, 3, False, True),
+]
+
+
+def bench_dwconv(out):
+    """Depthwise stencil: the two-row register-tiled kernel against the one-row kernel it replaced (S2F_DW_LEGACY=1)."""
+    g = torch.Generator().manual_seed(0)
+    for name, n, H, W, C, k, f32, spike in DW_CASES:
+        a = torch.randint(0, 9, (n, H, W, C), generator=g, dtype=torch.int8).cuda()
+        w = (torch.randn(k * k, C, generator=g) / k).cuda()
+        sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+
+        def run():
+            return ops.dwconv(a, w, n=n, H=H, W=W, C_=C, k=k, scale=sc, shift=sh, want_f32=f32, want_spike=spike)
+
+        res = {}
+        for mode in ("0", "1"):
+            os.environ["S2F_DW_LEGACY"] = mode
+            res[mode] = (timed(run), run())
+        os.environ["S2F_DW_LEGACY"] = "0"
+        same = all(torch.equal(x, y) for x, y in zip(res["0"][1], res["1"][1]) if x is not None)
+        t = res["0"][0]
+        nbytes = a.numel() * (1 + 4 * f32 + spike)
+        fma = 2.0 * a.numel() * k * k
+        line = dict(kernel="dwconv", case=name, us=t * 1e6, legacy_us=res["1"][0] * 1e6, gbs=nbytes / t / 1e9,
+                    tflops=fma / t / 1e12, bitwise_equal_to_legacy=same)
+        out.append(line)
+        print(f"{name:34s} {t * 1e6:8.1f} us (legacy {res['1'][0] * 1e6:8.1f})  {nbytes / t / 1e9:6.0f} GB/s  "
+              f"{fma / t / 1e12:5.1f} TFLOP/s fp32  bitwise==legacy {same}")
+
+
+def bench_sepconv(out):
+    """Fused SepConv tail (dw7x7 + pwconv2 + BN + residual + LIF) against the two launches it replaces."""
+    g = torch.Generator().manual_seed(0)
+    for name, n, H, W, Cm, Cout in [("SepConv @256^2 64->32", 32, 256, 256, 64, 32), ("SepConv @128^2 128->64", 32, 128, 128, 128, 64),
+                                    ("SepConv @64^2 256->128", 32, 64, 64, 256, 128)]:
+        a = torch.randint(0, 9, (n, H, W, Cm), generator=g, dtype=torch.int8).cuda()
+        wd = (torch.randn(49, Cm, generator=g) / 7).cuda()
+        wp = torch.randn(Cout, Cm, generator=g) / Cm ** 0.5
+        packed, rowscale = ops.pack_pw_f16(wp)
+        packed = packed.cuda()
+        sc, sh = (torch.rand(Cout, generator=g) + 0.5), torch.randn(Cout, generator=g).cuda()
+        scale = (sc.double() * rowscale.double() / 16.0).float().cuda()
+        res = torch.randn(n, H, W, Cout, generator=g).cuda()
+
+        def run():
+            return ops.sepconv_dwpw(a, wd, packed, n=n, H=H, W=W, Cm=Cm, Cout=Cout, k=7, scale=scale, shift=sh, a_pre=16.0,
+                                    residual=res, want_f32=True, want_spike=True)
+
+        t = timed(run)
+        nbytes = a.numel() + res.numel() * 9
+        fl = 2.0 * n * H * W * (Cm * 49 + Cm * Cout)
+        line = dict(kernel="sepconv_dwpw", case=name, us=t * 1e6, gbs=nbytes / t / 1e9, tflops=fl / t / 1e12)
+        out.append(line)
+        print(f"{name:34s} {t * 1e6:8.1f} us  {nbytes / t / 1e9:6.0f} GB/s  {fl / t / 1e12:5.1f} TFLOP/s")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     out = []
@@ -119,6 +185,10 @@ if __name__ == "__main__":
         bench_gemm(out)
     if what in ("nilif", "all"):
         bench_nilif(out)
+    if what in ("dwconv", "all"):
+        bench_dwconv(out)
+    if what in ("sepconv", "all"):
+        bench_sepconv(out)
     d = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(d):
         json.dump(out, open(os.path.join(d, f"kernels_{what}.json"), "w"), indent=1)
