@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 8 */
+S2F_API int s2f_abi_version(void);   /* currently 9 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -162,6 +162,17 @@ S2F_API int s2f_dwconv(const void* a, int a_is_spike, float a_scale, const float
  * hi / lo image of W_pw [Cout, Cm] with one power-of-two scale per row (spike2former_b200/ops.py::pack_pw_f16,
  * s2f_sepconv_bpack_bytes bytes); `scale` must contain rowscale[co] / a_pre besides the folded BatchNorm scale.
  * Cm % 64 == 0, 16 <= Cout <= 128, Cout % 4 == 0. */
+/* Top-down FPN merge of the two finest levels in one launch (pixel_decoder.py:451-462: `cur = lateral_conv(x);
+ * y = cur + F.interpolate(y, cur.shape[-2:], mode='bilinear', align_corners=False); y = output_conv(spike(y))`):
+ *   out_spike = NI-LIF( (W a) * scale[co] + shift[co] + bilinear_x2(prev)[pixel, co] )
+ * a: int8 levels [n,H,W,Cin] (Cin in {16,32,48,64}), prev: fp32 [n,H/2,W/2,256], Cout = 256.  The lateral conv runs on
+ * tcgen05.mma.kind::f16 (levels are exact in fp16; w_packed = fp16 hi / lo image of W [256, 64] with Cin zero-padded to
+ * 64, ops.pack_pw_f16), one fp32 accumulator per output; `scale` holds rowscale[co] * a_scale * BN scale.
+ * Same arithmetic for the upsample as s2f_upsample_add_lif. */
+S2F_API int s2f_fpn_merge_f16(const int8_t* a, const void* w_packed, const float* scale, const float* shift,
+                      const float* prev, int8_t* out_spike, int n, int H, int W, int Cin, int Cout, int Hp, int Wp,
+                      float d_max, void* stream);
+
 S2F_API int64_t s2f_sepconv_bpack_bytes(int Cm, int Cout);
 S2F_API int s2f_sepconv_dwpw(const int8_t* a, float a_scale, const float* w_dw, const void* w_pw_packed, float a_pre,
                      const float* scale, const float* shift, const float* residual, float* out_f32, int8_t* out_spike,

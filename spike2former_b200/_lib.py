@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S2F_LIB") or os.path.join(_HERE, "libs2f.so")      # S2F_LIB: experiment builds only
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class ConvArgs(C.Structure):
@@ -51,6 +51,7 @@ SIGNATURES = {
     "s2f_pack_weights_i8": (_L, [_P, _I, _I, _I, _I, _P, _P]),
     "s2f_pack_rows_i8_device": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P]),
     "s2f_dwconv": (_I, [_P, _I, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "s2f_fpn_merge_f16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "s2f_sepconv_bpack_bytes": (_L, [_I, _I]),
     "s2f_sepconv_dwpw": (_I, [_P, _F, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "s2f_linear_attn": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),

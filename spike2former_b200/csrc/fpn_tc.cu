@@ -1,0 +1,281 @@
+// Top-down FPN merge in one launch (pixel_decoder.py:451-462):
+//   y = BN(lateral_1x1(spikes)) + bilinear_x2(prev)        spikes_out = NI-LIF(y)
+// for the two finest levels, where the lateral conv has a tiny K (32 / 64 input channels) and the work is the epilogue:
+// 537 M outputs per 32 images at 256^2.  The int8 digit-plane GEMM (gemm_tc.cu, 128 x 64 tiles, three int32 planes per
+// output) spent 37 instructions per output there, most of them per-tile bookkeeping and plane merging.  This kernel:
+//   * tile = 16 x 8 pixels x ALL 256 channels: one fp32 accumulator of 256 TMEM columns (two of them, ping-pong);
+//   * lateral conv on tcgen05.mma.kind::f16: the spike levels 0..8 are exact in fp16 (converted from int8 by the producer
+//     warp on the way into shared memory), the weights are fp16 hi + lo with one power-of-two scale per output channel
+//     (ops.pack_pw_f16): D = A W_hi^T + A W_lo^T, 2 * Cin / 16 MMAs per tile, 4 bytes of TMEM drain per output;
+//   * the coarser level's 6 x 10-pixel patch is copied by cp.async into shared memory with a 16-byte skew per pixel, so
+//     that an epilogue warp whose lanes are PIXELS (the layout tcgen05.ld delivers) reads its four bilinear corners
+//     with conflict-free LDS.128;
+//   * 16 epilogue warps (four per TMEM lane quadrant, 64 channels each): affine, ATen's bilinear expression
+//     hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11), NI-LIF, one STG.128 per 16 levels: ~12 instructions per output.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace s2f {
+
+constexpr int FP_EW = 16;                          // epilogue warps
+constexpr int FP_THREADS = (1 + FP_EW) * 32;       // warp 0: producer + MMA issue
+constexpr int FP_TW = 16, FP_TH = 8;               // fine tile
+constexpr int FP_PW = FP_TW / 2 + 2, FP_PH = FP_TH / 2 + 2;     // coarse patch: 10 x 6 pixels
+constexpr int FP_COUT = 256;
+constexpr int FP_PIX_BYTES = FP_COUT * 4 + 16;     // skewed pixel stride of the patch
+constexpr int FP_PATCH_BYTES = FP_PW * FP_PH * FP_PIX_BYTES;    // 62400
+constexpr int FP_A_BYTES = 128 * 128;              // one A stage: 128 pixels x 64 fp16 (K padded to 64)
+
+struct FpnP {
+  const int8_t* a; const uint8_t* bpack; const float* scale; const float* shift; const float* prev; int8_t* out_spike;
+  int n, H, W, Cin, Hp, Wp, tiles_x, tiles_y, tiles;
+};
+
+__device__ __forceinline__ uint32_t fp_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t fp_desc(uint32_t saddr) {      // K-major SWIZZLE_128B, SBO = 1024 B, version 1
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void fp_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void fp_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void fp_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "FP_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra FP_DONE;\n\t"
+      "bra FP_WAIT;\n\t"
+      "FP_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fp_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fp_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 fp_lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+__global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP p) {
+  extern __shared__ __align__(1024) uint8_t fp_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fp_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int b_plane = FP_COUT * 128;            // one of W_hi / W_lo: one 64-element K atom
+  uint8_t* sB = smem;                               // [hi | lo]                       64 KB
+  uint8_t* sA = sB + 2 * b_plane;                   // [2 stages]                      32 KB
+  uint8_t* sP = sA + 2 * FP_A_BYTES;                // [2 stages] skewed patches      124.8 KB
+  float* s_sc = reinterpret_cast<float*>(sP + 2 * FP_PATCH_BYTES);     // [256] scale, [256] shift
+  float* s_sh = s_sc + FP_COUT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sh + FP_COUT);        // acc_full[2], prev_full[2], slot_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const uint32_t bar0 = fp_u32(bars);
+  auto acc_full = [&](int s) { return bar0 + 8u * s; };
+  auto prev_full = [&](int s) { return bar0 + 16u + 8u * s; };
+  auto slot_empty = [&](int s) { return bar0 + 32u + 8u * s; };
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(acc_full(s)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(prev_full(s)), "r"(32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(slot_empty(s)), "r"(FP_EW));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fp_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.bpack);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = tid; i < 2 * b_plane / 16; i += FP_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < FP_COUT; i += FP_THREADS) { s_sc[i] = __ldg(p.scale + i); s_sh[i] = __ldg(p.shift + i); }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer + MMA issue
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(FP_COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int ksteps = p.Cin >> 4;                                   // K = 16 per MMA
+    const int chunks = p.Cin >> 4;                                   // 16-byte int8 chunks per pixel
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      if (it >= 2) fp_wait(slot_empty(s), (uint32_t)(((it >> 1) - 1) & 1));     // epilogue of tile it-2 is done with slot s
+      // ---- coarse patch -> skewed shared image (clamped coordinates: the border rule of upsample_bilinear2d)
+      {
+        const int cy0 = ty * (FP_TH / 2) - 1, cx0 = tx * (FP_TW / 2) - 1;
+        const float* pimg = p.prev + (int64_t)img * p.Hp * p.Wp * FP_COUT;
+        const uint32_t pdst = fp_u32(sP) + (uint32_t)s * FP_PATCH_BYTES;
+        for (int lp = 0; lp < FP_PW * FP_PH; ++lp) {
+          const int gy = min(max(cy0 + lp / FP_PW, 0), p.Hp - 1), gx = min(max(cx0 + lp % FP_PW, 0), p.Wp - 1);
+          const float* src = pimg + ((int64_t)gy * p.Wp + gx) * FP_COUT;
+          const uint32_t d = pdst + (uint32_t)lp * FP_PIX_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(h * 32 + lane) * 16u),
+                         "l"(src + (h * 32 + lane) * 4) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(prev_full(s)) : "memory");
+      }
+      // ---- A operand: int8 levels -> fp16, K-major SWIZZLE_128B rows (pixel m = lane + 32 j)
+      {
+        const uint32_t adst = fp_u32(sA) + (uint32_t)s * FP_A_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = lane + 32 * j;
+          const int y = min(ty * FP_TH + (m >> 4), p.H - 1), x = min(tx * FP_TW + (m & 15), p.W - 1);
+          const uint4* src = reinterpret_cast<const uint4*>(p.a + (((int64_t)img * p.H + y) * p.W + x) * p.Cin);
+          for (int c = 0; c < chunks; ++c) {                           // 16 levels -> two 16-byte chunks of fp16
+            const uint4 v = __ldg(src + c);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t h[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              // bytes (b0, b1) -> halves (1024 + b0, 1024 + b1) by PRMT into the mantissa of 0x6400, then - 1024: exact
+              const uint32_t lo = __byte_perm(w[i], 0x64646464u, 0x4140), hi = __byte_perm(w[i], 0x64646464u, 0x4342);
+              const __half2 bias = __floats2half2_rn(1024.f, 1024.f);
+              const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), bias);
+              const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), bias);
+              h[2 * i] = *reinterpret_cast<const uint32_t*>(&hl);
+              h[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            const uint32_t row = adst + (uint32_t)m * 128u;
+            const uint32_t c0 = (uint32_t)((2 * c) ^ (m & 7)) << 4, c1 = (uint32_t)((2 * c + 1) ^ (m & 7)) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = fp_u32(sA) + (uint32_t)s * FP_A_BYTES, b_hi = fp_u32(sB), b_lo = b_hi + b_plane;
+        const uint32_t tacc = tmem_base + (uint32_t)(s * FP_COUT);
+        for (int combo = 0; combo < 2; ++combo)
+          for (int k = 0; k < ksteps; ++k)
+            fp_mma_f16(tacc, fp_desc(a0) + (uint64_t)(k * 2), fp_desc(combo ? b_lo : b_hi) + (uint64_t)(k * 2), idesc,
+                       (uint32_t)((combo | k) != 0));
+        fp_commit(acc_full(s));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane = pixel, warp = 64 channels
+    const int ew = warp - 1, q = warp & 3;              // TMEM lane quadrant is fixed by the warp index modulo 4
+    // the four warps of a quadrant take the four 64-channel groups: rank of this warp among the warps with warp % 4 == q
+    const int cg = (warp - (q == 0 ? 4 : q)) >> 2;      // warps q, q+4, q+8, q+12 (q = 0: 4, 8, 12, 16) -> 0..3
+    (void)ew;
+    const int m = q * 32 + lane;
+    const float shy = (float)p.Hp / (float)p.H, swx = (float)p.Wp / (float)p.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int y = ty * FP_TH + (m >> 4), x = tx * FP_TW + (m & 15);
+      const bool ok = y < p.H && x < p.W;
+      // upsample_bilinear2d, align_corners = False: src = (dst + 0.5) * scale - 0.5, clamped at 0
+      float sy = shy * ((float)y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+      float sx = swx * ((float)x + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+      int y0 = (int)sy, x0 = (int)sx;
+      y0 = min(y0, p.Hp - 1); x0 = min(x0, p.Wp - 1);                    // only for pixels outside the map (not stored)
+      const int y1 = y0 + (y0 < p.Hp - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wp - 1 ? 1 : 0);
+      const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+      const int cy0 = ty * (FP_TH / 2) - 1, cx0 = tx * (FP_TW / 2) - 1;
+      const int r0 = min(max(y0 - cy0, 0), FP_PH - 1), r1 = min(max(y1 - cy0, 0), FP_PH - 1);
+      const int c0 = min(max(x0 - cx0, 0), FP_PW - 1), c1 = min(max(x1 - cx0, 0), FP_PW - 1);
+      const uint32_t pbase = fp_u32(sP) + (uint32_t)s * FP_PATCH_BYTES + (uint32_t)(cg * 64) * 4u;
+      const uint32_t a00 = pbase + (uint32_t)(r0 * FP_PW + c0) * FP_PIX_BYTES, a01 = pbase + (uint32_t)(r0 * FP_PW + c1) * FP_PIX_BYTES;
+      const uint32_t a10 = pbase + (uint32_t)(r1 * FP_PW + c0) * FP_PIX_BYTES, a11 = pbase + (uint32_t)(r1 * FP_PW + c1) * FP_PIX_BYTES;
+      int8_t* dst = p.out_spike + (((int64_t)img * p.H + y) * p.W + x) * FP_COUT + cg * 64;
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      fp_wait(prev_full(s), par);
+      fp_wait(acc_full(s), par);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + (uint32_t)(s * FP_COUT + cg * 64) + ((uint32_t)(q * 32) << 16);
+      const uint32_t sc_s = fp_u32(s_sc) + (uint32_t)(cg * 64) * 4u, sh_s = fp_u32(s_sh) + (uint32_t)(cg * 64) * 4u;
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t v[16];
+        fp_ld16(trow + cb * 16, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t co = (uint32_t)(cb * 16 + j * 4) * 4u;
+          const float4 sc4 = fp_lds128(sc_s + co), sh4 = fp_lds128(sh_s + co);
+          const float4 p00 = fp_lds128(a00 + co), p01 = fp_lds128(a01 + co), p10 = fp_lds128(a10 + co), p11 = fp_lds128(a11 + co);
+          float y0f = fmaf(__uint_as_float(v[j * 4 + 0]), sc4.x, sh4.x), y1f = fmaf(__uint_as_float(v[j * 4 + 1]), sc4.y, sh4.y);
+          float y2f = fmaf(__uint_as_float(v[j * 4 + 2]), sc4.z, sh4.z), y3f = fmaf(__uint_as_float(v[j * 4 + 3]), sc4.w, sh4.w);
+          y0f = y0f + (hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x));
+          y1f = y1f + (hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y));
+          y2f = y2f + (hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z));
+          y3f = y3f + (hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w));
+          pk[j] = pack_levels4_d8(y0f, y1f, y2f, y3f);
+        }
+        if (ok) *reinterpret_cast<uint4*>(dst + cb * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) fp_arrive(slot_empty(s));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace s2f
+
+using namespace s2f;
+
+extern "C" int s2f_fpn_merge_f16(const int8_t* a, const void* w_packed, const float* scale, const float* shift,
+                                 const float* prev, int8_t* out_spike, int n, int H, int W, int Cin, int Cout, int Hp, int Wp,
+                                 float d_max, void* stream) {
+  S2F_REQUIRE(a && w_packed && scale && shift && prev && out_spike, "fpn_merge_f16: null pointer");
+  S2F_REQUIRE(Cout == FP_COUT, "fpn_merge_f16: Cout must be 256");
+  S2F_REQUIRE(Cin == 16 || Cin == 32 || Cin == 48 || Cin == 64, "fpn_merge_f16: Cin must be a multiple of 16, at most 64");
+  S2F_REQUIRE(H == 2 * Hp && W == 2 * Wp, "fpn_merge_f16: exact x2 upsampling only");
+  S2F_REQUIRE(d_max == 8.f, "fpn_merge_f16: d_max must be 8");
+  S2F_REQUIRE((int64_t)n * H * W < (1ll << 31), "fpn_merge_f16: problem too large");
+  FpnP p;
+  p.a = a; p.bpack = reinterpret_cast<const uint8_t*>(w_packed); p.scale = scale; p.shift = shift; p.prev = prev;
+  p.out_spike = out_spike; p.n = n; p.H = H; p.W = W; p.Cin = Cin; p.Hp = Hp; p.Wp = Wp;
+  p.tiles_x = (W + FP_TW - 1) / FP_TW; p.tiles_y = (H + FP_TH - 1) / FP_TH; p.tiles = n * p.tiles_x * p.tiles_y;
+  const size_t smem = 1024 + 2 * FP_COUT * 128 + 2 * FP_A_BYTES + 2 * FP_PATCH_BYTES + 2 * FP_COUT * sizeof(float) + 6 * 8 + 16;
+  static std::atomic<uint64_t> once{0};
+  if (first_use_on_this_device(once))
+    cudaFuncSetAttribute(fpn_merge_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+  fpn_merge_f16_kernel<<<grid, FP_THREADS, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("fpn_merge_f16_kernel");
+}

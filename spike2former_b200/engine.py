@@ -25,6 +25,7 @@ INV = 1.0 / NORM
 USE_TC = True            # spike-operand layers run on the tcgen05 kernel (the CUDA-core kernel covers the rest)
 import os as _os
 TC_PIECES = int(_os.environ.get("S2F_TC_PIECES", "3"))   # int8 digit planes per weight: 3 = 21-bit fixed point (default), 2 = 14-bit fast mode
+FUSE_FPN = _os.environ.get("S2F_FUSE_FPN", "1") != "0"           # finest FPN merges on the fp16 kernel (csrc/fpn_tc.cu)
 FUSE_SEPCONV = _os.environ.get("S2F_FUSE_SEPCONV", "1") != "0"   # SepConv dw7x7 + pwconv2 as one launch (csrc/sepconv_tc.cu)
 TC_MIN_ROWS = 1          # every eligible layer runs on the tensor-core kernel whatever the batch: its integer accumulation
                          # is order-independent, so an image's result never depends on how many images share the launch
@@ -110,6 +111,30 @@ class SepDwPw:
         return ops.sepconv_dwpw(a, self.w_dw, self.packed, n=n, H=H, W=W, Cm=self.cm, Cout=self.cout, k=self.k,
                                 scale=self.scale, shift=self.shift, a_pre=self.a_pre, residual=residual,
                                 want_f32=f32, want_spike=spike)
+
+
+class FpnMergeF16:
+    """lateral 1x1 + BN + bilinear x2 + add + NI-LIF of the two finest FPN levels (pixel_decoder.py:451-462) on
+    csrc/fpn_tc.cu: tcgen05 kind::f16 with fp16 hi / lo weights, one fp32 accumulator per output."""
+
+    def __init__(self, gm, device):
+        w = gm.w[:, :gm.cin].detach().double().cpu()
+        w64 = torch.zeros(gm.cout, 64, dtype=torch.float64)
+        w64[:, :gm.cin] = w
+        packed, rowscale = ops.pack_pw_f16(w64)
+        self.cin, self.cout = gm.cin, gm.cout
+        self.packed = packed.to(device)
+        self.scale = fold.f32(gm.scale.double().cpu() * rowscale.double() * INV, device)
+        self.shift = gm.shift
+        self.alg_macs = gm.alg_macs
+
+    @staticmethod
+    def eligible(gm):
+        return USE_TC and FUSE_FPN and gm.k == 1 and gm.cout == 256 and gm.cin % 16 == 0 and gm.cin <= 64
+
+    def __call__(self, a, prev, n, H, W):
+        return ops.fpn_merge_f16(a, self.packed, prev, n=n, H=H, W=W, Cin=self.cin, Cout=self.cout, scale=self.scale,
+                                 shift=self.shift, alg_macs=self.alg_macs)
 
 
 class StemU8:
@@ -301,6 +326,8 @@ class PixelDecoderPlan:
         for i in range(model.num_inputs - 1):
             L[f"lateral.{i}"] = _conv_gemm(sd, f"lateral_convs.{i}.0", f"lateral_convs.{i}.1", dev)
             L[f"output.{i}"] = _dw(sd, f"output_convs.{i}.0", f"output_convs.{i}.1", dev)
+        self.fpn_f16 = {i: FpnMergeF16(L[f"lateral.{i}"], dev) for i in range(model.num_inputs - 1)
+                        if FpnMergeF16.eligible(L[f"lateral.{i}"])}
         L["mask_feature"] = _conv_gemm(sd, "mask_feature", None, dev)
         # einsum(mask_embed, mask_feature(s)) == (mask_embed W_mf) s + mask_embed b: the per-image product
         # [nq, C] x [W_mf^T ; b] is a tiny GEMM, after which mask_feature never has to be materialised.
@@ -668,7 +695,11 @@ def pixel_decoder_forward(model, feats, probe=NOPROBE, want_mask_feature=True, s
             if not pr.active and lat.tc is not None and n * h * w >= TC_MIN_ROWS and C % 16 == 0:
                 # lateral 1x1 + BN, bilinear upsample of the coarser level, add and NI-LIF in one launch: the fp32 lateral
                 # map (1 GB at batch 16 for the 256^2 level) is never written
-                _, ys = lat(sp_i, n, h, w, spike=True, up_prev=y)
+                fm = plan.fpn_f16.get(i)
+                if fm is not None and h == 2 * hp and w == 2 * wp and sp_i.dtype == torch.int8:
+                    _, ys = fm(sp_i, y, n, h, w)
+                else:
+                    _, ys = lat(sp_i, n, h, w, spike=True, up_prev=y)
             else:
                 cur, _ = lat(sp_i, n, h, w, f32=True)
                 ys, yf = ops.upsample_add_lif(cur, y, n=n, H=h, W=w, Hp=hp, Wp=wp, C_=C, want_f32=pr.active)

@@ -346,6 +346,23 @@ def sepconv_dwpw(a, w_dw_tap, w_pw_packed, *, n, H, W, Cm, Cout, k, scale, shift
     return out_f, out_s
 
 
+def fpn_merge_f16(a, w_packed, prev, *, n, H, W, Cin, Cout, scale, shift, d_max=D_MAX, alg_macs=None):
+    """Lateral 1x1 + BN + bilinear x2 of the coarser level + NI-LIF in one launch (pixel_decoder.py:451-462) for
+    Cin <= 64, Cout = 256: w_packed = pack_pw_f16(W zero-padded to 64 input channels), scale = rowscale * a_scale * BN."""
+    if a.dtype != torch.int8:
+        raise S2FError("fpn_merge_f16: a must be int8 levels")
+    Hp, Wp = int(prev.shape[1]), int(prev.shape[2])
+    out_s = torch.empty((n, H, W, Cout), dtype=torch.int8, device=a.device)
+    e0 = _p0()
+    check(_lib.lib().s2f_fpn_merge_f16(_ptr(a, torch.int8, "a"), _ptr(w_packed, torch.uint8, "w_packed"),
+                                       _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"),
+                                       _ptr(prev, torch.float32, "prev"), _ptr(out_s), n, H, W, Cin, Cout, Hp, Wp,
+                                       float(d_max), _stream()), "s2f_fpn_merge_f16")
+    _p1(e0, "fpn_merge", 2.0 * n * H * W * (Cin * Cout if alg_macs is None else alg_macs), _nb(a, prev, out_s),
+        f"{n}x{H}x{W} {Cin}->{Cout} + up x2")
+    return None, out_s
+
+
 # ------------------------------------------------------------------------------------------ attention / DCN / tail
 def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=None, out_ld=None, want_f32=False,
                 d_max=D_MAX):

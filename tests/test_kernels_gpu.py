@@ -516,3 +516,36 @@ def test_sepconv_dwpw_fused_vs_float64_and_two_kernel_path(k, Cm, Cout, H, W, n)
     o2, _ = ops.conv_simt(d, ops.pad_rows4(w_pw.cuda()), n=n, H=H, W=W, Cin=Cm, Cout=Cout, scale=sc.cuda(), shift=sh.cuda(),
                           residual=res.cuda(), want_f32=True, want_spike=True)
     assert (of - o2).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("H,W,cin,n", [(32, 48, 32, 2), (24, 32, 64, 2), (18, 22, 32, 1), (256, 256, 32, 1)])
+def test_fpn_merge_f16_vs_float64_and_digit_plane_kernel(H, W, cin, n):
+    """Finest FPN merges (pixel_decoder.py:451-462) on csrc/fpn_tc.cu: lateral 1x1 on tcgen05 kind::f16 (fp16 hi / lo
+    weights, levels exact in fp16) + bilinear x2 + NI-LIF, against float64 and the int8 digit-plane kernel's fused merge."""
+    g = gen(41)
+    cout = 256
+    a = _levels((n, H, W, cin), g)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    w[3] *= 1e-3
+    w[5, 1] = 9.0
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) + 1
+    prev = torch.randn(n, H // 2, W // 2, cout, generator=g) * 2
+    lat = torch.einsum("nhwc,oc->nhwo", a.double() / 8, w.double()) * sc.double() + sh.double()
+    up = F.interpolate(prev.double().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    ref = lat + up
+    w64 = torch.zeros(cout, 64)
+    w64[:, :cin] = w
+    packed, rowscale = ops.pack_pw_f16(w64)
+    scale = (sc.double() * rowscale.double() / 8).float().cuda()
+    _, lv = ops.fpn_merge_f16(a.cuda(), packed.cuda(), prev.cuda(), n=n, H=H, W=W, Cin=cin, Cout=cout, scale=scale, shift=sh.cuda())
+    lv_ref = torch.round(torch.clamp(ref, 0, 8))
+    bad = lv.cpu().double() != lv_ref
+    frac = (torch.clamp(ref, 0, 8) - torch.floor(torch.clamp(ref, 0, 8)) - 0.5).abs()
+    assert bool((frac[bad] < 1e-4 * ref.abs().clamp_min(1.0)[bad]).all()), int(bad.sum())
+    assert int(bad.sum()) <= 2e-4 * bad.numel()
+    # the digit-plane kernel's fused merge (exact integer lateral conv): same levels up to the same near-ties
+    pk, rs = ops.pack_weights_i8(w, 1, cin, 3)
+    _, lv2 = ops.gemm_tc(a.cuda(), pk.cuda(), n=n, H=H, W=W, Cin=cin, Cout=cout, scale=(sc * rs / 8).cuda(), shift=sh.cuda(),
+                         want_spike=True, up_prev=prev.cuda())
+    diff = lv != lv2
+    assert bool((frac[diff.cpu()] < 1e-4 * ref.abs().clamp_min(1.0)[diff.cpu()]).all()), int(diff.sum())

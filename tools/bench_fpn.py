@@ -25,5 +25,14 @@ for (H, cin) in ((256, 32), (128, 64), (64, 128)):
     t_plain = timed(lambda: ops.gemm_tc(a, pk, want_spike=True, **kw), IT)
     t_up = timed(lambda: ops.gemm_tc(a, pk, want_spike=True, up_prev=prev, **kw), IT)
     byt = a.numel() + prev.numel() * 4 + B * H * H * cout
+    t_f16 = None
+    if cin <= 64:
+        w64 = torch.zeros(cout, 64)
+        w64[:, :cin] = w
+        pf, rs16 = ops.pack_pw_f16(w64)
+        pf, sc16 = pf.cuda(), (sc.double() * rs16.double() / 8).float().cuda()
+        shc = sh.cuda()
+        t_f16 = timed(lambda: ops.fpn_merge_f16(a, pf, prev, n=B, H=H, W=H, Cin=cin, Cout=cout, scale=sc16, shift=shc), IT)
     print(f"{H}x{H} {cin}->{cout} B={B}: spike-only {t_plain * 1e6:8.1f} us | fused FPN merge {t_up * 1e6:8.1f} us "
-          f"= {byt / t_up / 1e9:6.0f} GB/s algorithmic ({byt / 1e6:.0f} MB)")
+          f"= {byt / t_up / 1e9:6.0f} GB/s algorithmic ({byt / 1e6:.0f} MB)"
+          + (f" | fp16 kernel {t_f16 * 1e6:8.1f} us = {byt / t_f16 / 1e9:6.0f} GB/s" if t_f16 else ""))
