@@ -75,6 +75,20 @@ __device__ __forceinline__ float4 fp_lds128(uint32_t saddr) {
   return v;
 }
 
+__device__ __forceinline__ float fp_add_sat(float a, float b) {       // clamp(a + b, 0, 1) in one FADD.SAT
+  float r;
+  asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// four values u = clamp(y, 0, 8) / 8 in [0, 1] -> four int8 levels round_half_even(8 u): one FFMA each puts the level
+// into the mantissa of 2^23 (common.cuh::level_bits8 without its saturating multiply), three PRMT pack them
+__device__ __forceinline__ uint32_t pack_unit4(float a, float b, float c, float d) {
+  const uint32_t la = __float_as_uint(fmaf(a, 8.f, 8388608.f)), lb = __float_as_uint(fmaf(b, 8.f, 8388608.f));
+  const uint32_t lc = __float_as_uint(fmaf(c, 8.f, 8388608.f)), ld = __float_as_uint(fmaf(d, 8.f, 8388608.f));
+  return __byte_perm(__byte_perm(la, lb, 0x0040), __byte_perm(lc, ld, 0x0040), 0x5410);
+}
+
+template <int CHUNKS>   // 16-byte int8 chunks per input pixel = Cin / 16
 __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP p) {
   extern __shared__ __align__(1024) uint8_t fp_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fp_raw) + 1023) & ~uintptr_t(1023));
@@ -96,7 +110,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(acc_full(s)), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(prev_full(s)), "r"(32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(prev_full(s)), "r"(FP_EW * 32));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(slot_empty(s)), "r"(FP_EW));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -109,7 +123,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
     const uint4* src = reinterpret_cast<const uint4*>(p.bpack);
     uint4* dst = reinterpret_cast<uint4*>(sB);
     for (int i = tid; i < 2 * b_plane / 16; i += FP_THREADS) dst[i] = __ldg(src + i);
-    for (int i = tid; i < FP_COUT; i += FP_THREADS) { s_sc[i] = __ldg(p.scale + i); s_sh[i] = __ldg(p.shift + i); }
+    for (int i = tid; i < FP_COUT; i += FP_THREADS) { s_sc[i] = __ldg(p.scale + i) * 0.125f; s_sh[i] = __ldg(p.shift + i) * 0.125f; }   // 1/8 scale: exact
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -118,60 +132,59 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer + MMA issue
+    // ------------------------------------------------------------------ A operand + MMA issue
+    // int8 levels -> fp16, K-major SWIZZLE_128B rows (pixel m = lane + 32 j); the NEXT tile's levels are already in
+    // registers while this tile's are converted, so the global latency is off the per-tile critical path.
     const uint32_t idesc = (1u << 4) | ((uint32_t)(FP_COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int ksteps = p.Cin >> 4;                                   // K = 16 per MMA
-    const int chunks = p.Cin >> 4;                                   // 16-byte int8 chunks per pixel
+    constexpr int ksteps = CHUNKS;                                   // K = 16 per MMA
+    constexpr int chunks = CHUNKS;
+    uint4 nxt[4][CHUNKS];
+    auto load_a = [&](int tile) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = lane + 32 * j;
+        const int y = min(ty * FP_TH + (m >> 4), p.H - 1), x = min(tx * FP_TW + (m & 15), p.W - 1);
+        const uint4* src = reinterpret_cast<const uint4*>(p.a + (((int64_t)img * p.H + y) * p.W + x) * p.Cin);
+#pragma unroll
+        for (int c = 0; c < chunks; ++c) nxt[j][c] = __ldg(src + c);
+      }
+    };
+    if ((int)blockIdx.x < p.tiles) load_a(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
-      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
       if (it >= 2) fp_wait(slot_empty(s), (uint32_t)(((it >> 1) - 1) & 1));     // epilogue of tile it-2 is done with slot s
-      // ---- coarse patch -> skewed shared image (clamped coordinates: the border rule of upsample_bilinear2d)
-      {
-        const int cy0 = ty * (FP_TH / 2) - 1, cx0 = tx * (FP_TW / 2) - 1;
-        const float* pimg = p.prev + (int64_t)img * p.Hp * p.Wp * FP_COUT;
-        const uint32_t pdst = fp_u32(sP) + (uint32_t)s * FP_PATCH_BYTES;
-        for (int lp = 0; lp < FP_PW * FP_PH; ++lp) {
-          const int gy = min(max(cy0 + lp / FP_PW, 0), p.Hp - 1), gx = min(max(cx0 + lp % FP_PW, 0), p.Wp - 1);
-          const float* src = pimg + ((int64_t)gy * p.Wp + gx) * FP_COUT;
-          const uint32_t d = pdst + (uint32_t)lp * FP_PIX_BYTES;
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(h * 32 + lane) * 16u),
-                         "l"(src + (h * 32 + lane) * 4) : "memory");
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(prev_full(s)) : "memory");
-      }
-      // ---- A operand: int8 levels -> fp16, K-major SWIZZLE_128B rows (pixel m = lane + 32 j)
       {
         const uint32_t adst = fp_u32(sA) + (uint32_t)s * FP_A_BYTES;
+        const __half2 bias = __floats2half2_rn(1024.f, 1024.f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int m = lane + 32 * j;
-          const int y = min(ty * FP_TH + (m >> 4), p.H - 1), x = min(tx * FP_TW + (m & 15), p.W - 1);
-          const uint4* src = reinterpret_cast<const uint4*>(p.a + (((int64_t)img * p.H + y) * p.W + x) * p.Cin);
-          for (int c = 0; c < chunks; ++c) {                           // 16 levels -> two 16-byte chunks of fp16
-            const uint4 v = __ldg(src + c);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t h[8];
+          const uint32_t row = adst + (uint32_t)m * 128u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              // bytes (b0, b1) -> halves (1024 + b0, 1024 + b1) by PRMT into the mantissa of 0x6400, then - 1024: exact
-              const uint32_t lo = __byte_perm(w[i], 0x64646464u, 0x4140), hi = __byte_perm(w[i], 0x64646464u, 0x4342);
-              const __half2 bias = __floats2half2_rn(1024.f, 1024.f);
-              const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), bias);
-              const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), bias);
-              h[2 * i] = *reinterpret_cast<const uint32_t*>(&hl);
-              h[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          for (int c = 0; c < chunks; ++c) {
+            {                                                          // 16 levels -> two 16-byte chunks of fp16
+              const uint4 v = nxt[j][c];
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+              uint32_t h[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // bytes (b0, b1) -> halves (1024 + b0, 1024 + b1) by PRMT into the mantissa of 0x6400, then - 1024: exact
+                const uint32_t lo = __byte_perm(w[i], 0x64646464u, 0x4140), hi = __byte_perm(w[i], 0x64646464u, 0x4342);
+                const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), bias);
+                const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), bias);
+                h[2 * i] = *reinterpret_cast<const uint32_t*>(&hl);
+                h[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              const uint32_t c0 = (uint32_t)((2 * c) ^ (m & 7)) << 4, c1 = (uint32_t)((2 * c + 1) ^ (m & 7)) << 4;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
             }
-            const uint32_t row = adst + (uint32_t)m * 128u;
-            const uint32_t c0 = (uint32_t)((2 * c) ^ (m & 7)) << 4, c1 = (uint32_t)((2 * c + 1) ^ (m & 7)) << 4;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
           }
         }
       }
+      if (tile + (int)gridDim.x < p.tiles) load_a(tile + gridDim.x);   // in flight behind the MMAs and the next slot wait
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
@@ -191,12 +204,35 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
     const int ew = warp - 1, q = warp & 3;              // TMEM lane quadrant is fixed by the warp index modulo 4
     // the four warps of a quadrant take the four 64-channel groups: rank of this warp among the warps with warp % 4 == q
     const int cg = (warp - (q == 0 ? 4 : q)) >> 2;      // warps q, q+4, q+8, q+12 (q = 0: 4, 8, 12, 16) -> 0..3
-    (void)ew;
     const int m = q * 32 + lane;
     const float shy = (float)p.Hp / (float)p.H, swx = (float)p.Wp / (float)p.W;
+    // The coarse patch of a tile (6 x 10 pixels x 1 KB) is fetched by these 512 threads themselves, one tile ahead:
+    // 3840 16-byte cp.async, 7.5 per thread, all in flight at once; a warp's 32 chunks are half a pixel.
+    auto issue_patch = [&](int tile, int s) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int cy0 = ty * (FP_TH / 2) - 1, cx0 = tx * (FP_TW / 2) - 1;
+      const float* pimg = p.prev + (int64_t)img * p.Hp * p.Wp * FP_COUT + ((ew & 1) * 32 + lane) * 4;
+      const uint32_t pdst = fp_u32(sP) + (uint32_t)s * FP_PATCH_BYTES + (uint32_t)((ew & 1) * 32 + lane) * 16u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int lp = (ew >> 1) + 8 * i;                               // warp-uniform patch pixel
+        if (lp < FP_PW * FP_PH) {
+          const int gy = min(max(cy0 + lp / FP_PW, 0), p.Hp - 1), gx = min(max(cx0 + lp % FP_PW, 0), p.Wp - 1);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pdst + (uint32_t)lp * FP_PIX_BYTES),
+                       "l"(pimg + ((int64_t)gy * p.Wp + gx) * FP_COUT) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(prev_full(s)) : "memory");
+    };
+    if ((int)blockIdx.x < p.tiles) issue_patch(blockIdx.x, 0);
+    const uint32_t sc_s = fp_u32(s_sc) + (uint32_t)(cg * 64) * 4u, sh_s = fp_u32(s_sh) + (uint32_t)(cg * 64) * 4u;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
+      if (tile + (int)gridDim.x < p.tiles) {
+        if (it >= 1) fp_wait(slot_empty(s ^ 1), (uint32_t)(((it - 1) >> 1) & 1));   // every warp is done with tile it-1
+        issue_patch(tile + gridDim.x, s ^ 1);
+      }
       const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
       const int y = ty * FP_TH + (m >> 4), x = tx * FP_TW + (m & 15);
       const bool ok = y < p.H && x < p.W;
@@ -207,6 +243,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
       y0 = min(y0, p.Hp - 1); x0 = min(x0, p.Wp - 1);                    // only for pixels outside the map (not stored)
       const int y1 = y0 + (y0 < p.Hp - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wp - 1 ? 1 : 0);
       const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+      // everything below is carried at 1/8 scale (exact: a power of two), so that the final add saturates to [0, 1]
+      const float2 hx2 = make_float2(hx, hx), lx2 = make_float2(lx, lx);
+      const float2 hy8 = make_float2(hy * 0.125f, hy * 0.125f), ly8 = make_float2(ly * 0.125f, ly * 0.125f);
       const int cy0 = ty * (FP_TH / 2) - 1, cx0 = tx * (FP_TW / 2) - 1;
       const int r0 = min(max(y0 - cy0, 0), FP_PH - 1), r1 = min(max(y1 - cy0, 0), FP_PH - 1);
       const int c0 = min(max(x0 - cx0, 0), FP_PW - 1), c1 = min(max(x1 - cx0, 0), FP_PW - 1);
@@ -215,29 +254,34 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
       const uint32_t a10 = pbase + (uint32_t)(r1 * FP_PW + c0) * FP_PIX_BYTES, a11 = pbase + (uint32_t)(r1 * FP_PW + c1) * FP_PIX_BYTES;
       int8_t* dst = p.out_spike + (((int64_t)img * p.H + y) * p.W + x) * FP_COUT + cg * 64;
       const uint32_t par = (uint32_t)((it >> 1) & 1);
-      fp_wait(prev_full(s), par);
       fp_wait(acc_full(s), par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + (uint32_t)(s * FP_COUT + cg * 64) + ((uint32_t)(q * 32) << 16);
-      const uint32_t sc_s = fp_u32(s_sc) + (uint32_t)(cg * 64) * 4u, sh_s = fp_u32(s_sh) + (uint32_t)(cg * 64) * 4u;
-#pragma unroll 1
+      uint32_t v[2][16];
+      fp_ld16(trow, v[0]);
+      fp_wait(prev_full(s), par);
+#pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
-        uint32_t v[16];
-        fp_ld16(trow + cb * 16, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cb < 3) fp_ld16(trow + (cb + 1) * 16, v[(cb + 1) & 1]);
+        const uint32_t* vc = v[cb & 1];
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t co = (uint32_t)(cb * 16 + j * 4) * 4u;
           const float4 sc4 = fp_lds128(sc_s + co), sh4 = fp_lds128(sh_s + co);
           const float4 p00 = fp_lds128(a00 + co), p01 = fp_lds128(a01 + co), p10 = fp_lds128(a10 + co), p11 = fp_lds128(a11 + co);
-          float y0f = fmaf(__uint_as_float(v[j * 4 + 0]), sc4.x, sh4.x), y1f = fmaf(__uint_as_float(v[j * 4 + 1]), sc4.y, sh4.y);
-          float y2f = fmaf(__uint_as_float(v[j * 4 + 2]), sc4.z, sh4.z), y3f = fmaf(__uint_as_float(v[j * 4 + 3]), sc4.w, sh4.w);
-          y0f = y0f + (hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x));
-          y1f = y1f + (hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y));
-          y2f = y2f + (hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z));
-          y3f = y3f + (hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w));
-          pk[j] = pack_levels4_d8(y0f, y1f, y2f, y3f);
+          float2 ya = __ffma2_rn(make_float2(__uint_as_float(vc[j * 4 + 0]), __uint_as_float(vc[j * 4 + 1])),
+                                 make_float2(sc4.x, sc4.y), make_float2(sh4.x, sh4.y));
+          float2 yb = __ffma2_rn(make_float2(__uint_as_float(vc[j * 4 + 2]), __uint_as_float(vc[j * 4 + 3])),
+                                 make_float2(sc4.z, sc4.w), make_float2(sh4.z, sh4.w));
+          const float2 t0a = __ffma2_rn(lx2, make_float2(p01.x, p01.y), __fmul2_rn(hx2, make_float2(p00.x, p00.y)));
+          const float2 t0b = __ffma2_rn(lx2, make_float2(p01.z, p01.w), __fmul2_rn(hx2, make_float2(p00.z, p00.w)));
+          const float2 t1a = __ffma2_rn(lx2, make_float2(p11.x, p11.y), __fmul2_rn(hx2, make_float2(p10.x, p10.y)));
+          const float2 t1b = __ffma2_rn(lx2, make_float2(p11.z, p11.w), __fmul2_rn(hx2, make_float2(p10.z, p10.w)));
+          const float2 ua = __ffma2_rn(ly8, t1a, __fmul2_rn(hy8, t0a));
+          const float2 ub = __ffma2_rn(ly8, t1b, __fmul2_rn(hy8, t0b));
+          pk[j] = pack_unit4(fp_add_sat(ya.x, ua.x), fp_add_sat(ya.y, ua.y), fp_add_sat(yb.x, ub.x), fp_add_sat(yb.y, ub.y));
         }
         if (ok) *reinterpret_cast<uint4*>(dst + cb * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -273,9 +317,18 @@ extern "C" int s2f_fpn_merge_f16(const int8_t* a, const void* w_packed, const fl
   p.tiles_x = (W + FP_TW - 1) / FP_TW; p.tiles_y = (H + FP_TH - 1) / FP_TH; p.tiles = n * p.tiles_x * p.tiles_y;
   const size_t smem = 1024 + 2 * FP_COUT * 128 + 2 * FP_A_BYTES + 2 * FP_PATCH_BYTES + 2 * FP_COUT * sizeof(float) + 6 * 8 + 16;
   static std::atomic<uint64_t> once{0};
-  if (first_use_on_this_device(once))
-    cudaFuncSetAttribute(fpn_merge_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (first_use_on_this_device(once)) {
+    cudaFuncSetAttribute(fpn_merge_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fpn_merge_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fpn_merge_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fpn_merge_f16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
-  fpn_merge_f16_kernel<<<grid, FP_THREADS, smem, (cudaStream_t)stream>>>(p);
+  switch (Cin >> 4) {
+    case 1: fpn_merge_f16_kernel<1><<<grid, FP_THREADS, smem, (cudaStream_t)stream>>>(p); break;
+    case 2: fpn_merge_f16_kernel<2><<<grid, FP_THREADS, smem, (cudaStream_t)stream>>>(p); break;
+    case 3: fpn_merge_f16_kernel<3><<<grid, FP_THREADS, smem, (cudaStream_t)stream>>>(p); break;
+    default: fpn_merge_f16_kernel<4><<<grid, FP_THREADS, smem, (cudaStream_t)stream>>>(p); break;
+  }
   return check_launch("fpn_merge_f16_kernel");
 }
