@@ -641,17 +641,18 @@ extern "C" int s2f_semantic_tail_tc(const float* mask_pred, const float* cls, fl
     q.Q = Q; q.K = K; q.Np = Np; q.h = h; q.w = w; q.H = H; q.W = W;
     q.tiles_x = (W + 31) / 32; q.tiles_y = (h + 1 + 1) / 2;          // cell rows -1 .. h-1, two per tile
     const int tiles_img = q.tiles_x * q.tiles_y;
-    // CTAs per image: one CTA per SM (227 KB of shared memory), so the grid runs in k waves of 148; pick the k <= 3
+    // CTAs per image: one CTA per SM (227 KB of shared memory), so the grid runs in k waves of all SMs; pick the k <= 8
     // that wastes the fewest SM-waves (batch 32: 4 CTAs per image fill only 128 of 148 SMs, 9 per image = 288 CTAs
-    // fill 97 % of two waves)
+    // fill 97 % of two waves; batch 64: 16 per image = 1024 CTAs fill 99 % of seven)
+    const int sms = sm_count();
     int per_img = 1;
     double best_fill = 0.0;
-    for (int k = 1; k <= 3; ++k) {
-      int c = (148 * k) / n;
+    for (int k = 1; k <= 8; ++k) {
+      int c = (sms * k) / n;
       if (c < 1) c = 1;
       if (c > tiles_img) c = tiles_img;
-      const int waves = (c * n + 147) / 148;
-      const double fill = (double)(c * n) / (148.0 * waves);
+      const int waves = (c * n + sms - 1) / sms;
+      const double fill = (double)(c * n) / ((double)sms * waves);
       if (fill > best_fill + 0.02) { best_fill = fill; per_img = c; }
     }
     q.ctas_per_img = per_img;
