@@ -298,6 +298,278 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fpn_merge_f16_kernel(const FpnP
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Quad version: one epilogue lane = one 2 x 2 block of fine pixels = ONE coarse pixel's neighbourhood.
+// The 2 x 2 fine pixels (2r, 2r+1) x (2k, 2k+1) interpolate between the 3 x 3 coarse pixels (r-1..r+1) x (k-1..k+1), so a
+// lane that owns the whole block reads 9 shared-memory vectors for 4 outputs per channel instead of 16 -- the one-pixel
+// version above was bound by exactly those LDS.128 wavefronts (63 % of the shared-memory pipe, ncu).  The four pixels of
+// a block are four MMAs (sub-position (dy, dx) -> its own A tile and its own 64 TMEM columns), so a work unit is
+//   16 x 8 blocks = 32 x 16 fine pixels  x  64 output channels        (4 units per pixel tile, 2 TMEM stages of 256 columns)
+// and its coarse patch is 18 x 10 pixels x 64 channels (pixel stride 272 B: conflict-free LDS.128 across 8 lanes).
+// Horizontal interpolation is done once per coarse row and shared by the two fine rows; weights follow
+// upsample_bilinear2d(align_corners=False) on the fixed index pattern (k-1, k | k, k+1): (0.25, 0.75 | 0.75, 0.25), with
+// (0, 1) for the first fine column / row, where ATen's clamped source coordinate has weight 1 on pixel 0.
+// The 512 epilogue threads also fetch the next unit's patch (cp.async) and convert the next pixel tile's int8 levels to
+// the fp16 A tiles (one A row per thread); warp 0 only waits on barriers and issues the MMAs.
+constexpr int FQ_BW = 16, FQ_BH = 8;                              // blocks per tile
+constexpr int FQ_PW = FQ_BW + 2, FQ_PH = FQ_BH + 2;               // patch: 18 x 10 coarse pixels
+constexpr int FQ_PIX_BYTES = 64 * 4 + 16;                         // 272
+constexpr int FQ_PATCH_BYTES = FQ_PW * FQ_PH * FQ_PIX_BYTES;      // 48960
+constexpr int FQ_THREADS = FP_EW * 32;                          // 16 warps: 128 registers per thread
+constexpr int FQ_A_SUB = 128 * 128;                               // one sub-position tile: 128 blocks x 64 fp16
+
+__device__ __forceinline__ void fq_ld4(uint32_t taddr, float2& a, float2& b) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+  a = make_float2(__uint_as_float(r0), __uint_as_float(r1));
+  b = make_float2(__uint_as_float(r2), __uint_as_float(r3));
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(FQ_THREADS, 1) fpn_merge_quad_kernel(const FpnP p) {
+  extern __shared__ __align__(1024) uint8_t fp_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fp_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int b_plane = FP_COUT * 128;
+  uint8_t* sB = smem;                               // [hi | lo]                             64 KB
+  uint8_t* sA = sB + 2 * b_plane;                   // [4 sub-positions]                     64 KB
+  uint8_t* sP = sA + 4 * FQ_A_SUB;                  // [2 stages] skewed 64-channel patches  95.6 KB
+  float* s_sc = reinterpret_cast<float*>(sP + 2 * FQ_PATCH_BYTES);
+  float* s_sh = s_sc + FP_COUT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sh + FP_COUT);   // acc_full[2], prev_full[2], slot_empty[2], a_full, a_free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar0 = fp_u32(bars);
+  auto acc_full = [&](int s) { return bar0 + 8u * s; };
+  auto prev_full = [&](int s) { return bar0 + 16u + 8u * s; };
+  auto slot_empty = [&](int s) { return bar0 + 32u + 8u * s; };
+  const uint32_t a_full = bar0 + 48u, a_free = bar0 + 56u;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(acc_full(s)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(prev_full(s)), "r"(FP_EW * 32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(slot_empty(s)), "r"(FP_EW));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full), "r"(FP_EW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_free), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fp_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.bpack);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = tid; i < 2 * b_plane / 16; i += FQ_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < FP_COUT; i += FQ_THREADS) { s_sc[i] = __ldg(p.scale + i) * 0.125f; s_sh[i] = __ldg(p.shift + i) * 0.125f; }
+    uint4* za = reinterpret_cast<uint4*>(sA);       // K columns beyond Cin stay zero (never read by the MMAs, kept clean)
+    for (int i = tid; i < 4 * FQ_A_SUB / 16; i += FQ_THREADS) za[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_img = p.tiles_x * p.tiles_y;
+
+  {
+    // ------------------------------------------------------------------ every warp: loaders + epilogue; warp 0 also issues
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // MMAs of unit (g) into TMEM stage s: four sub-position tiles x (W_hi, W_lo) x K steps; one elected lane of warp 0
+    auto issue_mma = [&](int g, int s) {
+      const uint32_t b_hi = fp_u32(sB) + (uint32_t)g * 64u * 128u, b_lo = b_hi + b_plane;
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const uint32_t a0 = fp_u32(sA) + (uint32_t)sub * FQ_A_SUB;
+        const uint32_t tacc = tmem_base + (uint32_t)(s * 256 + sub * 64);
+#pragma unroll
+        for (int combo = 0; combo < 2; ++combo)
+#pragma unroll
+          for (int k = 0; k < CHUNKS; ++k)
+            fp_mma_f16(tacc, fp_desc(a0) + (uint64_t)(k * 2), fp_desc(combo ? b_lo : b_hi) + (uint64_t)(k * 2), idesc,
+                       (uint32_t)((combo | k) != 0));
+      }
+      fp_commit(acc_full(s));
+      if (g == 3) fp_commit(a_free);
+    };
+    const int ew = warp, q = warp & 3;                  // TMEM lane quadrant = warp index modulo 4
+    const int cs = warp >> 2;                           // 16-channel slice of the unit's 64
+    const int et = ew * 32 + lane;                      // 0..511
+    const int m = q * 32 + lane, by = m >> 4, bx = m & 15;
+    // ---- A rows: thread et converts row (et & 127) of sub-position (et >> 7)
+    const int a_sub = et >> 7, a_m = et & 127, a_dy = a_sub >> 1, a_dx = a_sub & 1;
+    uint4 nxt[CHUNKS];
+    auto load_a = [&](int tile) {
+      const int img = tile / tiles_img, tr = tile % tiles_img, ty = tr / p.tiles_x, tx = tr % p.tiles_x;
+      const int y = min(ty * (2 * FQ_BH) + 2 * (a_m >> 4) + a_dy, p.H - 1), x = min(tx * (2 * FQ_BW) + 2 * (a_m & 15) + a_dx, p.W - 1);
+      const uint4* src = reinterpret_cast<const uint4*>(p.a + (((int64_t)img * p.H + y) * p.W + x) * p.Cin);
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) nxt[c] = __ldg(src + c);
+    };
+    auto store_a = [&]() {
+      const uint32_t row = fp_u32(sA) + (uint32_t)a_sub * FQ_A_SUB + (uint32_t)a_m * 128u;
+      const __half2 bias = __floats2half2_rn(1024.f, 1024.f);
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const uint32_t w[4] = {nxt[c].x, nxt[c].y, nxt[c].z, nxt[c].w};
+        uint32_t h[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t lo = __byte_perm(w[i], 0x64646464u, 0x4140), hi = __byte_perm(w[i], 0x64646464u, 0x4342);
+          const __half2 hl = __hsub2(*reinterpret_cast<const __half2*>(&lo), bias);
+          const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&hi), bias);
+          h[2 * i] = *reinterpret_cast<const uint32_t*>(&hl);
+          h[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        const uint32_t c0 = (uint32_t)((2 * c) ^ (a_m & 7)) << 4, c1 = (uint32_t)((2 * c + 1) ^ (a_m & 7)) << 4;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) fp_arrive(a_full);
+    };
+    // ---- coarse patch of unit (tile, g): 180 pixels x 16 chunks of 16 bytes over 512 threads
+    auto issue_patch = [&](int tile, int g, int s) {
+      const int img = tile / tiles_img, tr = tile % tiles_img, ty = tr / p.tiles_x, tx = tr % p.tiles_x;
+      const int cy0 = ty * FQ_BH - 1, cx0 = tx * FQ_BW - 1;
+      const float* pimg = p.prev + (int64_t)img * p.Hp * p.Wp * FP_COUT + g * 64 + (et & 15) * 4;
+      const uint32_t pdst = fp_u32(sP) + (uint32_t)s * FQ_PATCH_BYTES + (uint32_t)(et & 15) * 16u;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int lp = (et >> 4) + 32 * i;
+        if (lp < FQ_PW * FQ_PH) {
+          const int gy = min(max(cy0 + lp / FQ_PW, 0), p.Hp - 1), gx = min(max(cx0 + lp % FQ_PW, 0), p.Wp - 1);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pdst + (uint32_t)lp * FQ_PIX_BYTES),
+                       "l"(pimg + ((int64_t)gy * p.Wp + gx) * FP_COUT) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(prev_full(s)) : "memory");
+    };
+    if ((int)blockIdx.x < p.tiles) {
+      load_a(blockIdx.x);
+      store_a();
+      if ((int)(blockIdx.x + gridDim.x) < p.tiles) load_a(blockIdx.x + gridDim.x);
+      issue_patch(blockIdx.x, 0, 0);
+      if (warp == 0) {
+        fp_wait(a_full, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) issue_mma(0, 0);
+        __syncwarp();
+      }
+    }
+    int it = 0, u = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const int img = tile / tiles_img, tr = tile % tiles_img, ty = tr / p.tiles_x, tx = tr % p.tiles_x;
+      const int yT = ty * (2 * FQ_BH) + 2 * by, xL = tx * (2 * FQ_BW) + 2 * bx;
+      // weights on the fixed pattern; everything vertical is carried at 1/8 scale (exact)
+      const float wL0 = xL == 0 ? 0.f : 0.25f, wL1 = xL == 0 ? 1.f : 0.75f;
+      const float wT0 = yT == 0 ? 0.f : 0.03125f, wT1 = yT == 0 ? 0.125f : 0.09375f;
+      const float wR0 = 0.75f, wR1 = 0.25f, wB0 = 0.09375f, wB1 = 0.03125f;
+      const bool okx0 = xL < p.W, okx1 = xL + 1 < p.W, oky0 = yT < p.H, oky1 = yT + 1 < p.H;
+      int8_t* dst = p.out_spike + (((int64_t)img * p.H + yT) * p.W + xL) * FP_COUT + cs * 16;
+      const int64_t row_b = (int64_t)p.W * FP_COUT;
+      for (int g = 0; g < 4; ++g, ++u) {
+        const int s = u & 1;
+        // ---- one unit ahead: the next unit's patch, (at g == 3) the next pixel tile's A rows, and its MMAs
+        {
+          const int ng = (g + 1) & 3, ntile = g == 3 ? tile + (int)gridDim.x : tile;
+          if (ntile < p.tiles) {
+            if (u >= 1) {
+              fp_wait(slot_empty(s ^ 1), (uint32_t)(((u - 1) >> 1) & 1));       // every warp is done with unit u - 1
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            issue_patch(ntile, ng, s ^ 1);
+            if (g == 3) {
+              // this tile's last MMAs were issued one unit ago: once they have completed the A tiles take the next
+              // tile's levels (already in registers), and the tile after that is requested
+              fp_wait(a_free, (uint32_t)(it & 1));
+              store_a();
+              if (tile + 2 * (int)gridDim.x < p.tiles) load_a(tile + 2 * gridDim.x);
+            }
+            if (warp == 0) {
+              if (g == 3) {
+                fp_wait(a_full, (uint32_t)((it + 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
+              if (lane == 0) issue_mma(ng, s ^ 1);
+              __syncwarp();
+            }
+          }
+        }
+        const uint32_t par = (uint32_t)((u >> 1) & 1);
+        fp_wait(acc_full(s), par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        fp_wait(prev_full(s), par);
+        // per-lane geometry re-derived from the thread index here (an opaque read): kept live across the loaders above
+        // it was spilled, and the reload queued behind the cp.asyncs in the load pipe (11 % of all stall samples)
+        uint32_t t_;
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t_));
+        const uint32_t cs_ = t_ >> 7, q_ = (t_ >> 5) & 3u, by_ = (t_ & 127u) >> 4, bx_ = t_ & 15u;
+        const uint32_t trow = tmem_base + (uint32_t)(s * 256) + cs_ * 16u + ((q_ * 32u) << 16);
+        const uint32_t pb = fp_u32(sP) + (uint32_t)s * FQ_PATCH_BYTES + (by_ * FQ_PW + bx_) * FQ_PIX_BYTES + cs_ * 64u;
+        const uint32_t sc_s = fp_u32(s_sc) + ((uint32_t)(g * 64) + cs_ * 16u) * 4u, sh_s = fp_u32(s_sh) + ((uint32_t)(g * 64) + cs_ * 16u) * 4u;
+        uint32_t pk[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 acc[4][2];
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) fq_ld4(trow + (uint32_t)(sub * 64 + j * 4), acc[sub][0], acc[sub][1]);
+          const uint32_t co = (uint32_t)(j * 4) * 4u;
+          const float4 sc4 = fp_lds128(sc_s + co), sh4 = fp_lds128(sh_s + co);
+          // horizontal interpolation of one coarse row: left / right fine column, channel pairs (0,1) and (2,3)
+          auto hrow = [&](int rr, float2 (&l)[2], float2 (&r)[2]) {
+            const uint32_t ra = pb + (uint32_t)(rr * FQ_PW) * FQ_PIX_BYTES + co;
+            const float4 c0 = fp_lds128(ra), c1 = fp_lds128(ra + FQ_PIX_BYTES), c2 = fp_lds128(ra + 2 * FQ_PIX_BYTES);
+            l[0] = __ffma2_rn(make_float2(wL1, wL1), make_float2(c1.x, c1.y), __fmul2_rn(make_float2(wL0, wL0), make_float2(c0.x, c0.y)));
+            l[1] = __ffma2_rn(make_float2(wL1, wL1), make_float2(c1.z, c1.w), __fmul2_rn(make_float2(wL0, wL0), make_float2(c0.z, c0.w)));
+            r[0] = __ffma2_rn(make_float2(wR1, wR1), make_float2(c2.x, c2.y), __fmul2_rn(make_float2(wR0, wR0), make_float2(c1.x, c1.y)));
+            r[1] = __ffma2_rn(make_float2(wR1, wR1), make_float2(c2.z, c2.w), __fmul2_rn(make_float2(wR0, wR0), make_float2(c1.z, c1.w)));
+          };
+          auto emit = [&](int sub, float w0, float w1, const float2 (&t0)[2], const float2 (&t1)[2]) {
+            const float2 ua = __ffma2_rn(make_float2(w1, w1), t1[0], __fmul2_rn(make_float2(w0, w0), t0[0]));
+            const float2 ub = __ffma2_rn(make_float2(w1, w1), t1[1], __fmul2_rn(make_float2(w0, w0), t0[1]));
+            const float2 ya = __ffma2_rn(acc[sub][0], make_float2(sc4.x, sc4.y), make_float2(sh4.x, sh4.y));
+            const float2 yb = __ffma2_rn(acc[sub][1], make_float2(sc4.z, sc4.w), make_float2(sh4.z, sh4.w));
+            pk[sub][j] = pack_unit4(fp_add_sat(ya.x, ua.x), fp_add_sat(ya.y, ua.y), fp_add_sat(yb.x, ub.x), fp_add_sat(yb.y, ub.y));
+          };
+          float2 la[2], ra_[2], lb[2], rb[2];
+          hrow(0, la, ra_);
+          hrow(1, lb, rb);
+          // the accumulator registers are operands of the wait, so that no use of them can be scheduled above it
+          asm volatile("tcgen05.wait::ld.sync.aligned;"
+                       : "+f"(acc[0][0].x), "+f"(acc[0][0].y), "+f"(acc[0][1].x), "+f"(acc[0][1].y), "+f"(acc[1][0].x), "+f"(acc[1][0].y),
+                         "+f"(acc[1][1].x), "+f"(acc[1][1].y), "+f"(acc[2][0].x), "+f"(acc[2][0].y), "+f"(acc[2][1].x), "+f"(acc[2][1].y),
+                         "+f"(acc[3][0].x), "+f"(acc[3][0].y), "+f"(acc[3][1].x), "+f"(acc[3][1].y)
+                       :: "memory");
+          emit(0, wT0, wT1, la, lb);
+          emit(1, wT0, wT1, ra_, rb);
+          hrow(2, la, ra_);                         // row 0's registers are free again
+          emit(2, wB0, wB1, lb, la);
+          emit(3, wB0, wB1, rb, ra_);
+        }
+        int8_t* d = dst + g * 64;
+        if (oky0 && okx0) *reinterpret_cast<uint4*>(d) = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
+        if (oky0 && okx1) *reinterpret_cast<uint4*>(d + FP_COUT) = make_uint4(pk[1][0], pk[1][1], pk[1][2], pk[1][3]);
+        if (oky1 && okx0) *reinterpret_cast<uint4*>(d + row_b) = make_uint4(pk[2][0], pk[2][1], pk[2][2], pk[2][3]);
+        if (oky1 && okx1) *reinterpret_cast<uint4*>(d + row_b + FP_COUT) = make_uint4(pk[3][0], pk[3][1], pk[3][2], pk[3][3]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) fp_arrive(slot_empty(s));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 }  // namespace s2f
 
 using namespace s2f;
@@ -314,6 +586,26 @@ extern "C" int s2f_fpn_merge_f16(const int8_t* a, const void* w_packed, const fl
   FpnP p;
   p.a = a; p.bpack = reinterpret_cast<const uint8_t*>(w_packed); p.scale = scale; p.shift = shift; p.prev = prev;
   p.out_spike = out_spike; p.n = n; p.H = H; p.W = W; p.Cin = Cin; p.Hp = Hp; p.Wp = Wp;
+  static const bool use_quad = []() { const char* e = getenv("S2F_FPN_QUAD"); return !(e && e[0] == '0'); }();
+  if (use_quad) {
+    p.tiles_x = (W + 2 * FQ_BW - 1) / (2 * FQ_BW); p.tiles_y = (H + 2 * FQ_BH - 1) / (2 * FQ_BH); p.tiles = n * p.tiles_x * p.tiles_y;
+    const size_t smemq = 1024 + 2 * FP_COUT * 128 + 4 * FQ_A_SUB + 2 * FQ_PATCH_BYTES + 2 * FP_COUT * sizeof(float) + 8 * 8 + 16;
+    static std::atomic<uint64_t> onceq{0};
+    if (first_use_on_this_device(onceq)) {
+      cudaFuncSetAttribute(fpn_merge_quad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemq);
+      cudaFuncSetAttribute(fpn_merge_quad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemq);
+      cudaFuncSetAttribute(fpn_merge_quad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemq);
+      cudaFuncSetAttribute(fpn_merge_quad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemq);
+    }
+    const int gridq = p.tiles < sm_count() ? p.tiles : sm_count();
+    switch (Cin >> 4) {
+      case 1: fpn_merge_quad_kernel<1><<<gridq, FQ_THREADS, smemq, (cudaStream_t)stream>>>(p); break;
+      case 2: fpn_merge_quad_kernel<2><<<gridq, FQ_THREADS, smemq, (cudaStream_t)stream>>>(p); break;
+      case 3: fpn_merge_quad_kernel<3><<<gridq, FQ_THREADS, smemq, (cudaStream_t)stream>>>(p); break;
+      default: fpn_merge_quad_kernel<4><<<gridq, FQ_THREADS, smemq, (cudaStream_t)stream>>>(p); break;
+    }
+    return check_launch("fpn_merge_quad_kernel");
+  }
   p.tiles_x = (W + FP_TW - 1) / FP_TW; p.tiles_y = (H + FP_TH - 1) / FP_TH; p.tiles = n * p.tiles_x * p.tiles_y;
   const size_t smem = 1024 + 2 * FP_COUT * 128 + 2 * FP_A_BYTES + 2 * FP_PATCH_BYTES + 2 * FP_COUT * sizeof(float) + 6 * 8 + 16;
   static std::atomic<uint64_t> once{0};
