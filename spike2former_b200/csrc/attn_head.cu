@@ -3,6 +3,10 @@
 
 namespace s2f {
 
+// attn_tc.cu: K^T V on tcgen05.mma.kind::i8 (TMA-fed, MN-major operands); the mma.sync kernel below covers unaligned operands
+bool kv_tc_eligible(const int8_t* k, const int8_t* v, int heads, int d, int kv_ld);
+int kv_tc_launch(const int8_t* k, const int8_t* v, int32_t* kv_ws, int n, int Nk, int heads, int d, int kv_ld, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // kv[img, h, i, j] = sum_tok K[img, tok, h*d+i] * V[img, tok, h*d+j]      (exact int32)
 // grid (n*heads, splits); each block reduces a token slice and atomically adds its d x d partial.
@@ -444,7 +448,9 @@ extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool fast_kv = d % 4 == 0 && kv_ld % 4 == 0 && al4(k) && al4(v);
   int rc;
-  if (fast_kv) {
+  if (kv_tc_eligible(k, v, heads, d, kv_ld)) {
+    rc = kv_tc_launch(k, v, kv_ws, n, Nk, heads, d, kv_ld, st);
+  } else if (fast_kv) {
     // token slices of >= 256 tokens; ~6 of these 4-warp blocks per SM keep enough loads in flight
     int splits = (int)ceil_div(148 * 6, (int64_t)n * heads);
     const int max_splits = (int)ceil_div(Nk, 256);
