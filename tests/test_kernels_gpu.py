@@ -269,7 +269,10 @@ def test_dwconv_spike_operands_bitwise_equal_to_fp32_operands(k, C, H, W):
 
 
 @pytest.mark.parametrize("n,Nq,Nk,heads,d", [(2, 64, 64, 4, 16), (1, 20, 300, 4, 16), (2, 100, 1024, 8, 32), (1, 64, 64, 8, 45),
-                                             (2, 1024, 1024, 8, 64), (1, 100, 4096, 8, 64)])     # d = 64: BASELINE config 2
+                                             (2, 1024, 1024, 8, 64), (1, 100, 4096, 8, 64),      # d = 64: BASELINE config 2
+                                             (2, 1024, 1024, 8, 48),       # stage 4: heads straddle the 128-channel slabs (256-wide key box)
+                                             (1, 100, 16384, 8, 32),       # batch 1: the keys are split over CTAs that add into kv
+                                             (3, 100, 100, 8, 32), (2, 33, 777, 2, 8), (1, 50, 130, 5, 48)])   # ragged token tiles, narrow / odd head counts
 def test_linear_attn_exact(n, Nq, Nk, heads, d):
     """(Q K^T) V == Q (K^T V) on integer levels; compared with the reference's op order in float64."""
     g = gen(9)
@@ -283,6 +286,33 @@ def test_linear_attn_exact(n, Nq, Nk, heads, d):
                               want_f32=True)
     assert (of.cpu().double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
     assert torch.equal(os_.cpu(), torch.round(torch.clamp(of.cpu(), 0, 8)).to(torch.int8))
+
+
+def test_linear_attn_tensor_core_kv_equals_the_mma_sync_kernel(monkeypatch):
+    """csrc/attn_tc.cu (K^T V on tcgen05, MN-major TMA operands) and the mma.sync kernel it replaces are both exact integer
+    sums: their kv workspaces and outputs must be identical bit for bit, also for column slices of a fused q|k|v buffer."""
+    import subprocess, sys, os
+    g = gen(23)
+    n, N, heads, d = 2, 640, 8, 48
+    C = heads * d
+    qkv = _levels((n, N, 3 * C), g).cuda()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    os_, of = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, out_scale=1e-4, q_ld=3 * C, kv_ld=3 * C, want_f32=True)
+    hs = lambda t: t.double().cpu().reshape(n, N, heads, d).permute(0, 2, 1, 3)
+    ref = (hs(q) @ (hs(k).transpose(-2, -1) @ hs(v))).permute(0, 2, 1, 3).reshape(n, N, C) * 1e-4
+    assert (of.cpu().double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    # the legacy kernel in a fresh process (the switch is read once per process)
+    code = ("import torch, sys; sys.path.insert(0, %r); from spike2former_b200 import ops; qkv = torch.load(sys.argv[1]).cuda();"
+            "C = %d; q, k, v = qkv[..., :C], qkv[..., C:2*C], qkv[..., 2*C:];"
+            "s, f = ops.linear_attn(q, k, v, n=%d, Nq=%d, Nk=%d, heads=%d, d=%d, out_scale=1e-4, q_ld=3*C, kv_ld=3*C, want_f32=True);"
+            "torch.save((s.cpu(), f.cpu()), sys.argv[2])") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), C, n, N, N, heads, d)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        torch.save(qkv.cpu(), os.path.join(td, "in.pt"))
+        env = dict(os.environ, S2F_ATTN_TC="0")
+        subprocess.check_call([sys.executable, "-c", code, os.path.join(td, "in.pt"), os.path.join(td, "out.pt")], env=env)
+        s_old, f_old = torch.load(os.path.join(td, "out.pt"))
+    assert torch.equal(of.cpu(), f_old) and torch.equal(os_.cpu(), s_old)
 
 
 @pytest.mark.parametrize("n,Nq,Nk,heads,d,masked", [(2, 100, 1024, 8, 32, True), (1, 37, 300, 4, 45, True), (2, 20, 64, 2, 64, True),
