@@ -35,7 +35,7 @@ extern "C" {
 /* Thread-local description of the last failure. */
 S2F_API const char* s2f_last_error(void);
 /* ABI version of the library (bumped when a signature changes). */
-S2F_API int s2f_abi_version(void);   /* currently 9 */
+S2F_API int s2f_abi_version(void);   /* currently 10 */
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 S2F_API uint64_t s2f_launch_count(void);
 
@@ -117,12 +117,16 @@ typedef struct {
   float* out_f32; int8_t* out_spike; int out_transposed;
   int n, H, W, Cin, Cout, KH, KW, stride, pad, pieces;
   float d_max;
-  int per_image_weights;   /* 1: w_packed / scale / shift hold one matrix per image (1x1, Ho*Wo % 128 == 0) */
+  int per_image_weights;   /* 1: w_packed / scale / shift hold one matrix per image (1x1, Ho*Wo % 128 == 0);
+                            * 2: w_packed per image, scale / shift shared by all images */
   /* Top-down FPN merge fused into the epilogue (pixel_decoder.py:455-462): when up_prev != NULL,
    *   y += bilinear_upsample(up_prev [n, up_H, up_W, Cout] fp32 -> [Ho, Wo], align_corners=False)[row, co]
    * is added after the affine (same arithmetic as s2f_upsample_add_lif), so lateral conv + upsample + add + NI-LIF
    * is one launch and the fp32 lateral map never reaches HBM.  Not combinable with out_transposed. */
   const float* up_prev; int up_H, up_W;
+  /* 1x1 layers: bytes between consecutive rows of A (0 = Cin), so that A may be a column slice of a wider buffer
+   * (the q block of a fused [n, N, 3C] q|k|v projection).  Multiple of 16. */
+  int64_t a_ld;
 } s2f_gemm_tc_args;
 
 S2F_API int s2f_gemm_i8_tc(const s2f_gemm_tc_args* args, void* stream);
@@ -184,11 +188,15 @@ S2F_API int s2f_sepconv_dwpw(const int8_t* a, float a_scale, const float* w_dw, 
  * With out_scale = d^-0.5 / norm^3 this is MS_Attention_RepConv_qkv_id (sdtv2.py:335-336); with
  * 1/(sqrt(C) * norm^3) it is {Cross,}MultiHeadAttentionBlock without mask, where
  * (Q K^T / sqrt(C)) V == Q (K^T V) / sqrt(C) (mmcv_spike/transformer.py:262-270, 345-353).
- * q has Nq tokens, k/v have Nk tokens.  kv_ws: int32 workspace [n, heads, d, d].
+ * q has Nq tokens, k/v have Nk tokens.  kv_ws: workspace of s2f_linear_attn_ws_bytes(n, heads, d) bytes (16-byte aligned);
+ * it starts with the int32 [n, heads, d, d] products K^T V.  On aligned operands both contractions run on tcgen05
+ * (csrc/attn_tc.cu): K^T V with MN-major operands, Q (K^T V) as a spike GEMM whose per-image weight matrix is the
+ * block-diagonal K^T V in three 7-bit digit planes (exact while Nk * 64 < 2^21).
  * out_f32 (optional) receives the pre-activation.
  * q_ld / kv_ld: elements between consecutive token rows of q and of k,v (>= heads*d), so the three
  * operands may be column slices of one fused [n, N, 3C] projection output.  out_ld: elements per output row;
  * columns [heads*d, out_ld) are written as zeros (channel padding to the 16-byte rows TMA needs). */
+S2F_API int64_t s2f_linear_attn_ws_bytes(int n, int heads, int d);
 S2F_API int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v, int32_t* kv_ws, int8_t* out_spike,
                     float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld, int out_ld,
                     float out_scale, float d_max, void* stream);

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S2F_LIB") or os.path.join(_HERE, "libs2f.so")      # S2F_LIB: experiment builds only
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class ConvArgs(C.Structure):
@@ -33,6 +33,7 @@ class GemmTcArgs(C.Structure):
         ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("pieces", C.c_int),
         ("d_max", C.c_float), ("per_image_weights", C.c_int),
         ("up_prev", C.c_void_p), ("up_H", C.c_int), ("up_W", C.c_int),
+        ("a_ld", C.c_int64),
     ]
 
 
@@ -54,6 +55,7 @@ SIGNATURES = {
     "s2f_fpn_merge_f16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "s2f_sepconv_bpack_bytes": (_L, [_I, _I]),
     "s2f_sepconv_dwpw": (_I, [_P, _F, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "s2f_linear_attn_ws_bytes": (_L, [_I, _I, _I]),
     "s2f_linear_attn": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "s2f_affine_add_lif": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "s2f_dcnv3_gather": (_I, [_P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _F, _P]),

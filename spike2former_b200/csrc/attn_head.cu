@@ -6,6 +6,11 @@ namespace s2f {
 // attn_tc.cu: K^T V on tcgen05.mma.kind::i8 (TMA-fed, MN-major operands); the mma.sync kernel below covers unaligned operands
 bool kv_tc_eligible(const int8_t* k, const int8_t* v, int heads, int d, int kv_ld);
 int kv_tc_launch(const int8_t* k, const int8_t* v, int32_t* kv_ws, int n, int Nk, int heads, int d, int kv_ld, cudaStream_t st);
+// Q (K^T V) as a per-image spike GEMM on the tcgen05 kernel of gemm_tc.cu (the workspace holds the digit planes)
+int64_t attn_ws_bytes(int n, int heads, int d);
+bool qkv_tc_eligible(const int8_t* q, int8_t* out_spike, float* out_f32, int Nq, int Nk, int heads, int d, int q_ld, int out_ld, float d_max);
+int qkv_tc_launch(const int8_t* q, int32_t* kv_ws, int8_t* out_spike, float* out_f32, int n, int Nq, int heads, int d, int q_ld,
+                  float out_scale, float d_max, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // kv[img, h, i, j] = sum_tok K[img, tok, h*d+i] * V[img, tok, h*d+j]      (exact int32)
@@ -433,6 +438,11 @@ __global__ void __launch_bounds__(256) semantic_tail_kernel(const float* __restr
 
 using namespace s2f;
 
+extern "C" int64_t s2f_linear_attn_ws_bytes(int n, int heads, int d) {
+  if (n < 1 || heads < 1 || d < 1) return -1;
+  return attn_ws_bytes(n, heads, d);
+}
+
 extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v, int32_t* kv_ws, int8_t* out_spike,
                                float* out_f32, int n, int Nq, int Nk, int heads, int d, int q_ld, int kv_ld,
                                int out_ld, float out_scale, float d_max, void* stream) {
@@ -476,6 +486,8 @@ extern "C" int s2f_linear_attn(const int8_t* q, const int8_t* k, const int8_t* v
     rc = check_launch("kv_kernel");
   }
   if (rc) return rc;
+  if (qkv_tc_eligible(q, out_spike, out_f32, Nq, Nk, heads, d, q_ld, out_ld, d_max))
+    return qkv_tc_launch(q, kv_ws, out_spike, out_f32, n, Nq, heads, d, q_ld, out_scale, d_max, st);
   const size_t sm = sizeof(int32_t) * (size_t)heads * dd;
   S2F_REQUIRE(sm <= 200 * 1024, "linear_attn: heads*d*d too large for shared memory");
   const bool fast_q = d % 4 == 0 && q_ld % 4 == 0 && out_ld % 4 == 0 && al4(q) && al16(kv_ws) && (!out_f32 || al16(out_f32)) &&

@@ -237,4 +237,79 @@ int kv_tc_launch(const int8_t* k, const int8_t* v, int32_t* kv_ws, int n, int Nk
   return check_launch("kv_tc_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Q (K^T V) as a spike GEMM with one weight matrix per image (gemm_tc.cu, per_image_weights = 2): the matrix is the
+// block-diagonal K^T V,  W[j][i] = kv[h][i - h d][j - h d]  for i, j in the same head h, 0 elsewhere.  kv is a non-negative
+// integer below 2^21 (Nk * 64), so three digits 0..127 represent it exactly; they are written straight in the kernel's
+// packed tile layout (rows (tile, plane, 64 channels), K-major, plane 0 most significant).  One thread = 16 K bytes.
+__host__ __device__ inline int kt_kpad(int C) { const int bk = C >= 128 ? 128 : (C >= 64 ? 64 : 32); return (C + bk - 1) / bk * bk; }
+
+__global__ void __launch_bounds__(256) kv_pack_kernel(const int32_t* __restrict__ kv, int8_t* __restrict__ packed, float* __restrict__ scale,
+                                                      float* __restrict__ shift, int n, int heads, int d, int kpad, int tiles_n,
+                                                      float out_scale) {
+  const int C = heads * d;
+  const int chunks = kpad >> 4;
+  const int64_t total = (int64_t)n * tiles_n * 3 * 64 * chunks;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < C) { scale[gid] = out_scale; shift[gid] = 0.f; }
+  if (gid >= total) return;
+  const int ck = (int)(gid % chunks);
+  int64_t row = gid / chunks;
+  const int r = (int)(row & 63); row >>= 6;
+  const int pl = (int)(row % 3); row /= 3;
+  const int t = (int)(row % tiles_n), img = (int)(row / tiles_n);
+  const int j = t * 64 + r;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (j < C) {
+    const int h = j / d, jj = j - h * d;
+    const int32_t* src = kv + ((int64_t)img * heads + h) * d * d + jj;
+    const int sh_ = pl == 0 ? 14 : (pl == 1 ? 7 : 0);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int ii = ck * 16 + e - h * d;
+      if (ii >= 0 && ii < d) w[e >> 2] |= (uint32_t)((__ldg(src + (int64_t)ii * d) >> sh_) & 127) << (8 * (e & 3));
+    }
+  }
+  reinterpret_cast<uint4*>(packed)[gid] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// workspace: [kv int32 n*heads*d*d][pad to 256][packed planes][scale C][shift C]
+static inline int64_t kt_align(int64_t x) { return (x + 255) & ~int64_t(255); }
+int64_t attn_ws_bytes(int n, int heads, int d) {
+  const int C = heads * d;
+  const int64_t kvb = kt_align((int64_t)n * heads * d * d * 4);
+  const int64_t pk = kt_align((int64_t)n * ((C + 63) / 64) * 192 * kt_kpad(C));
+  return kvb + pk + kt_align(2 * (int64_t)C * 4);
+}
+
+bool qkv_tc_eligible(const int8_t* q, int8_t* out_spike, float* out_f32, int Nq, int Nk, int heads, int d, int q_ld, int out_ld,
+                     float d_max) {
+  static const bool off = []() { const char* e = getenv("S2F_ATTN_TC"); return e && (e[0] == '0' || e[0] == '1'); }();   // 1: K^T V only
+  if (off) return false;
+  const int C = heads * d;
+  return Nq % 128 == 0 && C >= 32 && C % 16 == 0 && out_ld == C && q_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
+         (int64_t)Nk * 64 < (1ll << 21) && d_max == 8.f && (!out_spike || (reinterpret_cast<uintptr_t>(out_spike) & 15) == 0) &&
+         (!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0);
+}
+
+int qkv_tc_launch(const int8_t* q, int32_t* kv_ws, int8_t* out_spike, float* out_f32, int n, int Nq, int heads, int d, int q_ld,
+                  float out_scale, float d_max, cudaStream_t st) {
+  const int C = heads * d, kpad = kt_kpad(C), tiles_n = (C + 63) / 64;
+  uint8_t* base = reinterpret_cast<uint8_t*>(kv_ws);
+  int8_t* packed = reinterpret_cast<int8_t*>(base + kt_align((int64_t)n * heads * d * d * 4));
+  float* scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + kt_align((int64_t)n * tiles_n * 192 * kpad));
+  float* shift = scale + C;
+  const int64_t total = (int64_t)n * tiles_n * 192 * (kpad >> 4);
+  kv_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kv_ws, packed, scale, shift, n, heads, d, kpad, tiles_n, out_scale);
+  int rc = check_launch("kv_pack_kernel");
+  if (rc) return rc;
+  s2f_gemm_tc_args a;
+  memset(&a, 0, sizeof(a));
+  a.a = q; a.w_packed = packed; a.scale = scale; a.shift = shift; a.out_f32 = out_f32; a.out_spike = out_spike;
+  a.n = n; a.H = Nq; a.W = 1; a.Cin = C; a.Cout = C; a.KH = a.KW = 1; a.stride = 1; a.pad = 0; a.pieces = 3; a.d_max = d_max;
+  a.per_image_weights = 2; a.a_ld = q_ld;
+  return s2f_gemm_i8_tc(&a, st);
+}
+
 }  // namespace s2f

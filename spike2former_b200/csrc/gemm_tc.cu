@@ -852,6 +852,8 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   S2F_REQUIRE(a->stride == 1 || a->stride == 2, "gemm_i8_tc: stride 1 or 2");
   S2F_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0,
               "gemm_i8_tc: operands must be 16-byte aligned");
+  S2F_REQUIRE(a->a_ld == 0 || (a->KH == 1 && a->stride == 1 && a->pad == 0 && a->a_ld >= a->Cin && a->a_ld % 16 == 0 && !a->up_prev),
+              "gemm_i8_tc: a_ld needs a plain 1x1 layer and a multiple of 16 >= Cin");
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(S2F_ERR_CUDA, "gemm_i8_tc: %s", "cuTensorMapEncodeTiled entry point not found");
 
@@ -868,7 +870,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   p.taps_w = a->KW; p.taps = a->KH * a->KW; p.stride = a->stride; p.pad = a->pad;
   p.bk = tc_bk(a->Cin); p.cin_chunks = (a->Cin + p.bk - 1) / p.bk;
   p.pieces = a->pieces; p.out_transposed = a->out_transposed; p.d_max = a->d_max > 0.f ? a->d_max : 8.f;
-  const int per_img_w = a->per_image_weights ? 1 : 0;
+  const int per_img_w = a->per_image_weights;     // 1: weights + affine per image, 2: weights per image, shared affine
   p.mode_conv = (a->KH == 1 && a->stride == 1 && a->pad == 0) ? 0 : 1;
   p.staged = (p.d_max == 8.f && !a->out_transposed && a->Cout % 4 == 0 && (a->out_f32 || a->residual || a->up_prev) &&
               (!a->residual || (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0) &&
@@ -884,7 +886,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   int epi = EPI_GENERIC;
   if (up2x) epi = EPI_STAGED_UP;
   else if (p.staged) epi = EPI_STAGED;
-  else if (a->out_spike && !a->out_f32 && !a->residual && !a->up_prev && !a->out_transposed && !per_img_w && a->Cout % 16 == 0 &&
+  else if (a->out_spike && !a->out_f32 && !a->residual && !a->up_prev && !a->out_transposed && per_img_w != 1 && a->Cout % 16 == 0 &&
            p.d_max == 8.f && (reinterpret_cast<uintptr_t>(a->out_spike) & 15) == 0)
     epi = EPI_SPIKE;
   const int ew = epi == EPI_SPIKE ? EW_SPIKE : (epi == EPI_STAGED ? EW_STAGED : (epi == EPI_STAGED_UP ? EW_UP : 8));
@@ -893,7 +895,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   if (per_img_w) {
     S2F_REQUIRE(!p.mode_conv && p.M_img % TC_BM == 0, "gemm_i8_tc: per-image weights need a 1x1 layer with Ho*Wo % 128 == 0");
     p.w_img_rows = tiles_n * nB;
-    p.ss_img_stride = a->Cout;
+    p.ss_img_stride = per_img_w == 1 ? a->Cout : 0;
   }
   const int kpad = p.taps * tc_cin_pad(a->Cin);
 
@@ -916,7 +918,7 @@ extern "C" int s2f_gemm_i8_tc(const s2f_gemm_tc_args* a, void* stream) {
   } else {
     tiles_m = (p.M_total + TC_BM - 1) / TC_BM;
     cuuint64_t dims[2] = {(cuuint64_t)a->Cin, (cuuint64_t)p.M_total};
-    cuuint64_t strides[1] = {(cuuint64_t)a->Cin};
+    cuuint64_t strides[1] = {(cuuint64_t)(a->a_ld ? a->a_ld : a->Cin)};
     cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)TC_BM};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(a->a), dims, strides, box, es,

@@ -371,7 +371,7 @@ def linear_attn(q, k, v, *, n, Nq, Nk, heads, d, out_scale, q_ld=None, kv_ld=Non
         if t.dtype != torch.int8 or not t.is_cuda:
             raise S2FError(f"linear_attn: {nm} must be CUDA int8 levels")
     Cc = heads * d
-    ws = torch.empty((n, heads, d, d), dtype=torch.int32, device=q.device)
+    ws = torch.empty(int(_lib.lib().s2f_linear_attn_ws_bytes(n, heads, d)) // 4, dtype=torch.int32, device=q.device)
     out_ld = int(out_ld or Cc)
     out_s = torch.empty((n, Nq, out_ld), dtype=torch.int8, device=q.device)
     out_f = torch.empty((n, Nq, out_ld), dtype=torch.float32, device=q.device) if want_f32 else None

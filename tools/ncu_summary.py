@@ -6,6 +6,9 @@
         (one forward) so that warm-up passes do not count.
     python tools/ncu_summary.py full gpurun_out/X.ncu-rep profiles/X_full.md
         the roofline-relevant metrics of every launch in a `ncu --set full` report.
+    python tools/ncu_summary.py fullagg gpurun_out/X.ncu-rep profiles/X_full.md
+        the same report grouped per kernel (launch count, total time, DRAM traffic and GB/s, time-weighted pipe / DRAM /
+        SM utilisation, registers): one table for a whole forward captured with `--set full`.
 """
 import csv
 import io
@@ -110,9 +113,52 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def fullagg(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units, body = rd[0], rd[1], rd[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tmul = {"nsecond": 1e-9, "ns": 1e-9, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3, "ms": 1e-3}
+
+    def num(row, k):
+        try:
+            return float(row[idx[k]].replace(",", ""))
+        except Exception:  # noqa: BLE001
+            return 0.0
+
+    agg = {}
+    for row in body:
+        name = short(row[idx["Kernel Name"]])
+        t = num(row, "gpu__time_duration.sum") * tmul.get(units[idx["gpu__time_duration.sum"]], 1e-9)
+        by = num(row, "dram__bytes_read.sum") * mult.get(units[idx["dram__bytes_read.sum"]], 1) + \
+            num(row, "dram__bytes_write.sum") * mult.get(units[idx["dram__bytes_write.sum"]], 1)
+        a = agg.setdefault(name, dict(n=0, t=0.0, by=0.0, tensor=0.0, dram=0.0, sm=0.0, warps=0.0, regs=0, block=""))
+        a["n"] += 1; a["t"] += t; a["by"] += by
+        a["tensor"] += t * num(row, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+        a["dram"] += t * num(row, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+        a["sm"] += t * num(row, "sm__throughput.avg.pct_of_peak_sustained_elapsed")
+        a["warps"] += t * num(row, "sm__warps_active.avg.pct_of_peak_sustained_active")
+        a["regs"] = int(num(row, "launch__registers_per_thread")); a["block"] = row[idx["Block Size"]]
+    tot = sum(a["t"] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full, every launch of one forward, grouped per kernel ({src})\n\n")
+        f.write(f"{sum(a['n'] for a in agg.values())} launches, {tot * 1e3:.3f} ms under ncu (cold caches, serialised: compare shares). "
+                "Percentages are time-weighted means over the kernel's launches.\n\n")
+        f.write("| kernel | launches | total us | share | DRAM MB | GB/s | tensor pipe active % | DRAM thr % | SM thr % | warps active % | regs | block |\n")
+        f.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|\n")
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["t"]):
+            t = a["t"]
+            f.write(f"| `{name}` | {a['n']} | {t * 1e6:.1f} | {100 * t / tot:.1f}% | {a['by'] / 1e6:.0f} | {a['by'] / t / 1e9:.0f} | "
+                    f"{a['tensor'] / t:.1f} | {a['dram'] / t:.1f} | {a['sm'] / t:.1f} | {a['warps'] / t:.1f} | {a['regs']} | {a['block']} |\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else None)
+    elif mode == "fullagg":
+        fullagg(sys.argv[2], sys.argv[3])
     else:
         full(sys.argv[2], sys.argv[3])
