@@ -3,7 +3,8 @@
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${S2F_OUT:-$here/../libs2f.so}"
-bdir="$here/${S2F_BUILD_DIR:-build}"
+bdir="${S2F_BUILD_DIR:-build}"
+[[ "$bdir" = /* ]] || bdir="$here/$bdir"      # relative names live under csrc/, absolute paths are taken as they are
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC 
        --expt-relaxed-constexpr -Xptxas -v ${S2F_EXTRA_FLAGS:-})
@@ -16,5 +17,5 @@ for src in "$here"/*.cu; do
   fi
   objs+=("$obj")
 done
-"$NVCC" -shared -o "$out" "${objs[@]}" -lcudart_static -ldl -lpthread -lrt
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out" "${objs[@]}" -lcudart_static -ldl -lpthread -lrt
 echo "built $out"
