@@ -230,7 +230,12 @@ struct DcnGrid { float gx[25], gy[25]; };       // per sampling point: grid offs
 
 // SPLIT threads share one (pixel, group): each takes CQ of the group's channel quads (shorter dependent gather chains,
 // more warps in flight; the coordinate arithmetic is repeated, the kernel is latency-bound).
-template <int CQ, int SPLIT = 1>      // float4 channel quads per thread (Cg = 4 * CQ * SPLIT)
+__device__ __forceinline__ void ldg256(const float4* p, float (&v)[8]) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+
+template <int CQ, int SPLIT = 1, bool WIDE = false>      // float4 channel quads per thread (Cg = 4 * CQ * SPLIT)
 __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                     const int8_t* __restrict__ mask, float mask_scale,
                                                     float* __restrict__ out, int n, int H, int W, int G, int K,
@@ -289,16 +294,33 @@ __global__ void __launch_bounds__(256, S2F_DCN_MINB) dcnv3_kernel(const float* _
       const float4* p01 = reinterpret_cast<const float4*>(xb + ((int64_t)yc0 * W + xc1) * C);
       const float4* p10 = reinterpret_cast<const float4*>(xb + ((int64_t)yc1 * W + xc0) * C);
       const float4* p11 = reinterpret_cast<const float4*>(xb + ((int64_t)yc1 * W + xc1) * C);
+      if (CQ == 2 && WIDE) {
+        // 8 channels per corner in ONE 256-bit load (sm_100: LDG.E.256): half the load instructions and L1 sector
+        // look-ups of two LDG.128 that each take half of the same 32-byte sector
+        float v[4][8];
+        ldg256(p00, v[0]); ldg256(p01, v[1]); ldg256(p10, v[2]); ldg256(p11, v[3]);
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) {
-        const float4 v00 = __ldg(p00 + c), v01 = __ldg(p01 + c), v10 = __ldg(p10 + c), v11 = __ldg(p11 + c);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        s0 = fmaf(v00.x, q00, s0); s1 = fmaf(v00.y, q00, s1); s2 = fmaf(v00.z, q00, s2); s3 = fmaf(v00.w, q00, s3);
-        s0 = fmaf(v01.x, q01, s0); s1 = fmaf(v01.y, q01, s1); s2 = fmaf(v01.z, q01, s2); s3 = fmaf(v01.w, q01, s3);
-        s0 = fmaf(v10.x, q10, s0); s1 = fmaf(v10.y, q10, s1); s2 = fmaf(v10.z, q10, s2); s3 = fmaf(v10.w, q10, s3);
-        s0 = fmaf(v11.x, q11, s0); s1 = fmaf(v11.y, q11, s1); s2 = fmaf(v11.z, q11, s2); s3 = fmaf(v11.w, q11, s3);
-        acc[c][0] = fmaf(s0, m, acc[c][0]); acc[c][1] = fmaf(s1, m, acc[c][1]);
-        acc[c][2] = fmaf(s2, m, acc[c][2]); acc[c][3] = fmaf(s3, m, acc[c][3]);
+        for (int c = 0; c < 2; ++c) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          s0 = fmaf(v[0][4 * c], q00, s0); s1 = fmaf(v[0][4 * c + 1], q00, s1); s2 = fmaf(v[0][4 * c + 2], q00, s2); s3 = fmaf(v[0][4 * c + 3], q00, s3);
+          s0 = fmaf(v[1][4 * c], q01, s0); s1 = fmaf(v[1][4 * c + 1], q01, s1); s2 = fmaf(v[1][4 * c + 2], q01, s2); s3 = fmaf(v[1][4 * c + 3], q01, s3);
+          s0 = fmaf(v[2][4 * c], q10, s0); s1 = fmaf(v[2][4 * c + 1], q10, s1); s2 = fmaf(v[2][4 * c + 2], q10, s2); s3 = fmaf(v[2][4 * c + 3], q10, s3);
+          s0 = fmaf(v[3][4 * c], q11, s0); s1 = fmaf(v[3][4 * c + 1], q11, s1); s2 = fmaf(v[3][4 * c + 2], q11, s2); s3 = fmaf(v[3][4 * c + 3], q11, s3);
+          acc[c][0] = fmaf(s0, m, acc[c][0]); acc[c][1] = fmaf(s1, m, acc[c][1]);
+          acc[c][2] = fmaf(s2, m, acc[c][2]); acc[c][3] = fmaf(s3, m, acc[c][3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) {
+          const float4 v00 = __ldg(p00 + c), v01 = __ldg(p01 + c), v10 = __ldg(p10 + c), v11 = __ldg(p11 + c);
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          s0 = fmaf(v00.x, q00, s0); s1 = fmaf(v00.y, q00, s1); s2 = fmaf(v00.z, q00, s2); s3 = fmaf(v00.w, q00, s3);
+          s0 = fmaf(v01.x, q01, s0); s1 = fmaf(v01.y, q01, s1); s2 = fmaf(v01.z, q01, s2); s3 = fmaf(v01.w, q01, s3);
+          s0 = fmaf(v10.x, q10, s0); s1 = fmaf(v10.y, q10, s1); s2 = fmaf(v10.z, q10, s2); s3 = fmaf(v10.w, q10, s3);
+          s0 = fmaf(v11.x, q11, s0); s1 = fmaf(v11.y, q11, s1); s2 = fmaf(v11.z, q11, s2); s3 = fmaf(v11.w, q11, s3);
+          acc[c][0] = fmaf(s0, m, acc[c][0]); acc[c][1] = fmaf(s1, m, acc[c][1]);
+          acc[c][2] = fmaf(s2, m, acc[c][2]); acc[c][3] = fmaf(s3, m, acc[c][3]);
+        }
       }
     }
 #pragma unroll
@@ -482,6 +504,7 @@ extern "C" int s2f_dcnv3_gather(const float* x, const float* offset, const int8_
     case 1: dcnv3_kernel<1><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg); break;
     case 2:
       if (S2F_DCN_SPLIT8) dcnv3_kernel<1, 2><<<grid_for(total * 2, 256), 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg);
+      else if ((reinterpret_cast<uintptr_t>(x) & 31) == 0) dcnv3_kernel<2, 1, true><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg);
       else dcnv3_kernel<2><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg);
       break;
     case 3: dcnv3_kernel<3><<<grid, 256, 0, st>>>(x, offset, mask, mask_scale, out, n, H, W, G, K, offset_scale, dg); break;
