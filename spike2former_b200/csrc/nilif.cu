@@ -130,28 +130,32 @@ __global__ void __launch_bounds__(256, 3) nilif_vec_kernel(const float* __restri
   }
 }
 
-// Scalar kernel: any N / C / period, optional transposed store.  Used for ragged shapes only.
+// Scalar kernel: any N / C / period, optional transposed store.  Used for ragged shapes only.  IT = int when every
+// index fits 31 bits: the four divisions per element are then 32-bit (the 64-bit ones made the decoder's transposing
+// neurons on [B,100,256] cost 24 us each).
+template <typename IT>
 __global__ void __launch_bounds__(256) nilif_scalar_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
-                                                           const float* __restrict__ residual, int64_t res_period,
+                                                           const float* __restrict__ residual, int64_t res_period_,
                                                            const float* __restrict__ v_in, float* __restrict__ v_out,
                                                            int8_t* __restrict__ levels, float* __restrict__ y_norm,
-                                                           int T, int64_t N, int C, float d_max, float inv_norm,
+                                                           int T, int64_t N_, int C, float d_max, float inv_norm,
                                                            int tr_rows, int tr_cols,
                                                            unsigned long long* __restrict__ ties) {
   unsigned int my_ties = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+  const IT N = (IT)N_, res_period = (IT)res_period_;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (IT)gridDim.x * blockDim.x) {
     float v = v_in ? v_in[i] : 0.f;
     const int c = (int)(i % C);
     const float sc = scale ? scale[c] : 1.f, sh = scale ? shift[c] : 0.f;
-    int64_t o = i;
+    IT o = i;
     if (tr_rows > 0) {
-      const int64_t per = (int64_t)tr_rows * tr_cols;
-      const int64_t img = i / per, f = i % per;
+      const IT per = (IT)tr_rows * tr_cols;
+      const IT img = i / per, f = i % per;
       o = img * per + (f % tr_rows) * tr_cols + f / tr_rows;
     }
     for (int t = 0; t < T; ++t) {
-      const int64_t idx = (int64_t)t * N + i;
+      const IT idx = (IT)t * N + i;
       float u = x[idx];
       if (scale) u = __fadd_rn(__fmul_rn(u, sc), sh);
       if (residual) u += residual[res_period > 0 ? idx % res_period : idx];
@@ -159,8 +163,8 @@ __global__ void __launch_bounds__(256) nilif_scalar_kernel(const float* __restri
       if (ties) my_ties += is_tie(v, d_max) ? 1u : 0u;
       const float s = spike_level(v, d_max);
       v -= s;
-      levels[(int64_t)t * N + o] = (int8_t)(int)s;
-      if (y_norm) y_norm[(int64_t)t * N + o] = s * inv_norm;
+      levels[(IT)t * N + o] = (int8_t)(int)s;
+      if (y_norm) y_norm[(IT)t * N + o] = s * inv_norm;
     }
     if (v_out) v_out[i] = v;
   }
@@ -256,9 +260,14 @@ extern "C" int s2f_nilif_fwd(const float* x, const float* scale, const float* sh
   }
   const int64_t want = ceil_div(N, threads);
   const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
-  nilif_scalar_kernel<<<blocks, threads, 0, st>>>(x, scale, shift, residual, residual_period, v_in, v_out, levels,
-                                                  y_norm, T, N, C, d_max, inv_norm, transposed ? transpose_rows : 0,
-                                                  transposed ? transpose_cols : 0, ties);
+  if ((int64_t)T * N + (int64_t)148 * 16 * threads < (1ll << 31) && residual_period < (1ll << 31))
+    nilif_scalar_kernel<int><<<blocks, threads, 0, st>>>(x, scale, shift, residual, residual_period, v_in, v_out, levels,
+                                                         y_norm, T, N, C, d_max, inv_norm, transposed ? transpose_rows : 0,
+                                                         transposed ? transpose_cols : 0, ties);
+  else
+    nilif_scalar_kernel<int64_t><<<blocks, threads, 0, st>>>(x, scale, shift, residual, residual_period, v_in, v_out, levels,
+                                                             y_norm, T, N, C, d_max, inv_norm, transposed ? transpose_rows : 0,
+                                                             transposed ? transpose_cols : 0, ties);
   return check_launch("nilif_scalar_kernel");
 }
 
