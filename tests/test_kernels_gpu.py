@@ -301,6 +301,9 @@ def test_linear_attn_tensor_core_kv_equals_the_mma_sync_kernel(monkeypatch):
     hs = lambda t: t.double().cpu().reshape(n, N, heads, d).permute(0, 2, 1, 3)
     ref = (hs(q) @ (hs(k).transpose(-2, -1) @ hs(v))).permute(0, 2, 1, 3).reshape(n, N, C) * 1e-4
     assert (of.cpu().double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    # spikes only: the per-image spike GEMM then takes its spike-only epilogue instead of the staged fp32 one
+    os2, _ = ops.linear_attn(q, k, v, n=n, Nq=N, Nk=N, heads=heads, d=d, out_scale=1e-4, q_ld=3 * C, kv_ld=3 * C)
+    assert torch.equal(os2, os_)
     # the legacy kernel in a fresh process (the switch is read once per process)
     code = ("import torch, sys; sys.path.insert(0, %r); from spike2former_b200 import ops; qkv = torch.load(sys.argv[1]).cuda();"
             "C = %d; q, k, v = qkv[..., :C], qkv[..., C:2*C], qkv[..., 2*C:];"
